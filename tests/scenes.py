@@ -1,0 +1,57 @@
+"""Deterministic benchmark/parity scenes, expressed against the common builder
+surface shared by the CPU checkers (oracle.pyoracle.CpuPbd) and the product's host model
+(positionbaseddynamics_b200.SimulationModel facade): add_regular_triangle_model / add_regular_tet_model /
+set_mass / add_cloth_constraints / add_bending_constraints / add_solid_constraints / add_constraint /
+set_params.  Scene definitions follow Demos/ClothDemo/main.cpp:132-162 and Demos/BarDemo/main.cpp:130-166.
+"""
+import math
+import numpy as np
+
+RX90 = np.array([[1, 0, 0], [0, math.cos(math.pi / 2), -math.sin(math.pi / 2)],
+                 [0, math.sin(math.pi / 2), math.cos(math.pi / 2)]], dtype=np.float64)
+
+VOLUME = 7  # flat type code
+
+
+def cloth(m, nx, ny, cloth_method=1, bending_method=2, dist_k=1.0, bend_k=0.01, sub_steps=1, max_iter=5,
+          dt=0.005, vel_method=0, size=10.0, fem=(1.0, 1.0, 1.0, 0.3, 0.3)):
+    """ClothDemo (Demos/ClothDemo/main.cpp:132-162): nx x ny sheet, corners 0 and nx-1 pinned."""
+    m.add_regular_triangle_model(nx, ny, t=(0, 1, 0), R=RX90, scale=(size, size))
+    m.set_mass(0, 0.0)
+    m.set_mass(nx - 1, 0.0)
+    m.add_cloth_constraints(0, cloth_method, dist_k=dist_k, xx=fem[0], yy=fem[1], xy=fem[2], pxy=fem[3], pyx=fem[4])
+    m.add_bending_constraints(0, bending_method, bend_k)
+    m.set_params(dt=dt, sub_steps=sub_steps, max_iter=max_iter, vel_method=vel_method)
+
+
+def cfg1(m, n=50):
+    """cfg1: ClothDemo 50x50, Distance + IsometricBending (PBD), 1 substep x 5 iterations."""
+    cloth(m, n, n, cloth_method=1, bending_method=2, dist_k=1.0, bend_k=0.01, sub_steps=1, max_iter=5)
+
+
+def cfg2(m, n=1000, max_iter=20):
+    """cfg2: n x n cloth, Distance_XPBD (k=1e5) + IsometricBending_XPBD (k=100), 1 substep x 20 iterations."""
+    cloth(m, n, n, cloth_method=4, bending_method=3, dist_k=1.0e5, bend_k=100.0, sub_steps=1, max_iter=max_iter)
+
+
+def bar(m, w, h, d, solid_method=2, k=1.0e6, nu=0.3, vol_k=1.0, extra_volume=False, sub_steps=10, max_iter=5,
+        dt=0.005, scale=(10.0, 1.5, 1.5), norm_stretch=False):
+    """BarDemo (Demos/BarDemo/main.cpp:130-166): w x h x d regular tet bar, slab i == 0 fixed."""
+    m.add_regular_tet_model(w, h, d, t=(5, 0, 0), R=np.eye(3), scale=scale)
+    for j in range(h):
+        for kk in range(d):
+            m.set_mass(j * d + kk, 0.0)  # i == 0 slab: index i*h*d + j*d + k
+    m.add_solid_constraints(0, solid_method, k=k, nu=nu, vol_k=vol_k, norm_stretch=norm_stretch)
+    if extra_volume:
+        for t in m.tet_tets(0):
+            m.add_constraint(VOLUME, [int(v) for v in t], [vol_k])
+    m.set_params(dt=dt, sub_steps=sub_steps, max_iter=max_iter)
+
+
+def cfg3(m, w=101, h=21, d=21):
+    """cfg3: 101x21x21 bar = 200,000 tets, FEMTet (E=1e6, nu=0.3) + one Volume constraint per tet, 10 x 5."""
+    bar(m, w, h, d, solid_method=2, k=1.0e6, nu=0.3, vol_k=1.0, extra_volume=True, sub_steps=10, max_iter=5)
+
+
+def projections_per_step(num_constraints, sub_steps, max_iter):
+    return num_constraints * sub_steps * max_iter
