@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- constraint-projections/sec of the PBD/XPBD hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W   (the reference's own CPU implementation, all host threads)
+
+Workload (config.workload = "cfg2"): cloth sheet 1000x1000 particles, Distance_XPBD (k=1e5) + IsometricBending_XPBD
+(k=100), 1 substep x 20 iterations, h = 0.005 -- BASELINE.json configs[1], the configuration the metric is quoted on.
+A "step" is one TimeStepController::step over that scene; value = projections executed by all ranks / device time
+(CUDA events on the engine's stream, max over ranks), state resident in HBM.  e2e = the same metric through
+pbd_step_host: pinned host x,v in -> step -> host x out, every step, wall clock incl. the copies.
+Multi-GPU = independent scene replicas, one per rank ("replicas only"): weak scaling, no
+data-path collective; torch.distributed (NCCL) only gathers the per-rank timings.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "constraint_projections_per_sec"
+UNIT = "projections/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=1000, help="cloth is size x size particles (cfg2 = 1000)")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "launch"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_config(size, iters, n_gpus):
+    return {"workload": "cfg2", "scene": "cloth %dx%d particles, Distance_XPBD(k=1e5)+IsometricBending_XPBD(k=100)" % (size, size),
+            "sub_steps": 1, "iterations": iters, "dt": 0.005, "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus,
+            "l2": "inputs larger than L2: the per-sweep constraint stream (~192 MB at 1000x1000) exceeds the 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref when it was built, else the C restatement)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_arm(size, iters, steps, warmup):
+    import scenes
+    from oracle import pyoracle
+    if pyoracle.available("ref", "f32"):
+        kind, lib = "reference", pyoracle.CpuPbd("ref", "f32")
+    else:
+        if not pyoracle.available("oracle", "f32"):
+            pyoracle.build(ref=False)
+        kind, lib = "port", pyoracle.CpuPbd("oracle", "f32")
+    cores = os.cpu_count() or 1
+    lib.set_threads(cores)
+    scenes.cfg2(lib, size, iters)
+    ncons = lib.num_constraints()
+    lib.init_groups()
+    if warmup:
+        lib.step(warmup)
+    secs = lib.step(steps)
+    proj = ncons * 1 * iters * steps
+    return {"value": proj / secs, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": 1e3 * secs / steps,
+            "sample": "%d step(s) of the %dx%d cloth (%d constraints x %d iterations) after %d warm-up, fp32 build, OMP threads=%d"
+                      % (steps, size, size, ncons, iters, warmup, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs and prints the reference arm
+    size = args.size
+    # bound the run to a few minutes: a 1000x1000 step costs ~2.5 s on 8 cores; shrink the sample for long runs
+    budget_steps = args.steps + args.warmup
+    if budget_steps > 40:
+        size = max(200, int(args.size * (40.0 / budget_steps) ** 0.5))
+    r = cpu_arm(size, args.iters, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(size, args.iters, args.gpus),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index; self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import scenes
+    from positionbaseddynamics_b200 import _capi
+    from positionbaseddynamics_b200.model import HostModel
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(args.gpus, 1) and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- scene (host model mirror, C++) -> engine -----------------------------------------------------------------
+    t0 = time.time()
+    hm = HostModel()
+    scenes.cfg2(hm, args.size, args.iters)
+    types, bodies, params, _ = hm.constraints()
+    off, ids = hm.groups()
+    n = hm.num_particles(); ncons = len(types)
+    x0 = hm.get("x0"); mass, _ = hm.masses()
+    build_s = time.time() - t0
+    eng = _capi.Engine(local)
+    eng.set_particles(x0, mass)
+    eng.add_flat(types, bodies, params)
+    eng.set_groups(off, ids)
+    eng.set_params(dt=0.005, sub_steps=1, max_iter=args.iters)
+    del types, bodies, params
+    hm.close()
+
+    modes = {"graph": _capi.MODE_GRAPH, "persistent": _capi.MODE_PERSISTENT, "launch": _capi.MODE_LAUNCH}
+    proj_per_step = ncons * 1 * args.iters
+
+    def timed(mode, steps, warmup):
+        eng.set_mode(mode)
+        eng.step(warmup); eng.sync()
+        l0 = eng.stats().kernel_launches
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.step(steps); eng.sync()
+        torch.cuda.synchronize()
+        st = eng.stats()
+        return st.last_step_ms, st.kernel_launches - l0
+
+    # pick the execution mode on a short probe unless forced
+    if args.mode == "auto":
+        probe = {}
+        for name in ("graph", "persistent"):
+            try:
+                ms, _ = timed(modes[name], 3, 2)
+                probe[name] = ms
+            except Exception as ex:  # e.g. cooperative launch unsupported
+                probe[name] = float("inf"); sys.stderr.write("mode %s failed: %s\n" % (name, ex))
+        mode_name = min(probe, key=probe.get)
+    else:
+        mode_name = args.mode
+        probe = {}
+    mode = modes[mode_name]
+
+    # ---- timed region: K steps, state resident in HBM ---------------------------------------------------------------
+    sampler = ClockSampler(local if world == 1 else local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(mode, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        gathered = [torch.zeros_like(ms_t) for _ in range(world)]
+        dist.all_gather(gathered, ms_t)
+        ms_max = max(float(g.item()) for g in gathered)
+    else:
+        ms_max = ms
+    value = world * proj_per_step * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: pinned host buffers in and out every step ---------------------------------------------------------------
+    xh = torch.empty((n, 3), dtype=torch.float32, pin_memory=True); vh = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+    xo = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+    xh.numpy()[:] = eng.get_attr(_capi.ATTR_X); vh.numpy()[:] = eng.get_attr(_capi.ATTR_V)
+    e2e_steps = args.steps
+    for _ in range(2):
+        eng.step_host(1, xh.numpy(), vh.numpy(), xo.numpy())
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.step_host(1, xh.numpy(), vh.numpy(), xo.numpy())  # synchronises: result is in host memory on return
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        gathered = [torch.zeros_like(e2e_t) for _ in range(world)]
+        dist.all_gather(gathered, e2e_t)
+        e2e_max = max(float(g.item()) for g in gathered)
+    else:
+        e2e_max = e2e_s
+    e2e_value = world * proj_per_step * e2e_steps / e2e_max
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    st = eng.stats()
+    if mode_name == "persistent":
+        eng.set_mode(mode); eng.step(3); eng.sync()
+        eng.step(5); eng.sync()
+        k_ms = eng.stats().last_step_ms / 5.0
+        k_bytes = st.bytes_per_step
+        roof = {"kernel": "k_step_persistent (whole step, one cooperative launch)", "bytes_per_launch": k_bytes, "ms_per_launch": k_ms}
+    else:
+        eng.set_mode(_capi.MODE_LAUNCH)
+        eng.step(2); eng.sync()
+        tms = np.zeros(_capi.NUM_TYPES); tl = np.zeros(_capi.NUM_TYPES)
+        reps = 3
+        for _ in range(reps):
+            ms_t_, mi, mv, l_ = eng.profile_step()
+            tms += ms_t_; tl += l_
+        dom = int(np.argmax(tms))
+        per_proj = {_capi.DISTANCE_XPBD: 84.0, _capi.ISOBENDING_XPBD: 168.0}.get(dom)
+        cnt = st.constraints_per_type[dom]
+        k_ms = float(tms[dom] / max(tl[dom], 1))
+        k_bytes = float(cnt * per_proj * args.iters * reps / max(tl[dom], 1)) if per_proj else None
+        roof = {"kernel": "k_project<%s>" % _capi.TYPE_NAMES[dom], "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
+                "share_of_step": float(tms[dom] / max(tms.sum() + mi + mv, 1e-9))}
+        eng.set_mode(mode)
+    achieved = (roof["bytes_per_launch"] / (roof["ms_per_launch"] * 1e-3)) / 1e9 if roof["bytes_per_launch"] else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_source": peak_src, **roof,
+                "step_achieved_gbs": st.bytes_per_step / (ms_max / args.steps * 1e-3) / 1e9,
+                "note": "algorithmic bytes per SURVEY.md 8d / DESIGN.md; particle float4s are L2-resident (16 MB), so frac can exceed 1"}
+
+    # ---- CPU baseline (rank 0, N=1 only, bounded sample) ----------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_arm(args.size, args.iters, args.cpu_steps, 1)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % ex}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(workload_config(args.size, args.iters, world), mode=mode_name, particles=n, constraints=ncons,
+                                                 colour_groups=int(st.num_groups), buckets=int(st.num_buckets), scene_build_s=round(build_s, 2)),
+            "sim_steps_per_sec": world * args.steps / (ms_max * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 12, "d2h_bytes_per_step": n * 12,
+                    "ms_per_step": 1e3 * e2e_max / e2e_steps, "api": "pbd_step_host (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mode_probe_ms": probe}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,119 @@
+/* include/pbd_b200.h -- C ABI of the B200-native PBD/XPBD constraint-projection engine (libpbd_b200.so).
+ *
+ * Drop-in seam: this is what a `PBD::TimeStep` subclass on the reference side binds to replace
+ * `TimeStepController::step` (Simulation/TimeStepController.cpp:75-241; seam: Simulation/TimeStep.h:13-48,
+ * installed via Simulation::setTimeStep, Simulation/Simulation.h:48-49).  The reference-side adapter that
+ * flattens a `PBD::SimulationModel` into these calls is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success, non-zero on error
+ * (the reference's own convention is bool/void with no exceptions, Simulation/SimulationModel.cpp:565-575);
+ * pbd_last_error() returns the message of the last failure on the calling thread.  Nothing throws across
+ * this boundary.  One engine <-> one CUDA device + one stream; engines are independent.
+ * There is NO CPU fallback: without a CUDA device every entry point that needs one fails.
+ */
+#ifndef PBD_B200_H
+#define PBD_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbd_engine pbd_engine;
+
+/* Flat constraint types and their per-constraint parameter layout (floats, in this order).  The layout is the
+ * reference's own member set per constraint class (Simulation/Constraints.h:255-457), matrices row-major.
+ *  type                     bodies  params                                                   reference class
+ *  PBD_DISTANCE             2       restLength, stiffness                                    DistanceConstraint           Constraints.cpp:1166-1206
+ *  PBD_DISTANCE_XPBD        2       restLength, stiffness                         (+lambda)  DistanceConstraint_XPBD      Constraints.cpp:1211-1258
+ *  PBD_DIHEDRAL             4       restAngle, stiffness                                     DihedralConstraint           Constraints.cpp:1264-1339
+ *  PBD_ISOBENDING           4       stiffness, Q[16]                                         IsometricBendingConstraint   Constraints.cpp:1345-1402
+ *  PBD_ISOBENDING_XPBD      4       stiffness, Q[16]                              (+lambda)  IsometricBendingConstraint_XPBD :1407-1471
+ *  PBD_FEMTRIANGLE          3       area, invRestMat[4], Exx, Eyy, Exy, nu_xy, nu_yx         FEMTriangleConstraint        Constraints.cpp:1476-1538
+ *  PBD_STRAINTRIANGLE       3       invRestMat[4], kxx, kyy, kxy, normStretch, normShear     StrainTriangleConstraint     Constraints.cpp:1544-1610
+ *  PBD_VOLUME               4       restVolume, stiffness                                    VolumeConstraint             Constraints.cpp:1617-1677
+ *  PBD_VOLUME_XPBD          4       restVolume, stiffness                         (+lambda)  VolumeConstraint_XPBD        Constraints.cpp:1683-1750
+ *  PBD_FEMTET               4       volume, invRestMat[9], E, nu                             FEMTetConstraint             Constraints.cpp:1755-1825
+ *  PBD_FEMTET_XPBD          4       volume, invRestMat[9], E, nu                  (+lambda)  XPBD_FEMTetConstraint        Constraints.cpp:1830-1906
+ *  PBD_STRAINTET            4       invRestMat[9], stretchK, shearK, normStretch, normShear  StrainTetConstraint          Constraints.cpp:1912-1980
+ */
+enum pbd_constraint_type {
+    PBD_DISTANCE = 0, PBD_DISTANCE_XPBD = 1, PBD_DIHEDRAL = 2, PBD_ISOBENDING = 3, PBD_ISOBENDING_XPBD = 4,
+    PBD_FEMTRIANGLE = 5, PBD_STRAINTRIANGLE = 6, PBD_VOLUME = 7, PBD_VOLUME_XPBD = 8, PBD_FEMTET = 9,
+    PBD_FEMTET_XPBD = 10, PBD_STRAINTET = 11, PBD_NUM_TYPES = 12
+};
+
+/* particle attributes (ParticleData, Simulation/ParticleData.h:91-100); host layout = packed 3 floats per particle,
+ * exactly `std::vector<Vector3r>::data()` of the reference's fp32 build. */
+enum pbd_attr { PBD_ATTR_X = 0, PBD_ATTR_V = 1, PBD_ATTR_X0 = 2, PBD_ATTR_OLDX = 3, PBD_ATTR_LASTX = 4 };
+
+enum pbd_solver_mode {
+    PBD_MODE_GRAPH = 0,      /* one kernel per (colour,type) bucket, whole step replayed as a CUDA graph */
+    PBD_MODE_PERSISTENT = 1, /* one cooperative kernel per step; grid-wide barrier between colours */
+    PBD_MODE_LAUNCH = 2      /* plain stream launches (debug / per-kernel profiling) */
+};
+
+typedef struct pbd_stats {
+    unsigned long long projections;    /* solvePositionConstraint calls executed so far (reference counting: early-outs included) */
+    unsigned long long kernel_launches; /* kernels (or graph kernel nodes) launched by pbd_step so far */
+    unsigned long long steps;          /* TimeStepController::step equivalents executed */
+    unsigned num_particles, num_constraints, num_groups, num_buckets;
+    unsigned constraints_per_type[PBD_NUM_TYPES];
+    double bytes_per_step;             /* algorithmic bytes of one step */
+    float last_step_ms;                /* device time of the last pbd_step call (CUDA events on the engine stream), after pbd_sync */
+} pbd_stats;
+
+const char *pbd_last_error(void);
+int pbd_device_count(int *count);
+
+/* stream: a cudaStream_t owned by the caller (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let the
+ * engine create its own non-blocking stream. */
+int pbd_create(int device, void *stream, pbd_engine **out);
+int pbd_destroy(pbd_engine *e);
+
+/* ParticleData upload.  mass: n floats (invMass derived as ParticleData::setMass does, ParticleData.h:239-246).
+ * x0/v may be NULL (x0 = x, v = 0); oldX = lastX = x as ParticleData::addVertex does (ParticleData.h:127-137). */
+int pbd_set_particles(pbd_engine *e, unsigned n, const float *x, const float *x0, const float *v, const float *mass);
+int pbd_set_attr(pbd_engine *e, int attr, const float *src);  /* host -> device, n*3 floats */
+int pbd_get_attr(pbd_engine *e, int attr, float *dst);        /* device -> host, n*3 floats; synchronises */
+int pbd_set_masses(pbd_engine *e, const float *mass);
+
+/* Constraints.  `bodies`: count*numBodies(type) particle indices; `params`: count*numParams(type) floats in the
+ * layout above; `ids`: the constraint's index in the reference's SimulationModel::m_constraints (insertion order),
+ * or NULL for "append after everything added so far".  Insertion order defines colouring and hence the result. */
+int pbd_clear_constraints(pbd_engine *e);
+int pbd_add_constraints(pbd_engine *e, int type, unsigned count, const unsigned *bodies, const float *params,
+                        const unsigned *ids);
+int pbd_num_bodies(int type);
+int pbd_num_params(int type);
+
+/* Colour groups: either import the reference's SimulationModel::m_constraintGroups (offsets[nGroups+1], ids by
+ * insertion index) or recompute them with the reference's greedy first-fit (SimulationModel.cpp:1033-1094). */
+int pbd_set_groups(pbd_engine *e, unsigned nGroups, const unsigned *offsets, const unsigned *ids);
+int pbd_color_first_fit(pbd_engine *e);
+int pbd_get_num_groups(pbd_engine *e, unsigned *nGroups);
+int pbd_get_groups(pbd_engine *e, unsigned *offsets, unsigned *ids);
+
+/* TimeStepController knobs (NUM_SUB_STEPS, MAX_ITERATIONS, VELOCITY_UPDATE_METHOD: TimeStepController.cpp:47-72),
+ * TimeManager step size (TimeManager.h:26-27) and Simulation::GRAVITATION (Simulation.cpp:63). */
+int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsigned maxIter, int velocityUpdateMethod,
+                   const float gravity[3]);
+int pbd_set_mode(pbd_engine *e, int mode);
+/* sort constraints inside each (colour,type) bucket by their lowest particle index (order inside a colour is free). */
+int pbd_set_bucket_sort(pbd_engine *e, int enable);
+
+/* nSteps x TimeStepController::step, asynchronous on the engine's stream. */
+int pbd_step(pbd_engine *e, unsigned nSteps);
+int pbd_sync(pbd_engine *e);
+/* End-to-end convenience used by host-buffer callers: upload x and v (3 floats/particle each, pinned or pageable),
+ * run nSteps, download x (and v if v_out != NULL), synchronise. */
+int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out);
+
+int pbd_get_lambdas(pbd_engine *e, int type, float *dst, unsigned *ids); /* debug: per-type XPBD multipliers + insertion ids */
+int pbd_get_stats(pbd_engine *e, pbd_stats *out);
+/* per-type device time of one profiled step (plain launches bracketed by CUDA events; ms per type + prologue/epilogue) */
+int pbd_profile_step(pbd_engine *e, float *ms_per_type /*PBD_NUM_TYPES*/, float *ms_integrate, float *ms_velocity,
+                     unsigned *launches_per_type /*PBD_NUM_TYPES*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

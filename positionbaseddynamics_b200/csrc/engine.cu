@@ -1,0 +1,832 @@
+// positionbaseddynamics_b200/csrc/engine.cu
+//
+// Host side of the B200 PBD/XPBD engine behind the C ABI of include/pbd_b200.h:
+//   * flattening of a constraint list + the reference's colour groups into (colour,type) buckets of SoA arrays,
+//   * the step driver that replaces TimeStepController::step (Simulation/TimeStepController.cpp:75-241) for
+//     particle constraints: per substep  integrate -> maxIterations x (colour by colour, bucket by bucket) -> velocity update,
+//     executed as plain launches, as a replayed CUDA graph, or as one persistent cooperative kernel.
+// There is no CPU fallback: every path that computes needs the CUDA device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+#include "kernels.cuh"
+#include "persistent.cuh"
+#include "host/pbd_model.h"
+
+using namespace pbdk;
+
+// ------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKE(e) do { int r_ = (e); if (r_) return r_; } while (0)
+
+extern "C" const char *pbd_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------------------
+// engine state
+// ------------------------------------------------------------------------------------------------------------
+struct HostType {                 // constraints of one type as handed in through pbd_add_constraints
+    std::vector<unsigned> ids;    // insertion index in the reference's m_constraints
+    std::vector<unsigned> bodies; // nBodies per constraint
+    std::vector<float> params;    // nParams per constraint (reference layout)
+};
+
+struct DevBuf {
+    void *p = nullptr; size_t bytes = 0;
+    int alloc(size_t b) {
+        if (b <= bytes && p) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (b == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu) -> %s", b, cudaGetErrorString(e));
+        bytes = b;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct DevType {
+    DevBuf idx[3], gv[kMaxGeoV], gs[kMaxGeoS], mat[kMaxMat], lambda;
+    std::vector<unsigned> order;  // position in the device arrays -> insertion id
+    unsigned count = 0;
+    TypeArrays arrays{};
+};
+
+struct pbd_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownsStream = false;
+    int smCount = 148;
+    // particles
+    unsigned n = 0;
+    DevBuf pos, vel, oldp, lastp, pos0, stage, massStage;
+    float *pinned = nullptr; size_t pinnedBytes = 0;
+    // constraints (host copy, insertion order) and groups
+    HostType host[PBD_NUM_TYPES];
+    unsigned numConstraints = 0;
+    std::vector<unsigned> groupOff, groupIds;
+    bool groupsSet = false;
+    // device image
+    DevType dev[PBD_NUM_TYPES];
+    std::vector<Bucket> buckets;
+    DevBuf dBuckets, dTypeArrays, dBarrier;
+    bool imageDirty = true;
+    bool sortBuckets = true;
+    // parameters
+    float dt = 0.005f; unsigned subSteps = 5, maxIter = 1; int velMethod = 0; float g[3] = {0.f, -9.81f, 0.f};
+    int mode = PBD_MODE_GRAPH;
+    // graph cache
+    cudaGraphExec_t graphExec = nullptr;
+    bool graphValid = false;
+    // stats
+    pbd_stats stats{};
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool timingPending = false;
+    int persistentBlocksPerSM = 0;
+    unsigned coloursUsed = 0;             // colours that own at least one bucket
+    unsigned long long barrierBase = 0;   // value of the grid-barrier counter when the next persistent launch starts
+};
+
+static int use(pbd_engine *e) { CK(cudaSetDevice(e->device)); return 0; }
+
+extern "C" int pbd_device_count(int *count) {
+    cudaError_t err = cudaGetDeviceCount(count);
+    if (err != cudaSuccess) { *count = 0; return fail("cudaGetDeviceCount -> %s", cudaGetErrorString(err)); }
+    return 0;
+}
+extern "C" int pbd_num_bodies(int type) { return type_shape(type).nBodies; }
+extern "C" int pbd_num_params(int type) { return type_shape(type).nParams; }
+
+extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
+    if (!out) return fail("pbd_create: out == NULL");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail("pbd_create: no CUDA device available (%s); this engine has no CPU fallback",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+    if (device < 0 || device >= count) return fail("pbd_create: device %d out of range [0,%d)", device, count);
+    pbd_engine *e = new pbd_engine();
+    e->device = device;
+    if (use(e)) { delete e; return 1; }
+    cudaDeviceProp prop;
+    err = cudaGetDeviceProperties(&prop, device);
+    if (err != cudaSuccess) { delete e; return fail("cudaGetDeviceProperties -> %s", cudaGetErrorString(err)); }
+    e->smCount = prop.multiProcessorCount;
+    if (stream) { e->stream = (cudaStream_t)stream; e->ownsStream = false; }
+    else {
+        err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (err != cudaSuccess) { delete e; return fail("cudaStreamCreate -> %s", cudaGetErrorString(err)); }
+        e->ownsStream = true;
+    }
+    cudaEventCreate(&e->evStart); cudaEventCreate(&e->evStop);
+    *out = e;
+    return 0;
+}
+
+static void drop_graph(pbd_engine *e) {
+    if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
+    e->graphValid = false;
+}
+
+extern "C" int pbd_destroy(pbd_engine *e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    drop_graph(e);
+    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->massStage, &e->dBuckets, &e->dTypeArrays, &e->dBarrier}) b->release();
+    for (auto &d : e->dev) {
+        for (auto &b : d.idx) b.release();
+        for (auto &b : d.gv) b.release();
+        for (auto &b : d.gs) b.release();
+        for (auto &b : d.mat) b.release();
+        d.lambda.release();
+    }
+    if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->evStart) cudaEventDestroy(e->evStart);
+    if (e->evStop) cudaEventDestroy(e->evStop);
+    if (e->ownsStream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// particles
+// ------------------------------------------------------------------------------------------------------------
+static inline unsigned nblk(unsigned n, unsigned t) { return (n + t - 1) / t; }
+
+static float4 *attr_buf(pbd_engine *e, int attr) {
+    switch (attr) {
+    case PBD_ATTR_X: return (float4 *)e->pos.p;
+    case PBD_ATTR_V: return (float4 *)e->vel.p;
+    case PBD_ATTR_X0: return (float4 *)e->pos0.p;
+    case PBD_ATTR_OLDX: return (float4 *)e->oldp.p;
+    case PBD_ATTR_LASTX: return (float4 *)e->lastp.p;
+    default: return nullptr;
+    }
+}
+
+// host AoS-3 -> staging -> float4 (keeps .w)
+static int upload3(pbd_engine *e, const float *src, float4 *dst, int keepW) {
+    const size_t bytes = (size_t)e->n * 3 * sizeof(float);
+    CK(cudaMemcpyAsync(e->stage.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, dst, e->n, keepW);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pbd_set_masses(pbd_engine *e, const float *mass) {
+    if (!e || !mass) return fail("pbd_set_masses: null argument");
+    CKE(use(e));
+    if (e->n == 0) return 0;
+    CK(cudaMemcpyAsync(e->massStage.p, mass, (size_t)e->n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    k_set_w<<<nblk(e->n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (const float *)e->massStage.p, e->n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));  // staging buffers are reused by the next call
+    return 0;
+}
+
+extern "C" int pbd_set_particles(pbd_engine *e, unsigned n, const float *x, const float *x0, const float *v, const float *mass) {
+    if (!e || (n && (!x || !mass))) return fail("pbd_set_particles: null argument");
+    CKE(use(e));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n != e->n) { e->imageDirty = true; drop_graph(e); }
+    e->n = n;
+    const size_t b4 = (size_t)n * sizeof(float4);
+    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0}) CKE(b->alloc(b4));
+    CKE(e->stage.alloc((size_t)n * 3 * sizeof(float)));
+    CKE(e->massStage.alloc((size_t)n * sizeof(float)));
+    drop_graph(e);  // buffers may have moved
+    if (n == 0) return 0;
+    CK(cudaMemsetAsync(e->vel.p, 0, b4, e->stream));
+    CKE(upload3(e, x, (float4 *)e->pos.p, 0)); CK(cudaStreamSynchronize(e->stream));
+    if (v) { CKE(upload3(e, v, (float4 *)e->vel.p, 0)); CK(cudaStreamSynchronize(e->stream)); }
+    CKE(pbd_set_masses(e, mass));
+    // oldX = lastX = x, x0 = x unless given (ParticleData::addVertex, ParticleData.h:127-137)
+    CK(cudaMemcpyAsync(e->oldp.p, e->pos.p, b4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->lastp.p, e->pos.p, b4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->pos0.p, e->pos.p, b4, cudaMemcpyDeviceToDevice, e->stream));
+    if (x0) { CKE(upload3(e, x0, (float4 *)e->pos0.p, 1)); }
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.num_particles = n;
+    return 0;
+}
+
+extern "C" int pbd_set_attr(pbd_engine *e, int attr, const float *src) {
+    if (!e || !src) return fail("pbd_set_attr: null argument");
+    CKE(use(e));
+    float4 *dst = attr_buf(e, attr);
+    if (!dst) return fail("pbd_set_attr: bad attribute %d", attr);
+    if (e->n == 0) return 0;
+    CKE(upload3(e, src, dst, 1));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int pbd_get_attr(pbd_engine *e, int attr, float *dst) {
+    if (!e || !dst) return fail("pbd_get_attr: null argument");
+    CKE(use(e));
+    const float4 *src = attr_buf(e, attr);
+    if (!src) return fail("pbd_get_attr: bad attribute %d", attr);
+    if (e->n == 0) return 0;
+    k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>(src, (float *)e->stage.p, e->n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, e->stage.p, (size_t)e->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// constraints and groups
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int pbd_clear_constraints(pbd_engine *e) {
+    if (!e) return fail("null engine");
+    for (auto &h : e->host) { h.ids.clear(); h.bodies.clear(); h.params.clear(); }
+    e->numConstraints = 0;
+    e->groupOff.clear(); e->groupIds.clear(); e->groupsSet = false;
+    e->imageDirty = true;
+    return 0;
+}
+
+extern "C" int pbd_add_constraints(pbd_engine *e, int type, unsigned count, const unsigned *bodies, const float *params, const unsigned *ids) {
+    if (!e) return fail("null engine");
+    if (type < 0 || type >= PBD_NUM_TYPES) return fail("pbd_add_constraints: unknown constraint type %d", type);
+    if (count && (!bodies || !params)) return fail("pbd_add_constraints: null arrays");
+    const TypeShape s = type_shape(type);
+    for (size_t i = 0; i < (size_t)count * s.nBodies; i++)
+        if (bodies[i] >= e->n) return fail("pbd_add_constraints: particle index %u out of range (n=%u)", bodies[i], e->n);
+    HostType &h = e->host[type];
+    for (unsigned i = 0; i < count; i++) h.ids.push_back(ids ? ids[i] : e->numConstraints + i);
+    h.bodies.insert(h.bodies.end(), bodies, bodies + (size_t)count * s.nBodies);
+    h.params.insert(h.params.end(), params, params + (size_t)count * s.nParams);
+    e->numConstraints += count;
+    e->groupsSet = false;  // any add invalidates the groups (SimulationModel: m_groupsInitialized = false)
+    e->imageDirty = true;
+    return 0;
+}
+
+// insertion id -> (type, local index); verifies that the ids form a permutation of 0..N-1
+static int build_id_map(pbd_engine *e, std::vector<std::pair<int, unsigned>> &map) {
+    const unsigned N = e->numConstraints;
+    map.assign(N, std::make_pair(-1, 0u));
+    for (int t = 0; t < PBD_NUM_TYPES; t++) {
+        const HostType &h = e->host[t];
+        for (unsigned i = 0; i < h.ids.size(); i++) {
+            const unsigned id = h.ids[i];
+            if (id >= N) return fail("constraint id %u out of range (N=%u)", id, N);
+            if (map[id].first != -1) return fail("constraint id %u used twice", id);
+            map[id] = std::make_pair(t, i);
+        }
+    }
+    return 0;
+}
+
+extern "C" int pbd_set_groups(pbd_engine *e, unsigned nGroups, const unsigned *offsets, const unsigned *ids) {
+    if (!e || (nGroups && (!offsets || !ids))) return fail("pbd_set_groups: null argument");
+    const unsigned N = e->numConstraints;
+    if (nGroups == 0 && N != 0) return fail("pbd_set_groups: %u constraints but no groups", N);
+    if (nGroups && offsets[nGroups] != N) return fail("pbd_set_groups: groups cover %u constraints, model has %u", offsets[nGroups], N);
+    std::vector<unsigned char> seen(N, 0);
+    for (unsigned i = 0; i < N; i++) {
+        if (ids[i] >= N || seen[ids[i]]) return fail("pbd_set_groups: ids are not a permutation of 0..%u", N);
+        seen[ids[i]] = 1;
+    }
+    e->groupOff.assign(offsets, offsets + nGroups + 1);
+    e->groupIds.assign(ids, ids + N);
+    if (nGroups == 0) e->groupOff.assign(1, 0u);
+    e->groupsSet = true;
+    e->imageDirty = true;
+    return 0;
+}
+
+// Greedy first fit in insertion order == SimulationModel::initConstraintGroups (Simulation/SimulationModel.cpp:1033-1094);
+// the colouring itself is host/pbd_model.cpp:firstFitColouring (shared with the host model mirror).
+extern "C" int pbd_color_first_fit(pbd_engine *e) {
+    if (!e) return fail("null engine");
+    std::vector<std::pair<int, unsigned>> map;
+    CKE(build_id_map(e, map));
+    const unsigned N = e->numConstraints;
+    std::vector<unsigned> off(N + 1, 0), bodies;
+    bodies.reserve((size_t)N * 4);
+    for (unsigned id = 0; id < N; id++) {
+        const int t = map[id].first;
+        const int nb = type_shape(t).nBodies;
+        const unsigned *b = &e->host[t].bodies[(size_t)map[id].second * nb];
+        bodies.insert(bodies.end(), b, b + nb);
+        off[id + 1] = (unsigned)bodies.size();
+    }
+    std::vector<unsigned> colour;
+    const unsigned nColours = pbd_b200::firstFitColouring(e->n, N, off.data(), bodies.data(), colour);
+    std::vector<unsigned> goff(nColours + 1, 0);
+    for (unsigned id = 0; id < N; id++) goff[colour[id] + 1]++;
+    for (unsigned c = 0; c < nColours; c++) goff[c + 1] += goff[c];
+    std::vector<unsigned> cur(goff.begin(), goff.end() - 1), ids(N);
+    for (unsigned id = 0; id < N; id++) ids[cur[colour[id]]++] = id;
+    e->groupOff = goff; e->groupIds = ids;
+    e->groupsSet = true; e->imageDirty = true;
+    return 0;
+}
+
+extern "C" int pbd_get_num_groups(pbd_engine *e, unsigned *nGroups) {
+    if (!e || !nGroups) return fail("null argument");
+    if (!e->groupsSet) return fail("groups not initialised (call pbd_set_groups or pbd_color_first_fit)");
+    *nGroups = (unsigned)e->groupOff.size() - 1;
+    return 0;
+}
+extern "C" int pbd_get_groups(pbd_engine *e, unsigned *offsets, unsigned *ids) {
+    if (!e || !offsets || !ids) return fail("null argument");
+    if (!e->groupsSet) return fail("groups not initialised");
+    memcpy(offsets, e->groupOff.data(), e->groupOff.size() * sizeof(unsigned));
+    memcpy(ids, e->groupIds.data(), e->groupIds.size() * sizeof(unsigned));
+    return 0;
+}
+
+extern "C" int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsigned maxIter, int velMethod, const float gravity[3]) {
+    if (!e) return fail("null engine");
+    if (subSteps < 1) return fail("subSteps must be >= 1 (TimeStepController.cpp:50)");
+    if (maxIter < 1) return fail("maxIterations must be >= 1 (TimeStepController.cpp:55)");
+    if (velMethod != 0 && velMethod != 1) return fail("velocityUpdateMethod must be 0 or 1");
+    if (!(dt > 0.0f)) return fail("time step size must be positive");
+    e->dt = dt; e->subSteps = subSteps; e->maxIter = maxIter; e->velMethod = velMethod;
+    if (gravity) { e->g[0] = gravity[0]; e->g[1] = gravity[1]; e->g[2] = gravity[2]; }
+    drop_graph(e);
+    return 0;
+}
+extern "C" int pbd_set_mode(pbd_engine *e, int mode) {
+    if (!e) return fail("null engine");
+    if (mode < 0 || mode > 2) return fail("unknown solver mode %d", mode);
+    e->mode = mode; drop_graph(e);
+    return 0;
+}
+extern "C" int pbd_set_bucket_sort(pbd_engine *e, int enable) {
+    if (!e) return fail("null engine");
+    e->sortBuckets = enable != 0; e->imageDirty = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// flattening: constraints + colour groups -> per-type SoA arrays ordered bucket by bucket
+// ------------------------------------------------------------------------------------------------------------
+// Q (row-major 4x4, solver order) = -Kp Kp^T ?  Returns true and Kp when the rank-one negative-semidefinite form of
+// init_IsometricBendingConstraint (PositionBasedDynamics.cpp:169-180) reproduces Q to fp32 accuracy.
+static bool factor_rank1(const float *Q, float Kp[4]) {
+    int piv = 0; float best = 0.0f, maxAbs = 0.0f;
+    for (int j = 0; j < 4; j++) { if (-Q[5 * j] > best) { best = -Q[5 * j]; piv = j; } }
+    for (int i = 0; i < 16; i++) maxAbs = std::max(maxAbs, std::fabs(Q[i]));
+    if (maxAbs == 0.0f) { Kp[0] = Kp[1] = Kp[2] = Kp[3] = 0.0f; return true; }
+    if (!(best > 0.0f)) return false;
+    const double kp = std::sqrt((double)best);
+    double K[4];
+    for (int k = 0; k < 4; k++) K[k] = -(double)Q[4 * piv + k] / kp;
+    for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 4; k++)
+            if (std::fabs((double)Q[4 * j + k] + K[j] * K[k]) > 1e-5 * (double)maxAbs) return false;
+    for (int k = 0; k < 4; k++) Kp[k] = (float)K[k];
+    return true;
+}
+
+template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v, cudaStream_t s) {
+    if (v.empty()) return 0;
+    if (buf.alloc(v.size() * sizeof(T))) return 1;
+    cudaError_t e = cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return fail("upload -> %s", cudaGetErrorString(e));
+    e = cudaStreamSynchronize(s);  // the host vector dies with the caller's scope
+    if (e != cudaSuccess) return fail("upload sync -> %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int flatten(pbd_engine *e) {
+    if (!e->imageDirty) return 0;
+    CKE(use(e));
+    if (!e->groupsSet) {
+        if (e->numConstraints == 0) { e->groupOff.assign(1, 0u); e->groupIds.clear(); e->groupsSet = true; }
+        else CKE(pbd_color_first_fit(e));
+    }
+    drop_graph(e);
+    std::vector<std::pair<int, unsigned>> map;
+    CKE(build_id_map(e, map));
+    const unsigned nGroups = (unsigned)e->groupOff.size() - 1;
+
+    // 1. order every type's constraints bucket by bucket
+    std::vector<unsigned> order[PBD_NUM_TYPES];  // device position -> local host index
+    e->buckets.clear();
+    std::vector<unsigned> tmp[PBD_NUM_TYPES];
+    for (unsigned g = 0; g < nGroups; g++) {
+        for (auto &v : tmp) v.clear();
+        for (unsigned i = e->groupOff[g]; i < e->groupOff[g + 1]; i++) {
+            const auto &m = map[e->groupIds[i]];
+            tmp[m.first].push_back(m.second);
+        }
+        for (int t = 0; t < PBD_NUM_TYPES; t++) {
+            if (tmp[t].empty()) continue;
+            if (e->sortBuckets) {  // order inside a colour is free: sort by lowest particle index for gather locality
+                const int nb = type_shape(t).nBodies;
+                const unsigned *bod = e->host[t].bodies.data();
+                std::vector<std::pair<unsigned, unsigned>> keyed(tmp[t].size());
+                for (size_t i = 0; i < tmp[t].size(); i++) {
+                    const unsigned *b = bod + (size_t)tmp[t][i] * nb;
+                    unsigned mn = b[0];
+                    for (int k = 1; k < nb; k++) mn = std::min(mn, b[k]);
+                    keyed[i] = std::make_pair(mn, tmp[t][i]);
+                }
+                std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) { return a.first < b.first; });
+                for (size_t i = 0; i < keyed.size(); i++) tmp[t][i] = keyed[i].second;
+            }
+            Bucket b; b.type = t; b.first = (unsigned)order[t].size(); b.count = (unsigned)tmp[t].size(); b.colour = g;
+            e->buckets.push_back(b);
+            order[t].insert(order[t].end(), tmp[t].begin(), tmp[t].end());
+        }
+    }
+
+    // debug-grade safety: inside a colour no particle may be used twice (race freedom by construction)
+    {
+        std::vector<unsigned> stamp(e->n, 0xffffffffu);
+        size_t bi = 0;
+        for (unsigned g = 0; g < nGroups; g++) {
+            for (; bi < e->buckets.size() && e->buckets[bi].colour == g; bi++) {
+                const Bucket &b = e->buckets[bi];
+                const int nb = type_shape(b.type).nBodies;
+                for (unsigned i = 0; i < b.count; i++) {
+                    const unsigned *bd = &e->host[b.type].bodies[(size_t)order[b.type][b.first + i] * nb];
+                    for (int k = 0; k < nb; k++) {
+                        if (stamp[bd[k]] == g) return fail("colour group %u uses particle %u twice: the groups are not a valid colouring", g, bd[k]);
+                        stamp[bd[k]] = g;
+                    }
+                }
+            }
+        }
+    }
+
+    // 2. build and upload the SoA arrays of every type
+    double bytesPerSweep = 0.0;
+    for (int t = 0; t < PBD_NUM_TYPES; t++) {
+        DevType &d = e->dev[t];
+        const HostType &h = e->host[t];
+        const TypeShape s = type_shape(t);
+        const unsigned cnt = (unsigned)order[t].size();
+        d.count = cnt;
+        e->stats.constraints_per_type[t] = cnt;
+        d.arrays = TypeArrays{};
+        d.order.resize(cnt);
+        if (cnt == 0) continue;
+        for (unsigned i = 0; i < cnt; i++) d.order[i] = h.ids[order[t][i]];
+        auto P = [&](unsigned i, int k) { return h.params[(size_t)order[t][i] * s.nParams + k]; };
+        auto B = [&](unsigned i, int k) { return h.bodies[(size_t)order[t][i] * s.nBodies + k]; };
+
+        // indices
+        if (s.nBodies == 2) {
+            std::vector<uint2> v(cnt);
+            for (unsigned i = 0; i < cnt; i++) v[i] = make_uint2(B(i, 0), B(i, 1));
+            CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx2 = (const uint2 *)d.idx[0].p;
+        } else if (s.nBodies == 4) {
+            std::vector<uint4> v(cnt);
+            for (unsigned i = 0; i < cnt; i++) v[i] = make_uint4(B(i, 0), B(i, 1), B(i, 2), B(i, 3));
+            CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx4 = (const uint4 *)d.idx[0].p;
+        } else {
+            for (int k = 0; k < 3; k++) {
+                std::vector<unsigned> v(cnt);
+                for (unsigned i = 0; i < cnt; i++) v[i] = B(i, k);
+                CKE(upload_vec(d.idx[k], v, e->stream)); d.arrays.idx3[k] = (const unsigned *)d.idx[k].p;
+            }
+        }
+
+        // geometry + material slots: (param index of each material slot)
+        int matSlot[kMaxMat] = {-1, -1, -1, -1, -1};
+        std::vector<float4> gv[kMaxGeoV]; std::vector<float> gs[kMaxGeoS];
+        int variant = 0;
+        switch (t) {
+        case PBD_DISTANCE: case PBD_DISTANCE_XPBD: case PBD_DIHEDRAL: case PBD_VOLUME: case PBD_VOLUME_XPBD:
+            gs[0].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) gs[0][i] = P(i, 0);
+            matSlot[0] = 1;
+            break;
+        case PBD_ISOBENDING: case PBD_ISOBENDING_XPBD: {
+            matSlot[0] = 0;
+            gv[0].resize(cnt);
+            bool rank1 = true;
+            for (unsigned i = 0; i < cnt && rank1; i++) {
+                float Q[16], Kp[4];
+                for (int k = 0; k < 16; k++) Q[k] = P(i, 1 + k);
+                rank1 = factor_rank1(Q, Kp);
+                gv[0][i] = make_float4(Kp[0], Kp[1], Kp[2], Kp[3]);
+            }
+            if (!rank1) {  // user-modified Q somewhere in this type: literal 4x4 evaluation for the whole type
+                variant = 1;
+                for (int r = 0; r < 4; r++) {
+                    gv[r].resize(cnt);
+                    for (unsigned i = 0; i < cnt; i++) gv[r][i] = make_float4(P(i, 1 + 4 * r), P(i, 2 + 4 * r), P(i, 3 + 4 * r), P(i, 4 + 4 * r));
+                }
+            }
+            break; }
+        case PBD_FEMTRIANGLE:
+            gv[0].resize(cnt); gs[0].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) { gs[0][i] = P(i, 0); gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), P(i, 4)); }
+            for (int k = 0; k < 5; k++) matSlot[k] = 5 + k;
+            break;
+        case PBD_STRAINTRIANGLE:
+            gv[0].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), P(i, 3));
+            for (int k = 0; k < 5; k++) matSlot[k] = 4 + k;
+            break;
+        case PBD_FEMTET: case PBD_FEMTET_XPBD:
+            gv[0].resize(cnt); gv[1].resize(cnt); gs[0].resize(cnt); gs[1].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) {
+                gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), P(i, 4));
+                gv[1][i] = make_float4(P(i, 5), P(i, 6), P(i, 7), P(i, 8));
+                gs[0][i] = P(i, 9); gs[1][i] = P(i, 0);
+            }
+            matSlot[0] = 10; matSlot[1] = 11;
+            break;
+        case PBD_STRAINTET:
+            gv[0].resize(cnt); gv[1].resize(cnt); gs[0].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) {
+                gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), P(i, 3));
+                gv[1][i] = make_float4(P(i, 4), P(i, 5), P(i, 6), P(i, 7));
+                gs[0][i] = P(i, 8);
+            }
+            for (int k = 0; k < 4; k++) matSlot[k] = 9 + k;
+            break;
+        default: return fail("flatten: constraint type %d has no kernel", t);
+        }
+        d.arrays.variant = variant;
+        for (int k = 0; k < kMaxGeoV; k++) if (!gv[k].empty()) { CKE(upload_vec(d.gv[k], gv[k], e->stream)); d.arrays.gv[k] = (const float4 *)d.gv[k].p; }
+        for (int k = 0; k < kMaxGeoS; k++) if (!gs[k].empty()) { CKE(upload_vec(d.gs[k], gs[k], e->stream)); d.arrays.gs[k] = (const float *)d.gs[k].p; }
+        // material parameters: one uniform per type when every constraint agrees, else a per-constraint array
+        for (int k = 0; k < kMaxMat; k++) {
+            if (matSlot[k] < 0) continue;
+            const float first = P(0, matSlot[k]);
+            bool uniform = true;
+            for (unsigned i = 1; i < cnt && uniform; i++) uniform = (P(i, matSlot[k]) == first);
+            d.arrays.matU[k] = first;
+            if (!uniform) {
+                std::vector<float> v(cnt);
+                for (unsigned i = 0; i < cnt; i++) v[i] = P(i, matSlot[k]);
+                CKE(upload_vec(d.mat[k], v, e->stream)); d.arrays.mat[k] = (const float *)d.mat[k].p;
+            }
+        }
+        if (s.xpbd) {
+            CKE(d.lambda.alloc((size_t)cnt * sizeof(float)));
+            CK(cudaMemsetAsync(d.lambda.p, 0, (size_t)cnt * sizeof(float), e->stream));
+            d.arrays.lambda = (float *)d.lambda.p;
+        }
+        bytesPerSweep += (double)cnt * algorithmic_bytes(t, variant);
+    }
+
+    // 3. bucket table + type arrays for the persistent kernel
+    CKE(upload_vec(e->dBuckets, e->buckets, e->stream));
+    {
+        std::vector<TypeArrays> ta(PBD_NUM_TYPES);
+        for (int t = 0; t < PBD_NUM_TYPES; t++) ta[t] = e->dev[t].arrays;
+        CKE(upload_vec(e->dTypeArrays, ta, e->stream));
+    }
+    CKE(e->dBarrier.alloc(256));
+    CK(cudaMemsetAsync(e->dBarrier.p, 0, 256, e->stream));
+    e->barrierBase = 0;
+    e->coloursUsed = 0;
+    for (size_t i = 0; i < e->buckets.size(); i++)
+        if (i == 0 || e->buckets[i].colour != e->buckets[i - 1].colour) e->coloursUsed++;
+    CK(cudaStreamSynchronize(e->stream));
+
+    e->stats.num_constraints = e->numConstraints;
+    e->stats.num_groups = nGroups;
+    e->stats.num_buckets = (unsigned)e->buckets.size();
+    // algorithmic bytes of one step: sweeps + prologue/epilogue per particle per substep (integrate 48 read + 64 write
+    // when lastX is tracked, velocity update 32 (+16 second order) read + 16 write)  -- SURVEY.md section 8d
+    e->stats.bytes_per_step = bytesPerSweep;  // finalised in pbd_get_stats with the current parameters
+    e->imageDirty = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// step drivers
+// ------------------------------------------------------------------------------------------------------------
+static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, cudaStream_t s) {
+    float4 *pos = (float4 *)e->pos.p;
+    const TypeArrays &a = e->dev[b.type].arrays;
+    const unsigned grid = nblk(b.count, kProjectThreads);
+#define LB(T) case T: k_project<T><<<grid, kProjectThreads, 0, s>>>(pos, a, b.first, b.count, h, iterZero); break;
+    switch (b.type) {
+        LB(PBD_DISTANCE) LB(PBD_DISTANCE_XPBD) LB(PBD_DIHEDRAL) LB(PBD_ISOBENDING) LB(PBD_ISOBENDING_XPBD)
+        LB(PBD_FEMTRIANGLE) LB(PBD_STRAINTRIANGLE) LB(PBD_VOLUME) LB(PBD_VOLUME_XPBD) LB(PBD_FEMTET)
+        LB(PBD_FEMTET_XPBD) LB(PBD_STRAINTET)
+    default: return fail("no kernel for constraint type %d", b.type);
+    }
+#undef LB
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static inline int track_last(const pbd_engine *e) { return 1; }  // lastX is part of the reference's particle state
+
+// one TimeStepController::step as individual launches on stream s; returns the number of kernels launched
+static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
+    const float h = e->dt / (float)e->subSteps;  // TimeStepController.cpp:91
+    const float invH = (float)(1.0 / (double)h);
+    const unsigned n = e->n;
+    unsigned long long L = 0;
+    for (unsigned sub = 0; sub < e->subSteps; sub++) {
+        if (n) {
+            k_integrate<<<nblk(n, 256), 256, 0, s>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e));
+            CK(cudaGetLastError()); L++;
+        }
+        for (unsigned it = 0; it < e->maxIter; it++)
+            for (const Bucket &b : e->buckets) { CKE(launch_bucket(e, b, h, it == 0, s)); L++; }
+        if (n) {
+            k_velocity<<<nblk(n, 256), 256, 0, s>>>((const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod);
+            CK(cudaGetLastError()); L++;
+        }
+    }
+    *launches = L;
+    return 0;
+}
+
+static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
+    const float h = e->dt / (float)e->subSteps;
+    const float invH = (float)(1.0 / (double)h);
+    if (e->persistentBlocksPerSM == 0) {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step_persistent, kPersistentThreads, 0));
+        if (nb < 1) return fail("persistent kernel does not fit on an SM");
+        e->persistentBlocksPerSM = nb;
+    }
+    PersistentArgs pa;
+    pa.pos = (float4 *)e->pos.p; pa.vel = (float4 *)e->vel.p; pa.oldp = (float4 *)e->oldp.p; pa.lastp = (float4 *)e->lastp.p;
+    pa.n = e->n; pa.types = (const TypeArrays *)e->dTypeArrays.p; pa.buckets = (const Bucket *)e->dBuckets.p;
+    pa.nBuckets = (unsigned)e->buckets.size(); pa.subSteps = e->subSteps; pa.maxIter = e->maxIter;
+    pa.h = h; pa.invH = invH; pa.gx = e->g[0]; pa.gy = e->g[1]; pa.gz = e->g[2];
+    pa.secondOrder = e->velMethod; pa.trackLast = track_last(e);
+    pa.barrier = (unsigned long long *)e->dBarrier.p;
+    pa.barrierBase = e->barrierBase;
+    const int grid = e->smCount * e->persistentBlocksPerSM;
+    // barriers per launch: per substep one after the prologue and one per colour phase of every sweep
+    const unsigned long long barriers = (unsigned long long)e->subSteps * (1ull + (unsigned long long)e->maxIter * std::max(e->coloursUsed, 1u));
+    e->barrierBase += barriers * (unsigned long long)grid;
+    void *args[] = {&pa};
+    CK(cudaLaunchCooperativeKernel((void *)k_step_persistent, dim3(grid), dim3(kPersistentThreads), args, 0, s));
+    *launches = 1;
+    return 0;
+}
+
+static int ensure_graph(pbd_engine *e, unsigned long long *launchesPerStep) {
+    if (e->graphValid) return 0;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    unsigned long long L = 0;
+    int rc = enqueue_step_launches(e, e->stream, &L);
+    cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (err != cudaSuccess) return fail("cudaStreamEndCapture -> %s", cudaGetErrorString(err));
+    err = cudaGraphInstantiate(&e->graphExec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) return fail("cudaGraphInstantiate -> %s", cudaGetErrorString(err));
+    e->graphValid = true;
+    *launchesPerStep = L;
+    return 0;
+}
+
+extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    CKE(flatten(e));
+    static thread_local unsigned long long graphLaunches = 0;
+    CK(cudaEventRecord(e->evStart, e->stream));
+    for (unsigned s = 0; s < nSteps; s++) {
+        unsigned long long L = 0;
+        if (e->mode == PBD_MODE_LAUNCH) {
+            CKE(enqueue_step_launches(e, e->stream, &L));
+        } else if (e->mode == PBD_MODE_PERSISTENT) {
+            CKE(enqueue_step_persistent(e, e->stream, &L));
+        } else {
+            unsigned long long LL = 0;
+            if (!e->graphValid) { CKE(ensure_graph(e, &LL)); graphLaunches = LL; }
+            CK(cudaGraphLaunch(e->graphExec, e->stream));
+            L = graphLaunches;
+        }
+        e->stats.kernel_launches += L;
+        e->stats.steps++;
+        e->stats.projections += (unsigned long long)e->numConstraints * e->subSteps * e->maxIter;
+    }
+    CK(cudaEventRecord(e->evStop, e->stream));
+    e->timingPending = true;
+    return 0;
+}
+
+extern "C" int pbd_sync(pbd_engine *e) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->timingPending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, e->evStart, e->evStop) == cudaSuccess) e->stats.last_step_ms = ms;
+        e->timingPending = false;
+    }
+    return 0;
+}
+
+extern "C" int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    if (e->n == 0) return pbd_step(e, nSteps);
+    const size_t bytes = (size_t)e->n * 3 * sizeof(float);
+    // two staging areas so that x and v uploads do not serialise on a host sync
+    CKE(e->stage.alloc(bytes));
+    static thread_local DevBuf stage2;
+    CKE(stage2.alloc(bytes));
+    if (x_in) {
+        CK(cudaMemcpyAsync(e->stage.p, x_in, bytes, cudaMemcpyHostToDevice, e->stream));
+        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, (float4 *)e->pos.p, e->n, 1);
+    }
+    if (v_in) {
+        CK(cudaMemcpyAsync(stage2.p, v_in, bytes, cudaMemcpyHostToDevice, e->stream));
+        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)stage2.p, (float4 *)e->vel.p, e->n, 1);
+    }
+    CK(cudaGetLastError());
+    CKE(pbd_step(e, nSteps));
+    if (x_out) {
+        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float *)e->stage.p, e->n);
+        CK(cudaMemcpyAsync(x_out, e->stage.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (v_out) {
+        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->vel.p, (float *)stage2.p, e->n);
+        CK(cudaMemcpyAsync(v_out, stage2.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int pbd_get_lambdas(pbd_engine *e, int type, float *dst, unsigned *ids) {
+    if (!e || !dst) return fail("null argument");
+    if (type < 0 || type >= PBD_NUM_TYPES || !type_shape(type).xpbd) return fail("type %d has no multipliers", type);
+    CKE(use(e)); CKE(flatten(e));
+    DevType &d = e->dev[type];
+    if (d.count == 0) return 0;
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(dst, d.lambda.p, (size_t)d.count * sizeof(float), cudaMemcpyDeviceToHost));
+    if (ids) memcpy(ids, d.order.data(), (size_t)d.count * sizeof(unsigned));
+    return 0;
+}
+
+extern "C" int pbd_get_stats(pbd_engine *e, pbd_stats *out) {
+    if (!e || !out) return fail("null argument");
+    CKE(use(e)); CKE(flatten(e));
+    double sweep = 0.0;
+    for (int t = 0; t < PBD_NUM_TYPES; t++) sweep += (double)e->dev[t].count * algorithmic_bytes(t, e->dev[t].arrays.variant);
+    // per particle per substep: integrate 48 read + 64 write = 112, velocity update 32 read + 16 write = 48
+    const double perParticle = 112.0 + 48.0 + (e->velMethod ? 16.0 : 0.0);
+    e->stats.bytes_per_step = (sweep * e->maxIter + (double)e->n * perParticle) * e->subSteps;
+    *out = e->stats;
+    return 0;
+}
+
+extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegrate, float *msVelocity, unsigned *launchesPerType) {
+    if (!e) return fail("null engine");
+    CKE(use(e)); CKE(flatten(e));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    if (msPerType) for (int t = 0; t < PBD_NUM_TYPES; t++) msPerType[t] = 0.0f;
+    if (launchesPerType) for (int t = 0; t < PBD_NUM_TYPES; t++) launchesPerType[t] = 0;
+    float mi = 0.0f, mv = 0.0f, ms = 0.0f;
+    const float h = e->dt / (float)e->subSteps;
+    const float invH = (float)(1.0 / (double)h);
+    const unsigned n = e->n;
+    for (unsigned sub = 0; sub < e->subSteps; sub++) {
+        if (n) {
+            CK(cudaEventRecord(a, e->stream));
+            k_integrate<<<nblk(n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e));
+            CK(cudaEventRecord(b, e->stream)); CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b)); mi += ms;
+        }
+        for (unsigned it = 0; it < e->maxIter; it++)
+            for (const Bucket &bk : e->buckets) {
+                CK(cudaEventRecord(a, e->stream));
+                CKE(launch_bucket(e, bk, h, it == 0, e->stream));
+                CK(cudaEventRecord(b, e->stream)); CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b));
+                if (msPerType) msPerType[bk.type] += ms;
+                if (launchesPerType) launchesPerType[bk.type]++;
+            }
+        if (n) {
+            CK(cudaEventRecord(a, e->stream));
+            k_velocity<<<nblk(n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod);
+            CK(cudaEventRecord(b, e->stream)); CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b)); mv += ms;
+        }
+    }
+    if (msIntegrate) *msIntegrate = mi;
+    if (msVelocity) *msVelocity = mv;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    e->stats.steps++;
+    e->stats.projections += (unsigned long long)e->numConstraints * e->subSteps * e->maxIter;
+    return 0;
+}

@@ -1,0 +1,310 @@
+// positionbaseddynamics_b200/csrc/host/pbd_model.h
+//
+// Host-side mirror of the reference's model interface for the constraint-projection path: the same class and
+// method names, argument meaning and bool/void error behaviour as
+//   Simulation/ParticleData.h:86-311, Utils/IndexedFaceMesh.h, Utils/IndexedTetMesh.h, Simulation/TriangleModel.h,
+//   Simulation/TetModel.h, Simulation/SimulationModel.h:134-327, Simulation/TimeStepController.h, Simulation/TimeManager.h
+// so that scene-building code written against the reference drives the B200 engine unchanged.  The storage behind
+// the interface is NOT the reference's: constraints live in per-type structure-of-arrays stores (no heap object and
+// no vtable per constraint), which is what the device image is flattened from.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+#include "../../../include/pbd_b200.h"
+
+namespace pbd_b200 {
+
+using Real = float;  // the engine is fp32 (Common/Common.h:7-28 with USE_DOUBLE undefined)
+
+struct Vector3r {
+    Real v[3];
+    Vector3r() : v{0, 0, 0} {}
+    Vector3r(Real x, Real y, Real z) : v{x, y, z} {}
+    Real &operator[](int i) { return v[i]; }
+    const Real &operator[](int i) const { return v[i]; }
+};
+static_assert(sizeof(Vector3r) == 12, "Vector3r must be 3 packed floats (Eigen::DontAlign layout, Common/Common.h:31)");
+struct Vector2r { Real v[2]; Real &operator[](int i) { return v[i]; } const Real &operator[](int i) const { return v[i]; } };
+struct Matrix3r {  // row-major
+    Real m[9];
+    static Matrix3r Identity() { Matrix3r r{}; r.m[0] = r.m[4] = r.m[8] = 1; return r; }
+    Real operator()(int r, int c) const { return m[3 * r + c]; }
+    Real &operator()(int r, int c) { return m[3 * r + c]; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// ParticleData (Simulation/ParticleData.h:86-311)
+// ---------------------------------------------------------------------------------------------------------
+class SimulationModel;
+class ParticleData {
+public:
+    void addVertex(const Vector3r &vertex);  // mass = invMass = 1, v = a = 0, x0 = x = oldX = lastX (ParticleData.h:127-137)
+    unsigned int size() const { return (unsigned int)m_x.size(); }
+    unsigned int getNumberOfParticles() const { return size(); }
+    void reserve(unsigned int n);
+    void release();
+
+    // Non-const accessors hand out lvalues exactly like the reference; they first pull that attribute from the device
+    // when the engine is ahead and mark it as modified on the host (the next step re-uploads it).
+    Vector3r &getPosition(unsigned int i) { touch(PBD_ATTR_X); return m_x[i]; }
+    Vector3r &getPosition0(unsigned int i) { touch(PBD_ATTR_X0); return m_x0[i]; }
+    Vector3r &getVelocity(unsigned int i) { touch(PBD_ATTR_V); return m_v[i]; }
+    Vector3r &getAcceleration(unsigned int i) { return m_a[i]; }
+    Vector3r &getOldPosition(unsigned int i) { touch(PBD_ATTR_OLDX); return m_oldX[i]; }
+    Vector3r &getLastPosition(unsigned int i) { touch(PBD_ATTR_LASTX); return m_lastX[i]; }
+    const Vector3r &getPosition(unsigned int i) const { pull(PBD_ATTR_X); return m_x[i]; }
+    const Vector3r &getPosition0(unsigned int i) const { return m_x0[i]; }
+    const Vector3r &getVelocity(unsigned int i) const { pull(PBD_ATTR_V); return m_v[i]; }
+    const Vector3r &getOldPosition(unsigned int i) const { pull(PBD_ATTR_OLDX); return m_oldX[i]; }
+    const Vector3r &getLastPosition(unsigned int i) const { pull(PBD_ATTR_LASTX); return m_lastX[i]; }
+    void setPosition(unsigned int i, const Vector3r &p) { touch(PBD_ATTR_X); m_x[i] = p; }
+    void setPosition0(unsigned int i, const Vector3r &p) { touch(PBD_ATTR_X0); m_x0[i] = p; }
+    void setVelocity(unsigned int i, const Vector3r &p) { touch(PBD_ATTR_V); m_v[i] = p; }
+    void setAcceleration(unsigned int i, const Vector3r &p) { m_a[i] = p; }
+    Real getMass(unsigned int i) const { return m_masses[i]; }
+    Real getInvMass(unsigned int i) const { return m_invMasses[i]; }
+    void setMass(unsigned int i, Real mass);  // keeps invMass consistent (ParticleData.h:239-246)
+    const std::vector<Vector3r> &getVertices() const { pull(PBD_ATTR_X); return m_x; }  // pyPBD getVertices (ParticleDataModule.cpp:54-58)
+
+    // raw storage (reference member names)
+    std::vector<Real> m_masses, m_invMasses;
+    std::vector<Vector3r> m_x0, m_x, m_v, m_a, m_oldX, m_lastX;
+
+    // coherence with the device image: one bit per pbd_attr
+    mutable unsigned int dirtyMask = 0x1f;  // host copy of the attribute modified since the last upload
+    mutable unsigned int aheadMask = 0;     // device copy of the attribute newer than the host copy
+    mutable bool massDirty = true;
+    std::function<bool(int)> pullAttr;      // installed by the TimeStepController that owns the engine
+    void touch(int attr) const { pull(attr); dirtyMask |= 1u << attr; }
+    void pull(int attr) const { if ((aheadMask >> attr) & 1u) { if (pullAttr && pullAttr(attr)) aheadMask &= ~(1u << attr); } }
+    void pullAll() const { for (int a = 0; a < 5; a++) pull(a); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Mesh topology (Utils/IndexedFaceMesh.{h,cpp}, Utils/IndexedTetMesh.{h,cpp}); the edge DISCOVERY ORDER defines the
+// constraint order, hence the colouring and the Gauss-Seidel order.
+// ---------------------------------------------------------------------------------------------------------
+class IndexedFaceMesh {
+public:
+    struct Edge { std::array<unsigned int, 2> m_face; std::array<unsigned int, 2> m_vert; };  // IndexedFaceMesh.h:14-18
+    typedef std::vector<unsigned int> Faces;
+    typedef std::vector<Edge> Edges;
+    void initMesh(unsigned int nPoints, unsigned int nEdges, unsigned int nFaces);
+    void addFace(const unsigned int *indices);
+    void buildNeighbors();  // IndexedFaceMesh.cpp:118-226
+    const Faces &getFaces() const { return m_indices; }
+    const Edges &getEdges() const { return m_edges; }
+    unsigned int numVertices() const { return m_numPoints; }
+    unsigned int numFaces() const { return (unsigned int)m_indices.size() / 3; }
+    unsigned int numEdges() const { return (unsigned int)m_edges.size(); }
+    bool isClosed() const { return m_closed; }
+private:
+    unsigned int m_numPoints = 0;
+    Faces m_indices;
+    Edges m_edges;
+    bool m_closed = false;
+};
+
+class IndexedTetMesh {
+public:
+    struct Edge { std::array<unsigned int, 2> m_vert; };
+    typedef std::vector<unsigned int> Tets;
+    typedef std::vector<Edge> Edges;
+    void initMesh(unsigned int nPoints, unsigned int nEdges, unsigned int nFaces, unsigned int nTets);
+    void addTet(const unsigned int *indices);
+    void buildNeighbors();  // IndexedTetMesh.cpp:55-182 (edges + vertex->tet incidence; faces are not needed on this path)
+    const Tets &getTets() const { return m_tetIndices; }
+    const Edges &getEdges() const { return m_edges; }
+    const std::vector<unsigned int> &getVertexTetCounts() const { return m_vertexTetCount; }
+    unsigned int numVertices() const { return m_numPoints; }
+    unsigned int numTets() const { return (unsigned int)m_tetIndices.size() / 4; }
+    unsigned int numEdges() const { return (unsigned int)m_edges.size(); }
+private:
+    unsigned int m_numPoints = 0;
+    Tets m_tetIndices;
+    Edges m_edges;
+    std::vector<unsigned int> m_vertexTetCount;
+};
+
+class TriangleModel {
+public:
+    typedef IndexedFaceMesh ParticleMesh;
+    void initMesh(unsigned int nPoints, unsigned int nFaces, unsigned int indexOffset, const unsigned int *indices);  // TriangleModel.cpp:30-43
+    ParticleMesh &getParticleMesh() { return m_particleMesh; }
+    const ParticleMesh &getParticleMesh() const { return m_particleMesh; }
+    unsigned int getIndexOffset() const { return m_indexOffset; }
+private:
+    unsigned int m_indexOffset = 0;
+    ParticleMesh m_particleMesh;
+};
+
+class TetModel {
+public:
+    typedef IndexedTetMesh ParticleMesh;
+    void initMesh(unsigned int nPoints, unsigned int nTets, unsigned int indexOffset, const unsigned int *indices);  // TetModel.cpp
+    ParticleMesh &getParticleMesh() { return m_particleMesh; }
+    const ParticleMesh &getParticleMesh() const { return m_particleMesh; }
+    unsigned int getIndexOffset() const { return m_indexOffset; }
+private:
+    unsigned int m_indexOffset = 0;
+    ParticleMesh m_particleMesh;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Constraint storage: per-type SoA in the flat parameter layout of include/pbd_b200.h, plus the global insertion
+// order (the reference's m_constraints vector) as (type, local index) pairs.
+// ---------------------------------------------------------------------------------------------------------
+struct ConstraintRef { int type; unsigned int local; };
+struct ConstraintView {  // what `model.getConstraints()[i]` exposes
+    int type; unsigned int numberOfBodies; const unsigned int *m_bodies; const Real *params; unsigned int numParams;
+};
+struct TypeStore { std::vector<unsigned int> ids, bodies; std::vector<Real> params; };
+
+class SimulationModel {
+public:
+    typedef std::vector<TriangleModel *> TriangleModelVector;
+    typedef std::vector<TetModel *> TetModelVector;
+    typedef std::vector<std::vector<unsigned int>> ConstraintGroupVector;
+
+    SimulationModel();
+    ~SimulationModel();
+    void init() {}
+    void reset();    // SimulationModel.cpp:270-304: x = x0 = oldX = lastX, v = a = 0
+    void cleanup();  // SimulationModel.cpp:105-126
+
+    ParticleData &getParticles() { return m_particles; }
+    TriangleModelVector &getTriangleModels() { return m_triangleModels; }
+    TetModelVector &getTetModels() { return m_tetModels; }
+    ConstraintGroupVector &getConstraintGroups() { return m_constraintGroups; }
+    unsigned int numConstraints() const { return (unsigned int)m_order.size(); }
+    ConstraintView getConstraint(unsigned int i) const;
+    bool m_groupsInitialized = false;
+
+    void addTriangleModel(unsigned int nPoints, unsigned int nFaces, const Vector3r *points, const unsigned int *indices);
+    void addRegularTriangleModel(int width, int height, const Vector3r &translation = Vector3r(), const Matrix3r &rotation = Matrix3r::Identity(),
+                                 const Vector2r &scale = Vector2r{{1, 1}});
+    void addTetModel(unsigned int nPoints, unsigned int nTets, const Vector3r *points, const unsigned int *indices);
+    void addRegularTetModel(int width, int height, int depth, const Vector3r &translation = Vector3r(), const Matrix3r &rotation = Matrix3r::Identity(),
+                            const Vector3r &scale = Vector3r(1, 1, 1));
+
+    void initConstraintGroups();  // SimulationModel.cpp:1033-1094 (greedy first fit, insertion order)
+
+    // each returns false (and adds nothing) when the rest configuration is degenerate, like the reference
+    bool addDistanceConstraint(unsigned int p1, unsigned int p2, Real stiffness);
+    bool addDistanceConstraint_XPBD(unsigned int p1, unsigned int p2, Real stiffness);
+    bool addDihedralConstraint(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness);
+    bool addIsometricBendingConstraint(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness);
+    bool addIsometricBendingConstraint_XPBD(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness);
+    bool addFEMTriangleConstraint(unsigned int p1, unsigned int p2, unsigned int p3, Real xxStiffness, Real yyStiffness, Real xyStiffness,
+                                  Real xyPoissonRatio, Real yxPoissonRatio);
+    bool addStrainTriangleConstraint(unsigned int p1, unsigned int p2, unsigned int p3, Real xxStiffness, Real yyStiffness, Real xyStiffness,
+                                     bool normalizeStretch, bool normalizeShear);
+    bool addVolumeConstraint(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness);
+    bool addVolumeConstraint_XPBD(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness);
+    bool addFEMTetConstraint(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness, Real poissonRatio);
+    bool addFEMTetConstraint_XPBD(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness, Real poissonRatio);
+    bool addStrainTetConstraint(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stretchStiffness, Real shearStiffness,
+                                bool normalizeStretch, bool normalizeShear);
+
+    void addClothConstraints(const TriangleModel *tm, unsigned int clothMethod, Real distanceStiffness, Real xxStiffness, Real yyStiffness,
+                             Real xyStiffness, Real xyPoissonRatio, Real yxPoissonRatio, bool normalizeStretch, bool normalizeShear);
+    void addBendingConstraints(const TriangleModel *tm, unsigned int bendingMethod, Real stiffness);
+    void addSolidConstraints(const TetModel *tm, unsigned int solidMethod, Real stiffness, Real poissonRatio, Real volumeStiffness,
+                             bool normalizeStretch, bool normalizeShear);
+
+    // global stiffness setters (SimulationModel.cpp:1351-1485); reference quirk kept: YY and XY write the XX member (:1365-1377)
+    void setClothStiffness(Real val);
+    void setClothStiffnessXX(Real val);
+    void setClothStiffnessYY(Real val);
+    void setClothStiffnessXY(Real val);
+    void setClothPoissonRatioXY(Real val);
+    void setClothPoissonRatioYX(Real val);
+    void setClothBendingStiffness(Real val);
+    void setClothNormalizeStretch(bool val);
+    void setClothNormalizeShear(bool val);
+    void setSolidStiffness(Real val);
+    void setSolidPoissonRatio(Real val);
+    void setSolidVolumeStiffness(Real val);
+    void setSolidNormalizeStretch(bool val);
+    void setSolidNormalizeShear(bool val);
+
+    // flat view for the engine
+    const TypeStore &store(int type) const { return m_store[type]; }
+    uint64_t constraintGeneration() const { return m_generation; }  // bumps whenever constraints or their parameters change
+
+private:
+    bool pushConstraint(int type, const unsigned int *bodies, const Real *params, bool ok);
+    void setParam(int type, int slot, Real val);
+    ParticleData m_particles;
+    TriangleModelVector m_triangleModels;
+    TetModelVector m_tetModels;
+    TypeStore m_store[PBD_NUM_TYPES];
+    std::vector<ConstraintRef> m_order;
+    ConstraintGroupVector m_constraintGroups;
+    uint64_t m_generation = 1;
+};
+
+// Greedy first-fit colouring shared by SimulationModel::initConstraintGroups and pbd_color_first_fit: constraint c uses
+// bodies[bodyOff[c] .. bodyOff[c+1]); returns per-constraint colour and the number of colours.
+unsigned int firstFitColouring(unsigned int numBodies, unsigned int numConstraints, const unsigned int *bodyOff,
+                               const unsigned int *bodies, std::vector<unsigned int> &colour);
+
+// ---------------------------------------------------------------------------------------------------------
+// TimeManager / TimeStepController (Simulation/TimeManager.h, Simulation/TimeStepController.{h,cpp})
+// ---------------------------------------------------------------------------------------------------------
+class TimeManager {
+public:
+    Real getTime() const { return time; }
+    void setTime(Real t) { time = t; }
+    Real getTimeStepSize() const { return h; }
+    void setTimeStepSize(Real tss) { h = tss; }
+private:
+    Real time = 0; Real h = static_cast<Real>(0.005);  // TimeManager.cpp:10
+};
+
+class TimeStepController {
+public:
+    // parameter ids with the reference's names (TimeStepController.h:16-22, .cpp:47-72)
+    static const int NUM_SUB_STEPS = 0, MAX_ITERATIONS = 1, MAX_ITERATIONS_V = 2, VELOCITY_UPDATE_METHOD = 3;
+    static const int ENUM_VUPDATE_FIRST_ORDER = 0, ENUM_VUPDATE_SECOND_ORDER = 1;
+
+    explicit TimeStepController(int device = 0, void *stream = nullptr);
+    ~TimeStepController();
+    bool valid() const { return m_engine != nullptr; }
+    const std::string &error() const { return m_error; }
+
+    void init() {}
+    void reset();                         // TimeStepController.cpp:243-249
+    bool step(SimulationModel &model);    // TimeStepController.cpp:75-241; false + error() on CUDA failure (reference: void)
+
+    unsigned int getValueUInt(int id) const;
+    bool setValueUInt(int id, unsigned int v);
+    int getValueInt(int id) const { return id == VELOCITY_UPDATE_METHOD ? m_velocityUpdateMethod : 0; }
+    bool setValueInt(int id, int v);
+    void setGravitation(const Vector3r &g) { m_gravitation = g; }  // Simulation::GRAVITATION (Simulation.cpp:63)
+    const Vector3r &getGravitation() const { return m_gravitation; }
+    TimeManager &timeManager() { return m_tm; }
+    pbd_engine *engine() { return m_engine; }
+    void setSolverMode(int mode) { m_mode = mode; }
+
+private:
+    bool uploadModel(SimulationModel &model);
+    bool fail(const char *what);
+    pbd_engine *m_engine = nullptr;
+    std::string m_error;
+    TimeManager m_tm;
+    unsigned int m_subSteps = 5, m_maxIterations = 1, m_maxIterationsV = 5;  // TimeStepController.cpp:28-30
+    int m_velocityUpdateMethod = 0;
+    Vector3r m_gravitation = Vector3r(0, static_cast<Real>(-9.81), 0);  // Simulation.cpp:16
+    int m_mode = PBD_MODE_GRAPH, m_modeSent = -1;
+    struct SentParams { float dt; unsigned int subSteps, maxIter; int velMethod; float g[3]; } m_sent{};
+    bool m_sentValid = false;
+    const SimulationModel *m_boundModel = nullptr;
+    uint64_t m_boundGeneration = 0;
+    unsigned int m_boundParticles = 0;
+};
+
+}  // namespace pbd_b200
