@@ -1,7 +1,6 @@
 """Host model mirror over the C ABI of include/pbd_b200_model.h (ctypes; no compute happens in Python).
 
-`HostModel` carries the snake_case builder surface that tests/scenes.py drives (the same surface the CPU checkers in
-oracle/pyoracle.py expose), `TimeStep` wraps the engine-backed TimeStepController.  The camelCase API that mirrors
+`HostModel` carries the snake_case builder surface that tests/scenes.py drives (the same surface the CPU checkers of the test suite expose), `TimeStep` wraps the engine-backed TimeStepController.  The camelCase API that mirrors
 pyPBD one-to-one lives in positionbaseddynamics_b200/pypbd.py on top of these.
 """
 import ctypes as C
@@ -124,7 +123,7 @@ class HostModel:
         except Exception:
             pass
 
-    # -- builder surface shared with oracle.pyoracle.CpuPbd ------------------------------------------
+    # -- builder surface (snake_case; tests/scenes.py drives it) ---------------------------------------
     def add_regular_triangle_model(self, w, h, t=(0, 0, 0), R=np.eye(3), scale=(1, 1)):
         _l().pbdm_add_regular_triangle_model(self._h, w, h, _p(_f32(t)), _p(_f32(R)), _p(_f32(scale)))
 

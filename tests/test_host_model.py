@@ -1,0 +1,119 @@
+"""Host model mirror (C++ behind include/pbd_b200_model.h): scene construction, mesh topology, constraint
+initialisation, greedy colouring and error behaviour -- no GPU needed."""
+import os
+import numpy as np
+import pytest
+
+import scenes
+from golden.make_golden import STRUCT_SCENES
+from positionbaseddynamics_b200 import _capi
+from positionbaseddynamics_b200.model import HostModel, first_fit_colouring
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(STRUCT_SCENES))
+def test_structure_equals_reference_golden(name):
+    """Particle order, edge order, constraint order and colour groups must equal the reference's bit for bit
+    (integers); rest data within fp32 rounding of the reference's fp64 values."""
+    d = np.load(os.path.join(G, "structure.npz"))
+    m = HostModel()
+    STRUCT_SCENES[name](m)
+    t, b, p, nb = m.constraints()
+    off, ids = m.groups()
+    assert (t == d[name + "/types"]).all()
+    assert (b == d[name + "/bodies"]).all()
+    assert (off == d[name + "/group_off"]).all() and (ids == d[name + "/group_ids"]).all()
+    ref_p = d[name + "/params"]
+    sc = np.abs(ref_p).max(0) + 1e-30
+    assert (np.abs(p - ref_p) / sc).max() <= 2e-5   # fp32 positions feed the rest data
+    assert np.abs(m.get("x0") - d[name + "/x0"]).max() <= 1e-6
+    if name + "/tri_edges" in d:
+        assert (m.tri_edges(0) == d[name + "/tri_edges"]).all() and (m.tri_faces(0) == d[name + "/tri_faces"]).all()
+    if name + "/tet_edges" in d:
+        assert (m.tet_edges(0) == d[name + "/tet_edges"]).all() and (m.tet_tets(0) == d[name + "/tet_tets"]).all()
+    m.close()
+
+
+def test_structure_equals_oracle_on_larger_scenes(cpu_libs):
+    for build in (lambda m: scenes.cfg2(m, 120, 20), lambda m: scenes.cfg3(m, 21, 9, 9)):
+        h = HostModel(); o = cpu_libs.CpuPbd("oracle", "f64")
+        build(h); build(o)
+        th, bh, _, _ = h.constraints(); to, bo, _, _ = o.constraints()
+        assert (th == to).all() and (bh == bo).all()
+        gh, go = h.groups(), o.groups()
+        assert (gh[0] == go[0]).all() and (gh[1] == go[1]).all()
+        h.close()
+
+
+def test_cfg1_group_sizes_match_survey_probe():
+    m = HostModel(); scenes.cfg1(m)
+    off, _ = m.groups()
+    assert m.num_particles() == 2500 and m.num_constraints() == 14406
+    assert list(np.diff(off)) == [1250, 1249, 1224, 1154, 602, 624, 623, 577, 579, 530, 436, 445, 425, 447, 429, 441, 427, 416, 425,
+                                  444, 438, 375, 349, 316, 161, 20]
+    m.close()
+
+
+def test_colouring_is_valid_and_first_fit():
+    rng = np.random.RandomState(7)
+    nb, nc = 120, 6000
+    sizes = rng.choice([2, 3, 4], size=nc)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    bodies = np.concatenate([rng.choice(nb, size=s, replace=False) for s in sizes]).astype(np.uint32)
+    ncol, col = first_fit_colouring(nb, off, bodies)
+    assert ncol > 64  # exercises the multi-word bit sets
+    # reference semantics, restated naively: first colour whose byte map is free for all bodies
+    maps = []
+    for c in range(nc):
+        bs = bodies[off[c]:off[c + 1]]
+        for j, mp in enumerate(maps):
+            if not mp[bs].any():
+                break
+        else:
+            maps.append(np.zeros(nb, bool)); j = len(maps) - 1
+        maps[j][bs] = True
+        assert col[c] == j
+    assert ncol == len(maps)
+
+
+def test_degenerate_rest_states_are_rejected_like_the_reference():
+    m = HostModel()
+    pts = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]], np.float32)  # collinear
+    m.add_triangle_model(pts, np.zeros((0, 3), np.uint32))
+    assert m.add_constraint(_capi.FEMTET, [0, 1, 2, 3], [1e6, 0.3]) == 0       # singular rest matrix (PositionBasedDynamics.cpp:947-954)
+    assert m.add_constraint(_capi.STRAINTET, [0, 1, 2, 3], [1, 1, 0, 0]) == 0
+    assert m.add_constraint(_capi.FEMTRIANGLE, [0, 1, 2], [1, 1, 1, 0.3, 0.3]) == 0
+    assert m.num_constraints() == 0
+    assert m.add_constraint(_capi.DISTANCE, [0, 1], [1.0]) == 1
+    assert m.add_constraint(_capi.VOLUME, [0, 1, 2, 3], [1.0]) == 1           # rest volume 0 is accepted (Constraints.cpp:1617-1635)
+    assert m.num_constraints() == 2
+    m.close()
+
+
+def test_mass_and_parameter_setters():
+    m = HostModel(); scenes.cloth(m, 6, 6, 2, 2)
+    mass, w = m.masses()
+    assert mass[0] == 0 and w[0] == 0 and mass[5] == 0 and (mass[6:] == 1).all()
+    m.set_mass(7, 4.0)
+    mass, w = m.masses()
+    assert mass[7] == 4.0 and w[7] == 0.25
+    # reference quirk (SimulationModel.cpp:1365-1377): setClothStiffnessYY writes the XX member
+    m.set_model_param(2, 123.0)
+    t, _, p, _ = m.constraints()
+    fem = p[t == _capi.FEMTRIANGLE]
+    assert (fem[:, 5] == 123.0).all() and (fem[:, 6] == 1.0).all()
+    m.set_model_param(6, 0.77)  # bending stiffness
+    _, _, p, _ = m.constraints()
+    assert (p[t == _capi.ISOBENDING][:, 0] == np.float32(0.77)).all()
+    m.close()
+
+
+def test_particle_attribute_round_trip_and_view():
+    m = HostModel(); m.add_regular_triangle_model(5, 4, scale=(2, 1))
+    x = m.get("x"); assert x.shape == (20, 3)
+    x2 = x + 1
+    m.set("x", x2)
+    assert (m.get("x") == x2).all() and (m.vertices_view() == x2).all()
+    assert (m.get("x0") == x).all()
+    m.close()
