@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -96,6 +97,8 @@ struct pbd_engine {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timingPending = false;
     int persistentBlocksPerSM = 0;
+    bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
+    bool gatherCA = true;                 // particle gathers through L1 (tuning knob: PBD_B200_GATHER=cg selects L2-only loads)
     unsigned coloursUsed = 0;             // colours that own at least one bucket
     unsigned long long barrierBase = 0;   // value of the grid-barrier counter when the next persistent launch starts
 };
@@ -132,6 +135,8 @@ extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
         e->ownsStream = true;
     }
     cudaEventCreate(&e->evStart); cudaEventCreate(&e->evStop);
+    if (const char *g = getenv("PBD_B200_GATHER")) e->gatherCA = (strcmp(g, "cg") != 0);
+    if (const char *g = getenv("PBD_B200_PDL")) e->usePDL = (strcmp(g, "0") != 0);
     *out = e;
     return 0;
 }
@@ -616,7 +621,15 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
     float4 *pos = (float4 *)e->pos.p;
     const TypeArrays &a = e->dev[b.type].arrays;
     const unsigned grid = nblk(b.count, kProjectThreads);
-#define LB(T) case T: k_project<T><<<grid, kProjectThreads, 0, s>>>(pos, a, b.first, b.count, h, iterZero); break;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kProjectThreads); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = e->usePDL ? 1 : 0;
+    cudaError_t le = cudaSuccess;
+#define LB(T) case T: le = e->gatherCA ? cudaLaunchKernelEx(&cfg, k_project<T, true>, pos, a, b.first, b.count, h, iterZero) \
+                                       : cudaLaunchKernelEx(&cfg, k_project<T, false>, pos, a, b.first, b.count, h, iterZero); break;
     switch (b.type) {
         LB(PBD_DISTANCE) LB(PBD_DISTANCE_XPBD) LB(PBD_DIHEDRAL) LB(PBD_ISOBENDING) LB(PBD_ISOBENDING_XPBD)
         LB(PBD_FEMTRIANGLE) LB(PBD_STRAINTRIANGLE) LB(PBD_VOLUME) LB(PBD_VOLUME_XPBD) LB(PBD_FEMTET)
@@ -624,8 +637,20 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
     default: return fail("no kernel for constraint type %d", b.type);
     }
 #undef LB
-    CK(cudaGetLastError());
+    CK(le);
     return 0;
+}
+
+// prologue / epilogue launches share the PDL attribute so that the whole step is one programmatic dependency chain
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_particles(pbd_engine *e, cudaStream_t s, void (*kernel)(KArgs...), unsigned n, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((n + 255) / 256); cfg.blockDim = dim3(256); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = e->usePDL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 static inline int track_last(const pbd_engine *e) { return 1; }  // lastX is part of the reference's particle state
@@ -638,14 +663,14 @@ static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long lo
     unsigned long long L = 0;
     for (unsigned sub = 0; sub < e->subSteps; sub++) {
         if (n) {
-            k_integrate<<<nblk(n, 256), 256, 0, s>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e));
-            CK(cudaGetLastError()); L++;
+            CK(launch_particles(e, s, k_integrate, n, (float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e)));
+            L++;
         }
         for (unsigned it = 0; it < e->maxIter; it++)
             for (const Bucket &b : e->buckets) { CKE(launch_bucket(e, b, h, it == 0, s)); L++; }
         if (n) {
-            k_velocity<<<nblk(n, 256), 256, 0, s>>>((const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod);
-            CK(cudaGetLastError()); L++;
+            CK(launch_particles(e, s, k_velocity, n, (const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod));
+            L++;
         }
     }
     *launches = L;
@@ -657,7 +682,8 @@ static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long 
     const float invH = (float)(1.0 / (double)h);
     if (e->persistentBlocksPerSM == 0) {
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step_persistent, kPersistentThreads, 0));
+        if (e->gatherCA) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step_persistent<true>, kPersistentThreads, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step_persistent<false>, kPersistentThreads, 0));
         if (nb < 1) return fail("persistent kernel does not fit on an SM");
         e->persistentBlocksPerSM = nb;
     }
@@ -674,7 +700,8 @@ static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long 
     const unsigned long long barriers = (unsigned long long)e->subSteps * (1ull + (unsigned long long)e->maxIter * std::max(e->coloursUsed, 1u));
     e->barrierBase += barriers * (unsigned long long)grid;
     void *args[] = {&pa};
-    CK(cudaLaunchCooperativeKernel((void *)k_step_persistent, dim3(grid), dim3(kPersistentThreads), args, 0, s));
+    void *fn = e->gatherCA ? (void *)k_step_persistent<true> : (void *)k_step_persistent<false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistentThreads), args, 0, s));
     *launches = 1;
     return 0;
 }

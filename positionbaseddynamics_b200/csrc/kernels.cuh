@@ -17,7 +17,26 @@
 
 namespace pbdk {
 
-__device__ __forceinline__ float4 ldp(const float4 *p) { return __ldcg(p); }
+// Programmatic dependent launch (PDL): every kernel of the step is launched with the programmatic-stream-serialization
+// attribute, announces "dependents may launch" immediately and waits for its predecessor only right before it touches
+// particle data.  The next bucket's CTAs therefore get scheduled while the current bucket drains, and their coalesced
+// streaming loads of indices / rest data (the HBM-latency part) overlap the predecessor's tail.  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// wait that is data-dependent on the streamed operands, so that ptxas cannot sink their loads below the wait
+// (ptxas hoists an operand-less ACQBULK above independent loads; predicating the wait on the loaded data -- both
+// predicate senses wait, so it always executes -- pins it behind them)
+__device__ __forceinline__ void pdl_wait_after(unsigned a, float b) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p griddepcontrol.wait;\n\t@!p griddepcontrol.wait;\n\t}" :: "r"(a), "r"(__float_as_uint(b)) : "memory");
+}
+
+// Particle gather flavour (template parameter CA of the kernels):
+//   CA = false: ld.global.cg -- L2 only.
+//   CA = true : ld.global.ca -- through L1, so the 2-4 gathers of one constraint and of neighbouring threads that fall
+//               into the same 32 B sector / 128 B line are served once.  Safe because L1 is invalidated at every kernel
+//               boundary and, in the persistent kernel, by the gpu-scope fence on the acquire side of the grid barrier.
+template <bool CA> __device__ __forceinline__ float4 ldp(const float4 *p) { return CA ? *p : __ldcg(p); }
 __device__ __forceinline__ void stp(float4 *p, const float4 &v) { if (v.w != 0.0f) __stcg(p, v); }  // static particles never move
 
 __device__ __forceinline__ float matv(const TypeArrays &a, int slot, unsigned i) {
@@ -26,13 +45,14 @@ __device__ __forceinline__ float matv(const TypeArrays &a, int slot, unsigned i)
 __device__ __forceinline__ float xpbd_alpha(float k, float dt) { return (k != 0.0f) ? 1.0f / (k * dt * dt) : 0.0f; }
 
 // Gather -> project -> scatter for constraint i (index into the type's arrays).
-template <int T>
-__device__ __forceinline__ void process_constraint(float4 *__restrict__ pos, const TypeArrays &a, unsigned i, float dt,
+template <int T, bool CA, bool WAIT = false>
+__device__ __forceinline__ void process_constraint(float4 *pos, const TypeArrays &a, unsigned i, float dt,
                                                    bool iterZero) {
     if (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) {
         const uint2 b = __ldg(a.idx2 + i);
-        float4 p0 = ldp(pos + b.x), p1 = ldp(pos + b.y);
         const float rest = __ldg(a.gs[0] + i);
+        if (WAIT) pdl_wait_after(b.x, rest);
+        float4 p0 = ldp<CA>(pos + b.x), p1 = ldp<CA>(pos + b.y);
         const float k = matv(a, 0, i);
         if (T == PBD_DISTANCE) {
             project_distance(p0, p1, rest, k);
@@ -44,8 +64,9 @@ __device__ __forceinline__ void process_constraint(float4 *__restrict__ pos, con
         stp(pos + b.x, p0); stp(pos + b.y, p1);
     } else if (T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) {
         const unsigned b0 = __ldg(a.idx3[0] + i), b1 = __ldg(a.idx3[1] + i), b2 = __ldg(a.idx3[2] + i);
-        float4 p0 = ldp(pos + b0), p1 = ldp(pos + b1), p2 = ldp(pos + b2);
         const float4 inv = __ldg(a.gv[0] + i);
+        if (WAIT) pdl_wait_after(b0 + b1 + b2, inv.x);
+        float4 p0 = ldp<CA>(pos + b0), p1 = ldp<CA>(pos + b1), p2 = ldp<CA>(pos + b2);
         if (T == PBD_FEMTRIANGLE) {
             const FemTriMaterial m = femtri_material(matv(a, 0, i), matv(a, 1, i), matv(a, 2, i), matv(a, 3, i), matv(a, 4, i));
             project_femtriangle(p0, p1, p2, __ldg(a.gs[0] + i), inv, m);
@@ -55,16 +76,24 @@ __device__ __forceinline__ void process_constraint(float4 *__restrict__ pos, con
         stp(pos + b0, p0); stp(pos + b1, p1); stp(pos + b2, p2);
     } else {
         const uint4 b = __ldg(a.idx4 + i);
-        float4 p0 = ldp(pos + b.x), p1 = ldp(pos + b.y), p2 = ldp(pos + b.z), p3 = ldp(pos + b.w);
+        // stream the per-constraint constants before waiting on the predecessor kernel (they never change during a step)
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+        float s0 = 0.0f, s1 = 0.0f;
+        if (T == PBD_DIHEDRAL || T == PBD_VOLUME || T == PBD_VOLUME_XPBD) s0 = __ldg(a.gs[0] + i);
+        if (T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD) g0 = __ldg(a.gv[0] + i);
+        if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) { g0 = __ldg(a.gv[0] + i); g1 = __ldg(a.gv[1] + i); s0 = __ldg(a.gs[0] + i); }
+        if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD) s1 = __ldg(a.gs[1] + i);
+        if (WAIT) pdl_wait_after(b.x, g0.x + g1.x + s0 + s1);
+        float4 p0 = ldp<CA>(pos + b.x), p1 = ldp<CA>(pos + b.y), p2 = ldp<CA>(pos + b.z), p3 = ldp<CA>(pos + b.w);
         if (T == PBD_DIHEDRAL) {
-            project_dihedral(p0, p1, p2, p3, __ldg(a.gs[0] + i), matv(a, 0, i));
+            project_dihedral(p0, p1, p2, p3, s0, matv(a, 0, i));
         } else if (T == PBD_VOLUME) {
             float dummy = 0.0f;
-            project_volume<false>(p0, p1, p2, p3, __ldg(a.gs[0] + i), matv(a, 0, i), 0.0f, dummy);
+            project_volume<false>(p0, p1, p2, p3, s0, matv(a, 0, i), 0.0f, dummy);
         } else if (T == PBD_VOLUME_XPBD) {
             float lam = iterZero ? 0.0f : __ldcg(a.lambda + i);
             const float k = matv(a, 0, i);
-            project_volume<true>(p0, p1, p2, p3, __ldg(a.gs[0] + i), k, xpbd_alpha(k, dt), lam);
+            project_volume<true>(p0, p1, p2, p3, s0, k, xpbd_alpha(k, dt), lam);
             __stcg(a.lambda + i, lam);
         } else if (T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD) {
             constexpr bool X = (T == PBD_ISOBENDING_XPBD);
@@ -73,29 +102,29 @@ __device__ __forceinline__ void process_constraint(float4 *__restrict__ pos, con
             if (X && !iterZero) lam = __ldcg(a.lambda + i);
             const float alpha = X ? xpbd_alpha(k, dt) : 0.0f;
             if (a.variant == 0) {
-                project_isobending_rank1<X>(p0, p1, p2, p3, __ldg(a.gv[0] + i), k, alpha, lam);
+                project_isobending_rank1<X>(p0, p1, p2, p3, g0, k, alpha, lam);
             } else {
-                project_isobending_fullq<X>(p0, p1, p2, p3, __ldg(a.gv[0] + i), __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), k, alpha, lam);
+                project_isobending_fullq<X>(p0, p1, p2, p3, g0, __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), k, alpha, lam);
             }
             if (X) __stcg(a.lambda + i, lam);
         } else if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD) {
             constexpr bool X = (T == PBD_FEMTET_XPBD);
-            const float4 m0 = __ldg(a.gv[0] + i), m1 = __ldg(a.gv[1] + i);
+            const float4 m0 = g0, m1 = g1;
             M3 inv;
             inv.m[0][0] = m0.x; inv.m[0][1] = m0.y; inv.m[0][2] = m0.z; inv.m[1][0] = m0.w;
             inv.m[1][1] = m1.x; inv.m[1][2] = m1.y; inv.m[2][0] = m1.z; inv.m[2][1] = m1.w;
-            inv.m[2][2] = __ldg(a.gs[0] + i);
-            const float vol = __ldg(a.gs[1] + i);
+            inv.m[2][2] = s0;
+            const float vol = s1;
             float lam = 0.0f;
             if (X && !iterZero) lam = __ldcg(a.lambda + i);
             project_femtet<X>(p0, p1, p2, p3, vol, inv, matv(a, 0, i), matv(a, 1, i), dt, lam);
             if (X) __stcg(a.lambda + i, lam);
         } else if (T == PBD_STRAINTET) {
-            const float4 m0 = __ldg(a.gv[0] + i), m1 = __ldg(a.gv[1] + i);
+            const float4 m0 = g0, m1 = g1;
             M3 inv;
             inv.m[0][0] = m0.x; inv.m[0][1] = m0.y; inv.m[0][2] = m0.z; inv.m[1][0] = m0.w;
             inv.m[1][1] = m1.x; inv.m[1][2] = m1.y; inv.m[2][0] = m1.z; inv.m[2][1] = m1.w;
-            inv.m[2][2] = __ldg(a.gs[0] + i);
+            inv.m[2][2] = s0;
             project_straintet(p0, p1, p2, p3, inv, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i) != 0.0f, matv(a, 3, i) != 0.0f);
         }
         stp(pos + b.x, p0); stp(pos + b.y, p1); stp(pos + b.z, p2); stp(pos + b.w, p3);
@@ -104,19 +133,23 @@ __device__ __forceinline__ void process_constraint(float4 *__restrict__ pos, con
 
 constexpr int kProjectThreads = 256;
 
-template <int T>
-__global__ void __launch_bounds__(kProjectThreads) k_project(float4 *__restrict__ pos, TypeArrays a, unsigned first,
+template <int T, bool CA>
+__global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeArrays a, unsigned first,
                                                              unsigned count, float dt, int iterZero) {
+    pdl_launch_dependents();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) process_constraint<T>(pos, a, first + i, dt, iterZero != 0);
+    if (i < count) process_constraint<T, CA, true>(pos, a, first + i, dt, iterZero != 0);
+    // threads without a constraint simply exit: an exited thread counts as having passed the dependency
 }
 
 // lastX = oldX; oldX = x; if (mass != 0) { v += g h; x += v h }
 __global__ void __launch_bounds__(256) k_integrate(float4 *__restrict__ pos, float4 *__restrict__ vel,
                                                    float4 *__restrict__ oldp, float4 *__restrict__ lastp, unsigned n,
                                                    float h, float gx, float gy, float gz, int trackLast) {
+    pdl_launch_dependents();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    pdl_wait();
     float4 x = __ldcg(pos + i);
     if (trackLast) __stcs(lastp + i, __ldcs(oldp + i));
     __stcg(oldp + i, x);
@@ -133,8 +166,10 @@ __global__ void __launch_bounds__(256) k_integrate(float4 *__restrict__ pos, flo
 __global__ void __launch_bounds__(256) k_velocity(const float4 *__restrict__ pos, float4 *__restrict__ vel,
                                                   const float4 *__restrict__ oldp, const float4 *__restrict__ lastp,
                                                   unsigned n, float invH, int secondOrder) {
+    pdl_launch_dependents();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    pdl_wait();
     const float4 x = __ldcg(pos + i);
     if (x.w == 0.0f) return;  // invMass == 0  <=>  mass == 0 (ParticleData::setMass keeps them consistent)
     const float4 o = __ldcg(oldp + i);

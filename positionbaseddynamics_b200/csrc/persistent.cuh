@@ -40,19 +40,21 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsign
     target += gridDim.x;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        __threadfence();  // release: publish this CTA's stores
         atomicAdd(counter, 1ull);
         while (ld_acquire_u64(counter) < target) { }
+        __threadfence();  // acquire side: gpu-scope fence also drops this SM's L1 lines (stale particle data of the last phase)
     }
     __syncthreads();
 }
 
-template <int T>
+template <int T, bool CA>
 __device__ __forceinline__ void sweep_bucket(float4 *pos, const TypeArrays &ta, const Bucket &b, float h, bool iterZero,
                                              unsigned tid, unsigned stride) {
-    for (unsigned i = tid; i < b.count; i += stride) process_constraint<T>(pos, ta, b.first + i, h, iterZero);
+    for (unsigned i = tid; i < b.count; i += stride) process_constraint<T, CA>(pos, ta, b.first + i, h, iterZero);
 }
 
+template <bool CA>
 __global__ void __launch_bounds__(kPersistentThreads) k_step_persistent(PersistentArgs a) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned stride = gridDim.x * blockDim.x;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(kPersistentThreads) k_step_persistent(Persiste
                 if (b.colour != colour) { grid_barrier(a.barrier, target); colour = b.colour; }
                 const TypeArrays ta = a.types[b.type];
                 switch (b.type) {
-#define SB(T) case T: sweep_bucket<T>(a.pos, ta, b, a.h, iterZero, tid, stride); break;
+#define SB(T) case T: sweep_bucket<T, CA>(a.pos, ta, b, a.h, iterZero, tid, stride); break;
                     SB(PBD_DISTANCE) SB(PBD_DISTANCE_XPBD) SB(PBD_DIHEDRAL) SB(PBD_ISOBENDING) SB(PBD_ISOBENDING_XPBD)
                     SB(PBD_FEMTRIANGLE) SB(PBD_STRAINTRIANGLE) SB(PBD_VOLUME) SB(PBD_VOLUME_XPBD) SB(PBD_FEMTET)
                     SB(PBD_FEMTET_XPBD) SB(PBD_STRAINTET)
