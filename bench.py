@@ -36,12 +36,33 @@ def parse():
     ap.add_argument("--size", type=int, default=1000, help="cloth is size x size particles (cfg2 = 1000)")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "launch"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"],
+                    help="cfg2 is the BASELINE.json metric configuration (default); cfg1/cfg3 are side measurements for DESIGN.md")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
 
+WORKLOAD = "cfg2"
+
+
+def build_scene(m, size, iters):
+    """Build the selected workload on any object with the common builder surface; returns (sub_steps, iterations)."""
+    import scenes
+    if WORKLOAD == "cfg1":
+        scenes.cfg1(m, 50); return 1, 5
+    if WORKLOAD == "cfg3":
+        scenes.cfg3(m); return 10, 5
+    scenes.cfg2(m, size, iters); return 1, iters
+
+
 def workload_config(size, iters, n_gpus):
+    if WORKLOAD == "cfg1":
+        return {"workload": "cfg1", "scene": "ClothDemo 50x50, Distance + IsometricBending (PBD)", "sub_steps": 1, "iterations": 5, "dt": 0.005,
+                "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus, "l2": "L2-resident working set; L2 flushed between timed steps: no (latency-bound config)"}
+    if WORKLOAD == "cfg3":
+        return {"workload": "cfg3", "scene": "tet bar 101x21x21 = 200,000 tets, FEMTet(E=1e6, nu=0.3) + Volume per tet", "sub_steps": 10, "iterations": 5,
+                "dt": 0.005, "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus, "l2": "L2-resident working set (~16 MB); latency-bound config"}
     return {"workload": "cfg2", "scene": "cloth %dx%d particles, Distance_XPBD(k=1e5)+IsometricBending_XPBD(k=100)" % (size, size),
             "sub_steps": 1, "iterations": iters, "dt": 0.005, "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus,
             "l2": "inputs larger than L2: the per-sweep constraint stream (~192 MB at 1000x1000) exceeds the 126 MB L2"}
@@ -59,7 +80,7 @@ def cpu_arm(size, iters, steps, warmup):
         if not pyoracle.available("oracle", "f32"):
             pyoracle.build(ref=False)
         kind, lib = "port", pyoracle.CpuPbd("oracle", "f32")
-    scenes.cfg2(lib, size, iters)
+    sub_steps, iters = build_scene(lib, size, iters)
     ncons = lib.num_constraints()
     lib.init_groups()
     # "all the host threads it can use": the reference forks/joins an OpenMP team per colour group, which stops scaling
@@ -76,7 +97,7 @@ def cpu_arm(size, iters, steps, warmup):
     if warmup > 1:
         lib.step(warmup - 1)
     secs = lib.step(steps)
-    proj = ncons * 1 * iters * steps
+    proj = ncons * sub_steps * iters * steps
     return {"value": proj / secs, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": 1e3 * secs / steps,
             "sample": "%d step(s) of the %dx%d cloth (%d constraints x %d iterations) after warm-up, fp32 build, OMP threads=%d (fastest of %s on %d hardware threads)"
                       % (steps, size, size, ncons, iters, cores, cand, ncpu)}
@@ -175,7 +196,7 @@ def run_b200(args):
     # ---- scene (host model mirror, C++) -> engine -----------------------------------------------------------------
     t0 = time.time()
     hm = HostModel()
-    scenes.cfg2(hm, args.size, args.iters)
+    sub_steps, args.iters = build_scene(hm, args.size, args.iters)
     types, bodies, params, _ = hm.constraints()
     off, ids = hm.groups()
     n = hm.num_particles(); ncons = len(types)
@@ -185,12 +206,12 @@ def run_b200(args):
     eng.set_particles(x0, mass)
     eng.add_flat(types, bodies, params)
     eng.set_groups(off, ids)
-    eng.set_params(dt=0.005, sub_steps=1, max_iter=args.iters)
+    eng.set_params(dt=0.005, sub_steps=sub_steps, max_iter=args.iters)
     del types, bodies, params
     hm.close()
 
     modes = {"graph": _capi.MODE_GRAPH, "persistent": _capi.MODE_PERSISTENT, "launch": _capi.MODE_LAUNCH}
-    proj_per_step = ncons * 1 * args.iters
+    proj_per_step = ncons * sub_steps * args.iters
 
     def timed(mode, steps, warmup):
         eng.set_mode(mode)
@@ -281,10 +302,12 @@ def run_b200(args):
             ms_t_, mi, mv, l_ = eng.profile_step()
             tms += ms_t_; tl += l_
         dom = int(np.argmax(tms))
-        per_proj = {_capi.DISTANCE_XPBD: 84.0, _capi.ISOBENDING_XPBD: 168.0}.get(dom)
+        per_proj = {_capi.DISTANCE: 76.0, _capi.DISTANCE_XPBD: 84.0, _capi.DIHEDRAL: 148.0, _capi.ISOBENDING: 160.0, _capi.ISOBENDING_XPBD: 168.0,
+                    _capi.FEMTRIANGLE: 128.0, _capi.STRAINTRIANGLE: 124.0, _capi.VOLUME: 148.0, _capi.VOLUME_XPBD: 156.0, _capi.FEMTET: 184.0,
+                    _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0}.get(dom)  # DESIGN.md byte table
         cnt = st.constraints_per_type[dom]
         k_ms = float(tms[dom] / max(tl[dom], 1))
-        k_bytes = float(cnt * per_proj * args.iters * reps / max(tl[dom], 1)) if per_proj else None
+        k_bytes = float(cnt * per_proj * args.iters * sub_steps * reps / max(tl[dom], 1)) if per_proj else None
         roof = {"kernel": "k_project<%s>" % _capi.TYPE_NAMES[dom], "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                 "share_of_step": float(tms[dom] / max(tms.sum() + mi + mv, 1e-9))}
         eng.set_mode(mode)
@@ -318,6 +341,7 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse()
+    WORKLOAD = a.workload
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -1,0 +1,228 @@
+"""pyPBD-compatible facade (camelCase names of the reference's Python module `pypbd`) over the host model mirror.
+
+Covers the calls the reference's own example scripts make for the accelerated path
+(pyPBD/examples/cloth_model.py:18-124, beam_model.py:15-87):
+  Simulation.getCurrent/initDefault/getModel/getTimeStep/reset, TimeManager.getCurrent().getTime/setTimeStepSize,
+  SimulationModel.addRegularTriangleModel/addRegularTetModel/addTriangleModel/addTetModel/addClothConstraints/
+  addBendingConstraints/addSolidConstraints/add<X>Constraint/getParticles/getTriangleModels/getTetModels/getConstraints/
+  getConstraintGroups/cleanup, ParticleData.setMass/getMass/getPosition/setPosition/getVertices/size,
+  TimeStepController.NUM_SUB_STEPS/MAX_ITERATIONS/..., ts.setValueUInt/getValueUInt/setValueInt, ts.step(model).
+GUI, scene files, rigid bodies and collision detection are not part of this path.
+"""
+import numpy as np
+from . import _capi, model as _m
+from ._capi import PbdError  # noqa: F401
+
+
+class ParticleData:
+    def __init__(self, host):
+        self._h = host
+
+    def size(self):
+        return self._h.num_particles()
+
+    getNumberOfParticles = size
+
+    def setMass(self, i, mass):
+        self._h.set_mass(i, mass)
+
+    def getMass(self, i):
+        return float(_m._l().pbdm_get_mass(self._h._h, int(i)))
+
+    def getInvMass(self, i):
+        return float(_m._l().pbdm_get_inv_mass(self._h._h, int(i)))
+
+    def _get(self, attr, i):
+        out = np.zeros(3, dtype=np.float32)
+        if _m._l().pbdm_get_particle(self._h._h, attr, int(i), _m._p(out)):
+            raise IndexError(i)
+        return out
+
+    def _set(self, attr, i, v):
+        v = _m._f32(v)
+        if _m._l().pbdm_set_particle(self._h._h, attr, int(i), _m._p(v)):
+            raise IndexError(i)
+
+    def getPosition(self, i): return self._get(_capi.ATTR_X, i)
+    def getPosition0(self, i): return self._get(_capi.ATTR_X0, i)
+    def getVelocity(self, i): return self._get(_capi.ATTR_V, i)
+    def getOldPosition(self, i): return self._get(_capi.ATTR_OLDX, i)
+    def getLastPosition(self, i): return self._get(_capi.ATTR_LASTX, i)
+    def setPosition(self, i, v): self._set(_capi.ATTR_X, i, v)
+    def setPosition0(self, i, v): self._set(_capi.ATTR_X0, i, v)
+    def setVelocity(self, i, v): self._set(_capi.ATTR_V, i, v)
+
+    def getVertices(self):
+        """Zero-copy view of the positions (pyPBD/ParticleDataModule.cpp:54-58); pulled from the device lazily."""
+        return self._h.vertices_view()
+
+
+class _Mesh:
+    def __init__(self, host, idx, tri):
+        self._h, self._i, self._tri = host, idx, tri
+
+    def numFaces(self): return _m._l().pbdm_tri_num_faces(self._h._h, self._i)
+    def numEdges(self): return (_m._l().pbdm_tri_num_edges if self._tri else _m._l().pbdm_tet_num_edges)(self._h._h, self._i)
+    def numTets(self): return _m._l().pbdm_tet_num_tets(self._h._h, self._i)
+    def getFaces(self): return self._h.tri_faces(self._i).reshape(-1)
+    def getTets(self): return self._h.tet_tets(self._i).reshape(-1)
+    def getEdges(self): return self._h.tri_edges(self._i) if self._tri else self._h.tet_edges(self._i)
+
+
+class TriangleModel:
+    def __init__(self, host, idx): self._h, self._i = host, idx
+    def getIndexOffset(self): return self._h.tri_index_offset(self._i)
+    def getParticleMesh(self): return _Mesh(self._h, self._i, True)
+    def updateMeshNormals(self, pd): pass  # rendering helper of the reference; no normals are kept on this path
+
+
+class TetModel:
+    def __init__(self, host, idx): self._h, self._i = host, idx
+    def getIndexOffset(self): return self._h.tet_index_offset(self._i)
+    def getParticleMesh(self): return _Mesh(self._h, self._i, False)
+
+
+class SimulationModel:
+    def __init__(self):
+        self._host = _m.HostModel()
+
+    def init(self): pass
+    def reset(self): _m._l().pbdm_model_reset(self._host._h)
+    def cleanup(self): _m._l().pbdm_model_cleanup(self._host._h)
+    def getParticles(self): return ParticleData(self._host)
+    def getTriangleModels(self): return [TriangleModel(self._host, i) for i in range(_m._l().pbdm_num_triangle_models(self._host._h))]
+    def getTetModels(self): return [TetModel(self._host, i) for i in range(_m._l().pbdm_num_tet_models(self._host._h))]
+
+    def addRegularTriangleModel(self, width, height, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1)):
+        self._host.add_regular_triangle_model(width, height, translation, rotation, scale)
+
+    def addRegularTetModel(self, width, height, depth, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1, 1)):
+        self._host.add_regular_tet_model(width, height, depth, translation, rotation, scale)
+
+    def addTriangleModel(self, points, indices):
+        self._host.add_triangle_model(np.asarray(points).reshape(-1, 3), np.asarray(indices).reshape(-1, 3))
+
+    def addTetModel(self, points, indices):
+        self._host.add_tet_model(np.asarray(points).reshape(-1, 3), np.asarray(indices).reshape(-1, 4))
+
+    def addClothConstraints(self, tm, clothMethod, distanceStiffness, xxStiffness, yyStiffness, xyStiffness, xyPoissonRatio, yxPoissonRatio,
+                            normalizeStretch, normalizeShear):
+        self._host.add_cloth_constraints(tm._i, clothMethod, distanceStiffness, xxStiffness, yyStiffness, xyStiffness, xyPoissonRatio,
+                                         yxPoissonRatio, normalizeStretch, normalizeShear)
+
+    def addBendingConstraints(self, tm, bendingMethod, stiffness):
+        self._host.add_bending_constraints(tm._i, bendingMethod, stiffness)
+
+    def addSolidConstraints(self, tm, solidMethod, stiffness, poissonRatio, volumeStiffness, normalizeStretch, normalizeShear):
+        self._host.add_solid_constraints(tm._i, solidMethod, stiffness, poissonRatio, volumeStiffness, normalizeStretch, normalizeShear)
+
+    def addDistanceConstraint(self, p1, p2, k): return bool(self._host.add_constraint(_capi.DISTANCE, [p1, p2], [k]))
+    def addDistanceConstraint_XPBD(self, p1, p2, k): return bool(self._host.add_constraint(_capi.DISTANCE_XPBD, [p1, p2], [k]))
+    def addDihedralConstraint(self, p1, p2, p3, p4, k): return bool(self._host.add_constraint(_capi.DIHEDRAL, [p1, p2, p3, p4], [k]))
+    def addIsometricBendingConstraint(self, p1, p2, p3, p4, k): return bool(self._host.add_constraint(_capi.ISOBENDING, [p1, p2, p3, p4], [k]))
+    def addIsometricBendingConstraint_XPBD(self, p1, p2, p3, p4, k): return bool(self._host.add_constraint(_capi.ISOBENDING_XPBD, [p1, p2, p3, p4], [k]))
+    def addFEMTriangleConstraint(self, p1, p2, p3, xx, yy, xy, nuxy, nuyx): return bool(self._host.add_constraint(_capi.FEMTRIANGLE, [p1, p2, p3], [xx, yy, xy, nuxy, nuyx]))
+    def addStrainTriangleConstraint(self, p1, p2, p3, xx, yy, xy, ns, nsh): return bool(self._host.add_constraint(_capi.STRAINTRIANGLE, [p1, p2, p3], [xx, yy, xy, float(ns), float(nsh)]))
+    def addVolumeConstraint(self, p1, p2, p3, p4, k): return bool(self._host.add_constraint(_capi.VOLUME, [p1, p2, p3, p4], [k]))
+    def addVolumeConstraint_XPBD(self, p1, p2, p3, p4, k): return bool(self._host.add_constraint(_capi.VOLUME_XPBD, [p1, p2, p3, p4], [k]))
+    def addFEMTetConstraint(self, p1, p2, p3, p4, k, nu): return bool(self._host.add_constraint(_capi.FEMTET, [p1, p2, p3, p4], [k, nu]))
+    def addFEMTetConstraint_XPBD(self, p1, p2, p3, p4, k, nu): return bool(self._host.add_constraint(_capi.FEMTET_XPBD, [p1, p2, p3, p4], [k, nu]))
+    def addStrainTetConstraint(self, p1, p2, p3, p4, ks, kh, ns, nsh): return bool(self._host.add_constraint(_capi.STRAINTET, [p1, p2, p3, p4], [ks, kh, float(ns), float(nsh)]))
+
+    def initConstraintGroups(self): self._host.init_groups()
+
+    def getConstraintGroups(self):
+        off, ids = self._host.groups()
+        return [ids[off[g]:off[g + 1]] for g in range(len(off) - 1)]
+
+    def getConstraints(self):
+        t, b, p, nb = self._host.constraints()
+        return [dict(type=_capi.TYPE_NAMES[int(t[i])], bodies=b[i][:nb[i]], params=p[i][:_capi.num_params(int(t[i]))]) for i in range(len(t))]
+
+    def numConstraints(self): return self._host.num_constraints()
+
+    # global setters (Simulation/SimulationModel.cpp:1351-1485)
+    def setClothStiffness(self, v): self._host.set_model_param(0, v)
+    def setClothStiffnessXX(self, v): self._host.set_model_param(1, v)
+    def setClothStiffnessYY(self, v): self._host.set_model_param(2, v)
+    def setClothStiffnessXY(self, v): self._host.set_model_param(3, v)
+    def setClothPoissonRatioXY(self, v): self._host.set_model_param(4, v)
+    def setClothPoissonRatioYX(self, v): self._host.set_model_param(5, v)
+    def setClothBendingStiffness(self, v): self._host.set_model_param(6, v)
+    def setSolidStiffness(self, v): self._host.set_model_param(9, v)
+    def setSolidPoissonRatio(self, v): self._host.set_model_param(10, v)
+    def setSolidVolumeStiffness(self, v): self._host.set_model_param(11, v)
+
+
+class TimeManager:
+    _current = None
+
+    def __init__(self, ts): self._ts = ts
+
+    @staticmethod
+    def getCurrent(): return TimeManager(Simulation.getCurrent().getTimeStep())
+    def getTime(self): return self._ts._ts.get_time()
+    def setTime(self, t): self._ts._ts.set_time(t)
+    def getTimeStepSize(self): return self._ts._ts.get_time_step_size()
+    def setTimeStepSize(self, h): self._ts._ts.set_time_step_size(h)
+
+
+class TimeStepController:
+    NUM_SUB_STEPS, MAX_ITERATIONS, MAX_ITERATIONS_V, VELOCITY_UPDATE_METHOD = 0, 1, 2, 3
+    ENUM_VUPDATE_FIRST_ORDER, ENUM_VUPDATE_SECOND_ORDER = 0, 1
+
+    def __init__(self, device=0, stream=None):
+        self._ts = _m.TimeStep(device, stream)   # raises PbdError without a CUDA device: no CPU fallback
+
+    def init(self): pass
+    def reset(self): pass
+    def setValueUInt(self, pid, v): self._ts.set_uint(pid, v)
+    def getValueUInt(self, pid): return self._ts.get_uint(pid)
+    def setValueInt(self, pid, v): self._ts.set_int(pid, v)
+    def getValueInt(self, pid): return self._ts.get_int(pid)
+    def step(self, model): self._ts.step(model._host)
+
+
+class Simulation:
+    GRAVITATION = 0
+    _current = None
+
+    def __init__(self):
+        self._model = None; self._ts = None; self._gravity = (0.0, -9.81, 0.0); self._device = 0
+
+    @staticmethod
+    def getCurrent():
+        if Simulation._current is None:
+            Simulation._current = Simulation()
+        return Simulation._current
+
+    @staticmethod
+    def hasCurrent(): return Simulation._current is not None
+
+    def initDefault(self, device=0):
+        self._model = SimulationModel(); self._device = device
+
+    def getModel(self): return self._model
+    def setModel(self, m): self._model = m
+
+    def getTimeStep(self):
+        if self._ts is None:
+            self._ts = TimeStepController(self._device)
+            self._ts._ts.set_gravitation(self._gravity)
+        return self._ts
+
+    def setTimeStep(self, ts): self._ts = ts
+
+    def setVecValueReal(self, pid, v):
+        if pid == Simulation.GRAVITATION:
+            self._gravity = tuple(float(c) for c in v)
+            if self._ts is not None:
+                self._ts._ts.set_gravitation(self._gravity)
+
+    def getVecValueReal(self, pid): return list(self._gravity)
+
+    def reset(self):
+        if self._model is not None:
+            self._model.reset()
+        if self._ts is not None:
+            self._ts._ts.set_time(0.0)

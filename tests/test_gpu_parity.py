@@ -226,5 +226,5 @@ def test_empty_and_constraint_free_models():
     # semi-implicit Euler with 2 substeps of h=0.0025: y drop = g h^2 (1+2+3+4)
     h = 0.0025
     expect = -9.81 * h * h * 10
-    assert np.allclose(x[:, 1] - x0[:, 1], expect, rtol=1e-5, atol=1e-7)
+    assert np.allclose(x[:, 1] - x0[:, 1], expect, rtol=1e-4, atol=5e-7), (x[:, 1] - x0[:, 1], expect)  # fp32 ulp of x (~1) is 6e-8
     m.close()
