@@ -96,7 +96,7 @@ struct pbd_engine {
     pbd_stats stats{};
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timingPending = false;
-    int persistentBlocksPerSM = 0;
+    int persistentThreads = 0;
     bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
     bool gatherCA = true;                 // particle gathers through L1 (tuning knob: PBD_B200_GATHER=cg selects L2-only loads)
     unsigned coloursUsed = 0;             // colours that own at least one bucket
@@ -137,6 +137,7 @@ extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
     cudaEventCreate(&e->evStart); cudaEventCreate(&e->evStop);
     if (const char *g = getenv("PBD_B200_GATHER")) e->gatherCA = (strcmp(g, "cg") != 0);
     if (const char *g = getenv("PBD_B200_PDL")) e->usePDL = (strcmp(g, "0") != 0);
+    if (const char *g = getenv("PBD_B200_PTHREADS")) e->persistentThreads = atoi(g);
     *out = e;
     return 0;
 }
@@ -591,11 +592,6 @@ static int flatten(pbd_engine *e) {
 
     // 3. bucket table + type arrays for the persistent kernel
     CKE(upload_vec(e->dBuckets, e->buckets, e->stream));
-    {
-        std::vector<TypeArrays> ta(PBD_NUM_TYPES);
-        for (int t = 0; t < PBD_NUM_TYPES; t++) ta[t] = e->dev[t].arrays;
-        CKE(upload_vec(e->dTypeArrays, ta, e->stream));
-    }
     CKE(e->dBarrier.alloc(256));
     CK(cudaMemsetAsync(e->dBarrier.p, 0, 256, e->stream));
     e->barrierBase = 0;
@@ -677,33 +673,48 @@ static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long lo
     return 0;
 }
 
+// pick the smallest compiled type mask that covers the constraint types present in the model
+template <unsigned MASK, int THREADS>
+static int launch_persistent(pbd_engine *e, cudaStream_t s, PersistentArgs &pa) {
+    void *fn = e->gatherCA ? (void *)k_step_persistent<MASK, true, THREADS> : (void *)k_step_persistent<MASK, false, THREADS>;
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, THREADS, 0));
+    if (nb < 1) return fail("persistent kernel does not fit on an SM");
+    const int grid = e->smCount;  // one CTA per SM, all co-resident (cooperative launch)
+    // barriers per launch: per substep one after the prologue, one per colour phase of every sweep
+    const unsigned long long perSub = e->buckets.empty() ? 1ull : 1ull + (unsigned long long)e->maxIter * e->coloursUsed;
+    pa.barrierBase = e->barrierBase;
+    e->barrierBase += perSub * e->subSteps * (unsigned long long)grid;
+    void *args[] = {&pa};
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(THREADS), args, 0, s));
+    return 0;
+}
+
 static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
     const float h = e->dt / (float)e->subSteps;
     const float invH = (float)(1.0 / (double)h);
-    if (e->persistentBlocksPerSM == 0) {
-        int nb = 0;
-        if (e->gatherCA) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step_persistent<true>, kPersistentThreads, 0));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step_persistent<false>, kPersistentThreads, 0));
-        if (nb < 1) return fail("persistent kernel does not fit on an SM");
-        e->persistentBlocksPerSM = nb;
-    }
     PersistentArgs pa;
     pa.pos = (float4 *)e->pos.p; pa.vel = (float4 *)e->vel.p; pa.oldp = (float4 *)e->oldp.p; pa.lastp = (float4 *)e->lastp.p;
-    pa.n = e->n; pa.types = (const TypeArrays *)e->dTypeArrays.p; pa.buckets = (const Bucket *)e->dBuckets.p;
+    pa.n = e->n; pa.buckets = (const Bucket *)e->dBuckets.p;
     pa.nBuckets = (unsigned)e->buckets.size(); pa.subSteps = e->subSteps; pa.maxIter = e->maxIter;
     pa.h = h; pa.invH = invH; pa.gx = e->g[0]; pa.gy = e->g[1]; pa.gz = e->g[2];
     pa.secondOrder = e->velMethod; pa.trackLast = track_last(e);
     pa.barrier = (unsigned long long *)e->dBarrier.p;
-    pa.barrierBase = e->barrierBase;
-    const int grid = e->smCount * e->persistentBlocksPerSM;
-    // barriers per launch: per substep one after the prologue and one per colour phase of every sweep
-    const unsigned long long barriers = (unsigned long long)e->subSteps * (1ull + (unsigned long long)e->maxIter * std::max(e->coloursUsed, 1u));
-    e->barrierBase += barriers * (unsigned long long)grid;
-    void *args[] = {&pa};
-    void *fn = e->gatherCA ? (void *)k_step_persistent<true> : (void *)k_step_persistent<false>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistentThreads), args, 0, s));
+    unsigned present = 0;
+    for (int t = 0; t < PBD_NUM_TYPES; t++) { pa.types[t] = e->dev[t].arrays; if (e->dev[t].count) present |= 1u << t; }
     *launches = 1;
-    return 0;
+    const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
+    if ((present & ~kMaskClothXPBD) == 0) {
+        if (pt == 512) return launch_persistent<kMaskClothXPBD, 512>(e, s, pa);
+        if (pt == 768) return launch_persistent<kMaskClothXPBD, 768>(e, s, pa);
+        return launch_persistent<kMaskClothXPBD, 1024>(e, s, pa);
+    }
+    if ((present & ~kMaskLight) == 0) {
+        if (pt == 512) return launch_persistent<kMaskLight, 512>(e, s, pa);
+        return launch_persistent<kMaskLight, 1024>(e, s, pa);
+    }
+    if (pt == 256) return launch_persistent<kMaskAll, 256>(e, s, pa);
+    return launch_persistent<kMaskAll, 512>(e, s, pa);
 }
 
 static int ensure_graph(pbd_engine *e, unsigned long long *launchesPerStep) {

@@ -44,91 +44,84 @@ __device__ __forceinline__ float matv(const TypeArrays &a, int slot, unsigned i)
 }
 __device__ __forceinline__ float xpbd_alpha(float k, float dt) { return (k != 0.0f) ? 1.0f / (k * dt * dt) : 0.0f; }
 
-// Gather -> project -> scatter for constraint i (index into the type's arrays).
-template <int T, bool CA, bool WAIT = false>
-__device__ __forceinline__ void process_constraint(float4 *pos, const TypeArrays &a, unsigned i, float dt,
-                                                   bool iterZero) {
+// What a constraint streams from HBM before it touches any particle: indices + per-constraint constants.  These never
+// change during a step, so they can be fetched ahead of the dependency on the previous colour phase (before the PDL
+// wait in k_project, before the grid barrier in the persistent kernel).
+struct Streamed {
+    uint4 b;        // particle indices (x,y[,z[,w]])
+    float4 g0, g1;  // float4 geometry (Kp / invRestMat rows)
+    float s0, s1;   // scalar geometry (rest length / angle / volume / area / invRestMat(2,2))
+};
+
+template <int T>
+__device__ __forceinline__ Streamed load_streamed(const TypeArrays &a, unsigned i) {
+    Streamed s;
+    s.g0 = make_float4(0.f, 0.f, 0.f, 0.f); s.g1 = s.g0; s.s0 = 0.0f; s.s1 = 0.0f;
     if (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) {
         const uint2 b = __ldg(a.idx2 + i);
-        const float rest = __ldg(a.gs[0] + i);
-        if (WAIT) pdl_wait_after(b.x, rest);
-        float4 p0 = ldp<CA>(pos + b.x), p1 = ldp<CA>(pos + b.y);
-        const float k = matv(a, 0, i);
-        if (T == PBD_DISTANCE) {
-            project_distance(p0, p1, rest, k);
-        } else {
-            float lam = iterZero ? 0.0f : __ldcg(a.lambda + i);
-            project_distance_xpbd(p0, p1, rest, xpbd_alpha(k, dt), lam);
-            __stcg(a.lambda + i, lam);
-        }
-        stp(pos + b.x, p0); stp(pos + b.y, p1);
+        s.b = make_uint4(b.x, b.y, 0u, 0u);
+        s.s0 = __ldg(a.gs[0] + i);
     } else if (T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) {
-        const unsigned b0 = __ldg(a.idx3[0] + i), b1 = __ldg(a.idx3[1] + i), b2 = __ldg(a.idx3[2] + i);
-        const float4 inv = __ldg(a.gv[0] + i);
-        if (WAIT) pdl_wait_after(b0 + b1 + b2, inv.x);
-        float4 p0 = ldp<CA>(pos + b0), p1 = ldp<CA>(pos + b1), p2 = ldp<CA>(pos + b2);
-        if (T == PBD_FEMTRIANGLE) {
-            const FemTriMaterial m = femtri_material(matv(a, 0, i), matv(a, 1, i), matv(a, 2, i), matv(a, 3, i), matv(a, 4, i));
-            project_femtriangle(p0, p1, p2, __ldg(a.gs[0] + i), inv, m);
-        } else {
-            project_straintriangle(p0, p1, p2, inv, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i), matv(a, 3, i) != 0.0f, matv(a, 4, i) != 0.0f);
-        }
-        stp(pos + b0, p0); stp(pos + b1, p1); stp(pos + b2, p2);
+        s.b = make_uint4(__ldg(a.idx3[0] + i), __ldg(a.idx3[1] + i), __ldg(a.idx3[2] + i), 0u);
+        s.g0 = __ldg(a.gv[0] + i);
+        if (T == PBD_FEMTRIANGLE) s.s0 = __ldg(a.gs[0] + i);
     } else {
-        const uint4 b = __ldg(a.idx4 + i);
-        // stream the per-constraint constants before waiting on the predecessor kernel (they never change during a step)
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-        float s0 = 0.0f, s1 = 0.0f;
-        if (T == PBD_DIHEDRAL || T == PBD_VOLUME || T == PBD_VOLUME_XPBD) s0 = __ldg(a.gs[0] + i);
-        if (T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD) g0 = __ldg(a.gv[0] + i);
-        if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) { g0 = __ldg(a.gv[0] + i); g1 = __ldg(a.gv[1] + i); s0 = __ldg(a.gs[0] + i); }
-        if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD) s1 = __ldg(a.gs[1] + i);
-        if (WAIT) pdl_wait_after(b.x, g0.x + g1.x + s0 + s1);
-        float4 p0 = ldp<CA>(pos + b.x), p1 = ldp<CA>(pos + b.y), p2 = ldp<CA>(pos + b.z), p3 = ldp<CA>(pos + b.w);
-        if (T == PBD_DIHEDRAL) {
-            project_dihedral(p0, p1, p2, p3, s0, matv(a, 0, i));
-        } else if (T == PBD_VOLUME) {
-            float dummy = 0.0f;
-            project_volume<false>(p0, p1, p2, p3, s0, matv(a, 0, i), 0.0f, dummy);
-        } else if (T == PBD_VOLUME_XPBD) {
-            float lam = iterZero ? 0.0f : __ldcg(a.lambda + i);
-            const float k = matv(a, 0, i);
-            project_volume<true>(p0, p1, p2, p3, s0, k, xpbd_alpha(k, dt), lam);
-            __stcg(a.lambda + i, lam);
-        } else if (T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD) {
-            constexpr bool X = (T == PBD_ISOBENDING_XPBD);
-            const float k = matv(a, 0, i);
-            float lam = 0.0f;
-            if (X && !iterZero) lam = __ldcg(a.lambda + i);
-            const float alpha = X ? xpbd_alpha(k, dt) : 0.0f;
-            if (a.variant == 0) {
-                project_isobending_rank1<X>(p0, p1, p2, p3, g0, k, alpha, lam);
-            } else {
-                project_isobending_fullq<X>(p0, p1, p2, p3, g0, __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), k, alpha, lam);
-            }
-            if (X) __stcg(a.lambda + i, lam);
-        } else if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD) {
-            constexpr bool X = (T == PBD_FEMTET_XPBD);
-            const float4 m0 = g0, m1 = g1;
-            M3 inv;
-            inv.m[0][0] = m0.x; inv.m[0][1] = m0.y; inv.m[0][2] = m0.z; inv.m[1][0] = m0.w;
-            inv.m[1][1] = m1.x; inv.m[1][2] = m1.y; inv.m[2][0] = m1.z; inv.m[2][1] = m1.w;
-            inv.m[2][2] = s0;
-            const float vol = s1;
-            float lam = 0.0f;
-            if (X && !iterZero) lam = __ldcg(a.lambda + i);
-            project_femtet<X>(p0, p1, p2, p3, vol, inv, matv(a, 0, i), matv(a, 1, i), dt, lam);
-            if (X) __stcg(a.lambda + i, lam);
-        } else if (T == PBD_STRAINTET) {
-            const float4 m0 = g0, m1 = g1;
-            M3 inv;
-            inv.m[0][0] = m0.x; inv.m[0][1] = m0.y; inv.m[0][2] = m0.z; inv.m[1][0] = m0.w;
-            inv.m[1][1] = m1.x; inv.m[1][2] = m1.y; inv.m[2][0] = m1.z; inv.m[2][1] = m1.w;
-            inv.m[2][2] = s0;
-            project_straintet(p0, p1, p2, p3, inv, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i) != 0.0f, matv(a, 3, i) != 0.0f);
-        }
-        stp(pos + b.x, p0); stp(pos + b.y, p1); stp(pos + b.z, p2); stp(pos + b.w, p3);
+        s.b = __ldg(a.idx4 + i);
+        if (T == PBD_DIHEDRAL || T == PBD_VOLUME || T == PBD_VOLUME_XPBD) s.s0 = __ldg(a.gs[0] + i);
+        if (T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD) s.g0 = __ldg(a.gv[0] + i);
+        if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) { s.g0 = __ldg(a.gv[0] + i); s.g1 = __ldg(a.gv[1] + i); s.s0 = __ldg(a.gs[0] + i); }
+        if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD) s.s1 = __ldg(a.gs[1] + i);
     }
+    return s;
+}
+
+// Gather -> project -> scatter for constraint i (index into the type's arrays) whose streamed part is already here.
+template <int T, bool CA>
+__device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &a, unsigned i, const Streamed &s, float dt,
+                                                 bool iterZero) {
+    constexpr bool XPBD = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
+    constexpr int NB = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 2 : ((T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) ? 3 : 4);
+    float4 p0 = ldp<CA>(pos + s.b.x), p1 = ldp<CA>(pos + s.b.y), p2, p3;
+    if (NB >= 3) p2 = ldp<CA>(pos + s.b.z);
+    if (NB >= 4) p3 = ldp<CA>(pos + s.b.w);
+    float lam = 0.0f;
+    if (XPBD && !iterZero) lam = __ldcg(a.lambda + i);  // m_lambda; zero at the first sweep of a substep (Constraints.cpp:1241-1242)
+
+    if (T == PBD_DISTANCE) {
+        project_distance(p0, p1, s.s0, matv(a, 0, i));
+    } else if (T == PBD_DISTANCE_XPBD) {
+        project_distance_xpbd(p0, p1, s.s0, xpbd_alpha(matv(a, 0, i), dt), lam);
+    } else if (T == PBD_FEMTRIANGLE) {
+        const FemTriMaterial m = femtri_material(matv(a, 0, i), matv(a, 1, i), matv(a, 2, i), matv(a, 3, i), matv(a, 4, i));
+        project_femtriangle(p0, p1, p2, s.s0, s.g0, m);
+    } else if (T == PBD_STRAINTRIANGLE) {
+        project_straintriangle(p0, p1, p2, s.g0, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i), matv(a, 3, i) != 0.0f, matv(a, 4, i) != 0.0f);
+    } else if (T == PBD_DIHEDRAL) {
+        project_dihedral(p0, p1, p2, p3, s.s0, matv(a, 0, i));
+    } else if (T == PBD_VOLUME) {
+        project_volume<false>(p0, p1, p2, p3, s.s0, matv(a, 0, i), 0.0f, lam);
+    } else if (T == PBD_VOLUME_XPBD) {
+        const float k = matv(a, 0, i);
+        project_volume<true>(p0, p1, p2, p3, s.s0, k, xpbd_alpha(k, dt), lam);
+    } else if (T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD) {
+        constexpr bool X = (T == PBD_ISOBENDING_XPBD);
+        const float k = matv(a, 0, i);
+        const float alpha = X ? xpbd_alpha(k, dt) : 0.0f;
+        if (a.variant == 0) project_isobending_rank1<X>(p0, p1, p2, p3, s.g0, k, alpha, lam);
+        else project_isobending_fullq<X>(p0, p1, p2, p3, s.g0, __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), k, alpha, lam);
+    } else if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) {
+        M3 inv;
+        inv.m[0][0] = s.g0.x; inv.m[0][1] = s.g0.y; inv.m[0][2] = s.g0.z; inv.m[1][0] = s.g0.w;
+        inv.m[1][1] = s.g1.x; inv.m[1][2] = s.g1.y; inv.m[2][0] = s.g1.z; inv.m[2][1] = s.g1.w;
+        inv.m[2][2] = s.s0;
+        if (T == PBD_STRAINTET) project_straintet(p0, p1, p2, p3, inv, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i) != 0.0f, matv(a, 3, i) != 0.0f);
+        else project_femtet<(T == PBD_FEMTET_XPBD)>(p0, p1, p2, p3, s.s1, inv, matv(a, 0, i), matv(a, 1, i), dt, lam);
+    }
+
+    if (XPBD) __stcg(a.lambda + i, lam);
+    stp(pos + s.b.x, p0); stp(pos + s.b.y, p1);
+    if (NB >= 3) stp(pos + s.b.z, p2);
+    if (NB >= 4) stp(pos + s.b.w, p3);
 }
 
 constexpr int kProjectThreads = 256;
@@ -138,8 +131,10 @@ __global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeAr
                                                              unsigned count, float dt, int iterZero) {
     pdl_launch_dependents();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) process_constraint<T, CA, true>(pos, a, first + i, dt, iterZero != 0);
-    // threads without a constraint simply exit: an exited thread counts as having passed the dependency
+    if (i >= count) return;  // an exited thread counts as having passed the dependency
+    const Streamed s = load_streamed<T>(a, first + i);
+    pdl_wait_after(s.b.x ^ s.b.y, s.g0.x + s.g1.x + s.s0 + s.s1);
+    project_streamed<T, CA>(pos, a, first + i, s, dt, iterZero != 0);
 }
 
 // lastX = oldX; oldX = x; if (mass != 0) { v += g h; x += v h }

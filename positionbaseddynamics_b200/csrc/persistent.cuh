@@ -1,33 +1,39 @@
 // positionbaseddynamics_b200/csrc/persistent.cuh
 //
 // k_step_persistent: one TimeStepController::step (Simulation/TimeStepController.cpp:75-241, particle part) as a single
-// cooperative launch.  The grid is sized to be co-resident (SM count x occupancy); every CTA walks the same bucket list
-//     per substep:  integrate | barrier | maxIter x ( colour 0 | barrier | colour 1 | ... | barrier ) | velocity update
-// and a grid-wide barrier separates the colour phases (the reference's "for group in groups" loop,
+// cooperative launch.  The grid is co-resident (one CTA per SM); every CTA walks the same phase list
+//     per substep:  integrate | B | maxIter x ( colour 0 | B | colour 1 | B | ... ) | B | velocity update
+// with a grid-wide barrier B between colour phases only (the reference's "for group in groups" loop,
 // TimeStepController.cpp:272-286, is sequential over colours and parallel inside one).  Buckets of different types inside
-// one colour touch disjoint particles and need no barrier between them.  The velocity update of particle i and the next
-// substep's integration of particle i are done by the same thread, so no barrier is needed between them either.
+// one colour touch disjoint particles and need no barrier between them; the velocity update of particle i and the next
+// substep's integration of particle i are done by the same thread, so no barrier separates them either.
+//
+// Latency hiding: the indices and rest data a thread needs for its first constraint of the NEXT phase are streamed from
+// HBM *before* it arrives at the barrier (they never change during a step), and inside a phase the loop over a thread's
+// constraints is software-pipelined the same way.  After the barrier only the L2-resident particle gather, the arithmetic
+// and the scatter remain on the critical path.
+//
+// Specialisation: the kernel is instantiated for a few masks of constraint types (cloth, tets, everything); types outside
+// the mask are compiled out, which keeps the light instantiations at <= 64 registers so that 1024 threads fit on an SM.
 //
 // Barrier: monotonically increasing 64-bit arrival counter in global memory (one atomic per CTA per phase, thread 0
-// spins with ld.acquire.gpu).  Particle data is read/written with .cg (L2) accesses, so no L1 line can go stale
-// across phases; the __threadfence() before the arrival publishes the CTA's stores.
+// spins with ld.acquire.gpu).  The gpu-scope fence before the arrival publishes the CTA's stores, the one after the
+// spin drops the SM's L1 lines so that cached particle gathers (ld.ca) can never see data of an earlier phase.
 #pragma once
 #include "kernels.cuh"
 
 namespace pbdk {
 
-constexpr int kPersistentThreads = 512;
-
 struct PersistentArgs {
     float4 *pos, *vel, *oldp, *lastp;
     unsigned n;
-    const TypeArrays *types;  // [PBD_NUM_TYPES] in global memory
     const Bucket *buckets;
     unsigned nBuckets, subSteps, maxIter;
     float h, invH, gx, gy, gz;
     int secondOrder, trackLast;
     unsigned long long *barrier;
     unsigned long long barrierBase;  // counter value when this launch starts
+    TypeArrays types[PBD_NUM_TYPES]; // by value: lives in the kernel's constant bank, indexed with compile-time T
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
@@ -43,19 +49,44 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsign
         __threadfence();  // release: publish this CTA's stores
         atomicAdd(counter, 1ull);
         while (ld_acquire_u64(counter) < target) { }
-        __threadfence();  // acquire side: gpu-scope fence also drops this SM's L1 lines (stale particle data of the last phase)
+        __threadfence();  // acquire side: gpu-scope fence also invalidates this SM's L1
     }
     __syncthreads();
 }
 
-template <int T, bool CA>
-__device__ __forceinline__ void sweep_bucket(float4 *pos, const TypeArrays &ta, const Bucket &b, float h, bool iterZero,
-                                             unsigned tid, unsigned stride) {
-    for (unsigned i = tid; i < b.count; i += stride) process_constraint<T, CA>(pos, ta, b.first + i, h, iterZero);
+constexpr unsigned type_bit(int t) { return 1u << t; }
+constexpr unsigned kMaskClothXPBD = type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_ISOBENDING_XPBD);
+constexpr unsigned kMaskLight = type_bit(PBD_DISTANCE) | type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_DIHEDRAL) | type_bit(PBD_ISOBENDING) |
+                                type_bit(PBD_ISOBENDING_XPBD) | type_bit(PBD_VOLUME) | type_bit(PBD_VOLUME_XPBD) | type_bit(PBD_FEMTRIANGLE);
+constexpr unsigned kMaskAll = (1u << PBD_NUM_TYPES) - 1u;
+
+// dispatch a functor on the runtime type, restricted to the compiled-in mask
+#define PBD_FOR_TYPE(MASK, type, ...)                                                                                  \
+    switch (type) {                                                                                                      \
+    case PBD_DISTANCE:        if constexpr ((MASK) & type_bit(PBD_DISTANCE))        { constexpr int T = PBD_DISTANCE;        __VA_ARGS__ } break; \
+    case PBD_DISTANCE_XPBD:   if constexpr ((MASK) & type_bit(PBD_DISTANCE_XPBD))   { constexpr int T = PBD_DISTANCE_XPBD;   __VA_ARGS__ } break; \
+    case PBD_DIHEDRAL:        if constexpr ((MASK) & type_bit(PBD_DIHEDRAL))        { constexpr int T = PBD_DIHEDRAL;        __VA_ARGS__ } break; \
+    case PBD_ISOBENDING:      if constexpr ((MASK) & type_bit(PBD_ISOBENDING))      { constexpr int T = PBD_ISOBENDING;      __VA_ARGS__ } break; \
+    case PBD_ISOBENDING_XPBD: if constexpr ((MASK) & type_bit(PBD_ISOBENDING_XPBD)) { constexpr int T = PBD_ISOBENDING_XPBD; __VA_ARGS__ } break; \
+    case PBD_FEMTRIANGLE:     if constexpr ((MASK) & type_bit(PBD_FEMTRIANGLE))     { constexpr int T = PBD_FEMTRIANGLE;     __VA_ARGS__ } break; \
+    case PBD_STRAINTRIANGLE:  if constexpr ((MASK) & type_bit(PBD_STRAINTRIANGLE))  { constexpr int T = PBD_STRAINTRIANGLE;  __VA_ARGS__ } break; \
+    case PBD_VOLUME:          if constexpr ((MASK) & type_bit(PBD_VOLUME))          { constexpr int T = PBD_VOLUME;          __VA_ARGS__ } break; \
+    case PBD_VOLUME_XPBD:     if constexpr ((MASK) & type_bit(PBD_VOLUME_XPBD))     { constexpr int T = PBD_VOLUME_XPBD;     __VA_ARGS__ } break; \
+    case PBD_FEMTET:          if constexpr ((MASK) & type_bit(PBD_FEMTET))          { constexpr int T = PBD_FEMTET;          __VA_ARGS__ } break; \
+    case PBD_FEMTET_XPBD:     if constexpr ((MASK) & type_bit(PBD_FEMTET_XPBD))     { constexpr int T = PBD_FEMTET_XPBD;     __VA_ARGS__ } break; \
+    case PBD_STRAINTET:       if constexpr ((MASK) & type_bit(PBD_STRAINTET))       { constexpr int T = PBD_STRAINTET;       __VA_ARGS__ } break; \
+    default: break;                                                                                                      \
+    }
+
+__device__ __forceinline__ Bucket load_bucket(const Bucket *buckets, unsigned bi) {
+    Bucket b;
+    const int4 raw = __ldg(reinterpret_cast<const int4 *>(buckets) + bi);  // Bucket is 16 bytes
+    b.type = raw.x; b.first = (unsigned)raw.y; b.count = (unsigned)raw.z; b.colour = (unsigned)raw.w;
+    return b;
 }
 
-template <bool CA>
-__global__ void __launch_bounds__(kPersistentThreads) k_step_persistent(PersistentArgs a) {
+template <unsigned MASK, bool CA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_step_persistent(const __grid_constant__ PersistentArgs a) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned stride = gridDim.x * blockDim.x;
     unsigned long long target = a.barrierBase;
@@ -74,29 +105,45 @@ __global__ void __launch_bounds__(kPersistentThreads) k_step_persistent(Persiste
                 __stcg(a.pos + i, x);
             }
         }
-        grid_barrier(a.barrier, target);
 
         // ---- coloured Gauss-Seidel sweeps -------------------------------------------------------------------
+        // `pre` holds the streamed part of this thread's first constraint of the bucket about to be processed.
+        Streamed pre;
+        pre.b = make_uint4(0u, 0u, 0u, 0u); pre.g0 = make_float4(0.f, 0.f, 0.f, 0.f); pre.g1 = pre.g0; pre.s0 = 0.f; pre.s1 = 0.f;
+        Bucket nb;
+        nb.type = -1; nb.first = 0u; nb.count = 0u; nb.colour = 0u;
+        if (a.nBuckets) {
+            nb = load_bucket(a.buckets, 0);
+            if (tid < nb.count) { PBD_FOR_TYPE(MASK, nb.type, pre = load_streamed<T>(a.types[T], nb.first + tid);) }
+        }
+        grid_barrier(a.barrier, target);  // integration done everywhere before the first colour reads positions
+
         for (unsigned it = 0; it < a.maxIter; it++) {
             const bool iterZero = (it == 0);
-            unsigned colour = a.nBuckets ? __ldg(&a.buckets[0].colour) : 0u;
             for (unsigned bi = 0; bi < a.nBuckets; bi++) {
-                Bucket b;
-                b.type = __ldg(&a.buckets[bi].type); b.first = __ldg(&a.buckets[bi].first);
-                b.count = __ldg(&a.buckets[bi].count); b.colour = __ldg(&a.buckets[bi].colour);
-                if (b.colour != colour) { grid_barrier(a.barrier, target); colour = b.colour; }
-                const TypeArrays ta = a.types[b.type];
-                switch (b.type) {
-#define SB(T) case T: sweep_bucket<T, CA>(a.pos, ta, b, a.h, iterZero, tid, stride); break;
-                    SB(PBD_DISTANCE) SB(PBD_DISTANCE_XPBD) SB(PBD_DIHEDRAL) SB(PBD_ISOBENDING) SB(PBD_ISOBENDING_XPBD)
-                    SB(PBD_FEMTRIANGLE) SB(PBD_STRAINTRIANGLE) SB(PBD_VOLUME) SB(PBD_VOLUME_XPBD) SB(PBD_FEMTET)
-                    SB(PBD_FEMTET_XPBD) SB(PBD_STRAINTET)
-#undef SB
-                default: break;
+                const Bucket b = nb;
+                // bucket that follows this one in execution order (wraps into the next sweep)
+                const bool lastOfSweep = (bi + 1 == a.nBuckets);
+                const bool more = !lastOfSweep || (it + 1 < a.maxIter);
+                if (more) nb = load_bucket(a.buckets, lastOfSweep ? 0u : bi + 1);
+                // software-pipelined walk over this thread's constraints of bucket b
+                PBD_FOR_TYPE(MASK, b.type,
+                    const TypeArrays &ta = a.types[T];
+                    Streamed cur = pre;
+                    for (unsigned i = tid; i < b.count; i += stride) {
+                        Streamed nxt = cur;
+                        if (i + stride < b.count) nxt = load_streamed<T>(ta, b.first + i + stride);
+                        project_streamed<T, CA>(a.pos, ta, b.first + i, cur, a.h, iterZero);
+                        cur = nxt;
+                    })
+                // stream the first constraint of the next bucket, then synchronise if it starts a new colour phase
+                if (more) {
+                    if (tid < nb.count) { PBD_FOR_TYPE(MASK, nb.type, pre = load_streamed<T>(a.types[T], nb.first + tid);) }
+                    if (nb.colour != b.colour || lastOfSweep) grid_barrier(a.barrier, target);
                 }
             }
-            grid_barrier(a.barrier, target);
         }
+        if (a.nBuckets) grid_barrier(a.barrier, target);  // all projections done before velocities are derived
 
         // ---- epilogue: velocity update ----------------------------------------------------------------------
         for (unsigned i = tid; i < a.n; i += stride) {
