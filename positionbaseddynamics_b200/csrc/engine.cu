@@ -678,7 +678,8 @@ template <unsigned MASK, int THREADS>
 static int launch_persistent(pbd_engine *e, cudaStream_t s, PersistentArgs &pa) {
     void *fn = e->gatherCA ? (void *)k_step_persistent<MASK, true, THREADS> : (void *)k_step_persistent<MASK, false, THREADS>;
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, THREADS, 0));
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersistentSmemBytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, THREADS, kPersistentSmemBytes));
     if (nb < 1) return fail("persistent kernel does not fit on an SM");
     const int grid = e->smCount;  // one CTA per SM, all co-resident (cooperative launch)
     // barriers per launch: per substep one after the prologue, one per colour phase of every sweep
@@ -686,7 +687,7 @@ static int launch_persistent(pbd_engine *e, cudaStream_t s, PersistentArgs &pa) 
     pa.barrierBase = e->barrierBase;
     e->barrierBase += perSub * e->subSteps * (unsigned long long)grid;
     void *args[] = {&pa};
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(THREADS), args, 0, s));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(THREADS), args, kPersistentSmemBytes, s));
     return 0;
 }
 
