@@ -83,7 +83,7 @@ struct pbd_engine {
     // device image
     DevType dev[PBD_NUM_TYPES];
     std::vector<Bucket> buckets;
-    DevBuf dBuckets, dTypeArrays, dBarrier;
+    DevBuf dBuckets, dTypeArrays, dBarrier, dTrace;
     bool imageDirty = true;
     bool sortBuckets = true;
     // parameters
@@ -701,9 +701,27 @@ static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long 
     pa.h = h; pa.invH = invH; pa.gx = e->g[0]; pa.gy = e->g[1]; pa.gz = e->g[2];
     pa.secondOrder = e->velMethod; pa.trackLast = track_last(e);
     pa.barrier = (unsigned long long *)e->dBarrier.p;
+    pa.trace = nullptr; pa.tracePhases = 0;
+    static const char *tracePath = getenv("PBD_B200_TRACE");  // development aid: dump per-phase barrier timelines of one step
+    const unsigned kTracePhases = 128;
+    if (tracePath) {
+        CKE(e->dTrace.alloc((size_t)kTracePhases * e->smCount * 4 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(e->dTrace.p, 0, e->dTrace.bytes, s));
+        pa.trace = (unsigned long long *)e->dTrace.p; pa.tracePhases = kTracePhases;
+    }
     unsigned present = 0;
     for (int t = 0; t < PBD_NUM_TYPES; t++) { pa.types[t] = e->dev[t].arrays; if (e->dev[t].count) present |= 1u << t; }
     *launches = 1;
+    struct TraceDump {  // development aid: runs after the launch below has been enqueued (scope exit)
+        pbd_engine *e; cudaStream_t s; const char *path; unsigned phases;
+        ~TraceDump() {
+            if (!path) return;
+            cudaStreamSynchronize(s);
+            std::vector<unsigned long long> h((size_t)phases * e->smCount * 4);
+            cudaMemcpy(h.data(), e->dTrace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+        }
+    } dump{e, s, tracePath, kTracePhases};
     const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
     if ((present & ~kMaskClothXPBD) == 0) {
         if (pt == 512) return launch_persistent<kMaskClothXPBD, 512>(e, s, pa);
