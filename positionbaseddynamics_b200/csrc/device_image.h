@@ -16,6 +16,19 @@ constexpr int kMaxMat = 5;   // material parameters per type (stiffness, Young's
 constexpr int kMaxGeoV = 4;  // float4 geometry arrays per type
 constexpr int kMaxGeoS = 2;  // scalar geometry arrays per type
 
+// Particle placement in the device arrays.  Layout 1 ("de-interleaved") puts the even-numbered particles first and the
+// odd-numbered ones behind them.  Reason (measured, profiles/README.md): the step is bound by L2 *sector* throughput, and
+// constraints of one colour never share a particle, so consecutive constraints of a bucket touch particles 2 apart --
+// with the identity layout a warp's gather then uses only one 16-byte half of every 32-byte sector.  After de-interleaving
+// a stride-2 pattern becomes contiguous (full sectors) and a stride-1 pattern becomes two contiguous streams (also full
+// sectors).  Simulated sectors per gather on cfg2: 0.94 -> 0.72 (ideal 0.5).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline unsigned particle_slot(unsigned i, unsigned n, int layout) {
+    return layout == 1 ? (i >> 1) + (i & 1u) * ((n + 1u) >> 1) : i;
+}
+
 struct TypeArrays {
     const uint2 *idx2;         // 2-body types
     const uint4 *idx4;         // 4-body types

@@ -97,6 +97,7 @@ struct pbd_engine {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timingPending = false;
     int persistentThreads = 0;
+    int layout = 1;                       // particle placement (device_image.h particle_slot); PBD_B200_LAYOUT=linear selects 0
     bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
     bool gatherCA = true;                 // particle gathers through L1 (tuning knob: PBD_B200_GATHER=cg selects L2-only loads)
     unsigned coloursUsed = 0;             // colours that own at least one bucket
@@ -138,6 +139,7 @@ extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
     if (const char *g = getenv("PBD_B200_GATHER")) e->gatherCA = (strcmp(g, "cg") != 0);
     if (const char *g = getenv("PBD_B200_PDL")) e->usePDL = (strcmp(g, "0") != 0);
     if (const char *g = getenv("PBD_B200_PTHREADS")) e->persistentThreads = atoi(g);
+    if (const char *g = getenv("PBD_B200_LAYOUT")) e->layout = (strcmp(g, "linear") == 0) ? 0 : 1;
     *out = e;
     return 0;
 }
@@ -188,7 +190,7 @@ static float4 *attr_buf(pbd_engine *e, int attr) {
 static int upload3(pbd_engine *e, const float *src, float4 *dst, int keepW) {
     const size_t bytes = (size_t)e->n * 3 * sizeof(float);
     CK(cudaMemcpyAsync(e->stage.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
-    k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, dst, e->n, keepW);
+    k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, dst, e->n, keepW, e->layout);
     CK(cudaGetLastError());
     return 0;
 }
@@ -198,7 +200,7 @@ extern "C" int pbd_set_masses(pbd_engine *e, const float *mass) {
     CKE(use(e));
     if (e->n == 0) return 0;
     CK(cudaMemcpyAsync(e->massStage.p, mass, (size_t)e->n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    k_set_w<<<nblk(e->n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (const float *)e->massStage.p, e->n);
+    k_set_w<<<nblk(e->n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (const float *)e->massStage.p, e->n, e->layout);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));  // staging buffers are reused by the next call
     return 0;
@@ -247,7 +249,7 @@ extern "C" int pbd_get_attr(pbd_engine *e, int attr, float *dst) {
     const float4 *src = attr_buf(e, attr);
     if (!src) return fail("pbd_get_attr: bad attribute %d", attr);
     if (e->n == 0) return 0;
-    k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>(src, (float *)e->stage.p, e->n);
+    k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>(src, (float *)e->stage.p, e->n, e->layout);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, e->stage.p, (size_t)e->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -443,8 +445,8 @@ static int flatten(pbd_engine *e) {
                 std::vector<std::pair<unsigned, unsigned>> keyed(tmp[t].size());
                 for (size_t i = 0; i < tmp[t].size(); i++) {
                     const unsigned *b = bod + (size_t)tmp[t][i] * nb;
-                    unsigned mn = b[0];
-                    for (int k = 1; k < nb; k++) mn = std::min(mn, b[k]);
+                    unsigned mn = particle_slot(b[0], e->n, e->layout);
+                    for (int k = 1; k < nb; k++) mn = std::min(mn, particle_slot(b[k], e->n, e->layout));
                     keyed[i] = std::make_pair(mn, tmp[t][i]);
                 }
                 std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) { return a.first < b.first; });
@@ -489,7 +491,7 @@ static int flatten(pbd_engine *e) {
         if (cnt == 0) continue;
         for (unsigned i = 0; i < cnt; i++) d.order[i] = h.ids[order[t][i]];
         auto P = [&](unsigned i, int k) { return h.params[(size_t)order[t][i] * s.nParams + k]; };
-        auto B = [&](unsigned i, int k) { return h.bodies[(size_t)order[t][i] * s.nBodies + k]; };
+        auto B = [&](unsigned i, int k) { return particle_slot(h.bodies[(size_t)order[t][i] * s.nBodies + k], e->n, e->layout); };
 
         // indices
         if (s.nBodies == 2) {
@@ -803,20 +805,20 @@ extern "C" int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, 
     CKE(stage2.alloc(bytes));
     if (x_in) {
         CK(cudaMemcpyAsync(e->stage.p, x_in, bytes, cudaMemcpyHostToDevice, e->stream));
-        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, (float4 *)e->pos.p, e->n, 1);
+        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, (float4 *)e->pos.p, e->n, 1, e->layout);
     }
     if (v_in) {
         CK(cudaMemcpyAsync(stage2.p, v_in, bytes, cudaMemcpyHostToDevice, e->stream));
-        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)stage2.p, (float4 *)e->vel.p, e->n, 1);
+        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)stage2.p, (float4 *)e->vel.p, e->n, 1, e->layout);
     }
     CK(cudaGetLastError());
     CKE(pbd_step(e, nSteps));
     if (x_out) {
-        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float *)e->stage.p, e->n);
+        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float *)e->stage.p, e->n, e->layout);
         CK(cudaMemcpyAsync(x_out, e->stage.p, bytes, cudaMemcpyDeviceToHost, e->stream));
     }
     if (v_out) {
-        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->vel.p, (float *)stage2.p, e->n);
+        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->vel.p, (float *)stage2.p, e->n, e->layout);
         CK(cudaMemcpyAsync(v_out, stage2.p, bytes, cudaMemcpyDeviceToHost, e->stream));
     }
     CK(cudaGetLastError());

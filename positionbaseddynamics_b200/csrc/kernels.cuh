@@ -183,26 +183,29 @@ __global__ void __launch_bounds__(256) k_velocity(const float4 *__restrict__ pos
     __stcs(vel + i, v);
 }
 
-// host AoS-3 <-> device float4 conversion (std::vector<Vector3r> layout on the host side)
-__global__ void k_pack3(const float *__restrict__ src, float4 *__restrict__ dst, unsigned n, int keepW) {
+// host AoS-3 <-> device float4 conversion (std::vector<Vector3r> layout on the host side); particle i of the host lives
+// in device slot particle_slot(i, n, layout) (device_image.h)
+__global__ void k_pack3(const float *__restrict__ src, float4 *__restrict__ dst, unsigned n, int keepW, int layout) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 d = keepW ? dst[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned s = particle_slot(i, n, layout);
+    float4 d = keepW ? dst[s] : make_float4(0.f, 0.f, 0.f, 0.f);
     d.x = src[3 * i]; d.y = src[3 * i + 1]; d.z = src[3 * i + 2];
-    dst[i] = d;
+    dst[s] = d;
 }
-__global__ void k_unpack3(const float4 *__restrict__ src, float *__restrict__ dst, unsigned n) {
+__global__ void k_unpack3(const float4 *__restrict__ src, float *__restrict__ dst, unsigned n, int layout) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 s = src[i];
+    const float4 s = src[particle_slot(i, n, layout)];
     dst[3 * i] = s.x; dst[3 * i + 1] = s.y; dst[3 * i + 2] = s.z;
 }
-__global__ void k_set_w(float4 *__restrict__ pos, float4 *__restrict__ vel, const float *__restrict__ mass, unsigned n) {
+__global__ void k_set_w(float4 *__restrict__ pos, float4 *__restrict__ vel, const float *__restrict__ mass, unsigned n, int layout) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float m = mass[i];
-    pos[i].w = (m != 0.0f) ? 1.0f / m : 0.0f;  // ParticleData::setMass (ParticleData.h:239-246)
-    vel[i].w = m;
+    const unsigned s = particle_slot(i, n, layout);
+    pos[s].w = (m != 0.0f) ? 1.0f / m : 0.0f;  // ParticleData::setMass (ParticleData.h:239-246)
+    vel[s].w = m;
 }
 
 }  // namespace pbdk
