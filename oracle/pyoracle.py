@@ -60,6 +60,9 @@ class CpuPbd:
         for name in ("step", "time"):
             getattr(self.lib, self.prefix + name).restype = C.c_double
         assert self.f("real_size")() == (4 if precision == "f32" else 8)
+        # the reference forks an OpenMP team per colour group; on many-core hosts the default team (all hardware threads)
+        # makes small scenes crawl.  Checkers default to a small team; bench.py picks its own.
+        self.set_threads(min(8, os.cpu_count() or 1))
         self.reset()
 
     def f(self, name):

@@ -97,6 +97,7 @@ struct pbd_engine {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timingPending = false;
     int persistentThreads = 0;
+    bool mergeColours = true;             // one launch per colour when it holds several types (PBD_B200_MERGE=0 disables)
     int layout = 1;                       // particle placement (device_image.h particle_slot); PBD_B200_LAYOUT=linear selects 0
     bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
     bool gatherCA = true;                 // particle gathers through L1 (tuning knob: PBD_B200_GATHER=cg selects L2-only loads)
@@ -139,6 +140,7 @@ extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
     if (const char *g = getenv("PBD_B200_GATHER")) e->gatherCA = (strcmp(g, "cg") != 0);
     if (const char *g = getenv("PBD_B200_PDL")) e->usePDL = (strcmp(g, "0") != 0);
     if (const char *g = getenv("PBD_B200_PTHREADS")) e->persistentThreads = atoi(g);
+    if (const char *g = getenv("PBD_B200_MERGE")) e->mergeColours = (strcmp(g, "0") != 0);
     if (const char *g = getenv("PBD_B200_LAYOUT")) e->layout = (strcmp(g, "linear") == 0) ? 0 : 1;
     *out = e;
     return 0;
@@ -639,6 +641,39 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
     return 0;
 }
 
+// all buckets [b0, b1) belong to one colour: one launch for up to kMultiSegments of them
+static int launch_colour(pbd_engine *e, size_t b0, size_t b1, float h, int iterZero, cudaStream_t s, unsigned long long *launches) {
+    if (b1 - b0 == 1 || !e->mergeColours) {
+        for (size_t i = b0; i < b1; i++) { CKE(launch_bucket(e, e->buckets[i], h, iterZero, s)); (*launches)++; }
+        return 0;
+    }
+    for (size_t c0 = b0; c0 < b1; c0 += kMultiSegments) {
+        const size_t c1 = std::min(b1, c0 + (size_t)kMultiSegments);
+        MultiArgs m{};
+        m.nSeg = (int)(c1 - c0);
+        unsigned blocks = 0;
+        for (size_t i = c0; i < c1; i++) {
+            const Bucket &b = e->buckets[i];
+            const int k = (int)(i - c0);
+            m.type[k] = b.type; m.first[k] = b.first; m.count[k] = b.count; m.blockStart[k] = blocks;
+            m.arrays[k] = e->dev[b.type].arrays;
+            blocks += nblk(b.count, kProjectThreads);
+        }
+        for (int k = m.nSeg; k <= kMultiSegments; k++) m.blockStart[k] = blocks;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kProjectThreads); cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = e->usePDL ? 1 : 0;
+        float4 *pos = (float4 *)e->pos.p;
+        CK(e->gatherCA ? cudaLaunchKernelEx(&cfg, k_project_multi<true>, pos, m, h, iterZero)
+                       : cudaLaunchKernelEx(&cfg, k_project_multi<false>, pos, m, h, iterZero));
+        (*launches)++;
+    }
+    return 0;
+}
+
 // prologue / epilogue launches share the PDL attribute so that the whole step is one programmatic dependency chain
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_particles(pbd_engine *e, cudaStream_t s, void (*kernel)(KArgs...), unsigned n, Args... args) {
@@ -665,7 +700,12 @@ static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long lo
             L++;
         }
         for (unsigned it = 0; it < e->maxIter; it++)
-            for (const Bucket &b : e->buckets) { CKE(launch_bucket(e, b, h, it == 0, s)); L++; }
+            for (size_t b0 = 0; b0 < e->buckets.size();) {
+                size_t b1 = b0 + 1;
+                while (b1 < e->buckets.size() && e->buckets[b1].colour == e->buckets[b0].colour) b1++;
+                CKE(launch_colour(e, b0, b1, h, it == 0, s, &L));
+                b0 = b1;
+            }
         if (n) {
             CK(launch_particles(e, s, k_velocity, n, (const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod));
             L++;
@@ -854,37 +894,54 @@ extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegr
     if (!e) return fail("null engine");
     CKE(use(e)); CKE(flatten(e));
     CK(cudaStreamSynchronize(e->stream));
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    if (msPerType) for (int t = 0; t < PBD_NUM_TYPES; t++) msPerType[t] = 0.0f;
-    if (launchesPerType) for (int t = 0; t < PBD_NUM_TYPES; t++) launchesPerType[t] = 0;
-    float mi = 0.0f, mv = 0.0f, ms = 0.0f;
+    // One event between every pair of consecutive launches, all recorded in stream order without host synchronisation
+    // (a host sync per launch would time the idle-launch latency, not the kernel); read back after one final sync.
+    const size_t nLaunch = (size_t)e->subSteps * (2 + (size_t)e->maxIter * e->buckets.size());
+    std::vector<cudaEvent_t> ev(nLaunch + 1);
+    for (auto &x : ev) CK(cudaEventCreate(&x));
+    std::vector<int> what(nLaunch);  // >= 0: type, -1 integrate, -2 velocity
     const float h = e->dt / (float)e->subSteps;
     const float invH = (float)(1.0 / (double)h);
     const unsigned n = e->n;
-    for (unsigned sub = 0; sub < e->subSteps; sub++) {
+    const bool pdl = e->usePDL;
+    e->usePDL = false;  // serialise: each kernel's duration must be its own
+    size_t k = 0;
+    int rc = 0;
+    CK(cudaEventRecord(ev[0], e->stream));
+    for (unsigned sub = 0; sub < e->subSteps && !rc; sub++) {
         if (n) {
-            CK(cudaEventRecord(a, e->stream));
             k_integrate<<<nblk(n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e));
-            CK(cudaEventRecord(b, e->stream)); CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b)); mi += ms;
+            what[k] = -1; cudaEventRecord(ev[++k], e->stream);
         }
-        for (unsigned it = 0; it < e->maxIter; it++)
+        for (unsigned it = 0; it < e->maxIter && !rc; it++)
             for (const Bucket &bk : e->buckets) {
-                CK(cudaEventRecord(a, e->stream));
-                CKE(launch_bucket(e, bk, h, it == 0, e->stream));
-                CK(cudaEventRecord(b, e->stream)); CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b));
-                if (msPerType) msPerType[bk.type] += ms;
-                if (launchesPerType) launchesPerType[bk.type]++;
+                rc = launch_bucket(e, bk, h, it == 0, e->stream);
+                if (rc) break;
+                what[k] = bk.type; cudaEventRecord(ev[++k], e->stream);
             }
-        if (n) {
-            CK(cudaEventRecord(a, e->stream));
+        if (n && !rc) {
             k_velocity<<<nblk(n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod);
-            CK(cudaEventRecord(b, e->stream)); CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b)); mv += ms;
+            what[k] = -2; cudaEventRecord(ev[++k], e->stream);
         }
     }
+    e->usePDL = pdl;
+    cudaError_t se = cudaStreamSynchronize(e->stream);
+    if (msPerType) for (int t = 0; t < PBD_NUM_TYPES; t++) msPerType[t] = 0.0f;
+    if (launchesPerType) for (int t = 0; t < PBD_NUM_TYPES; t++) launchesPerType[t] = 0;
+    float mi = 0.0f, mv = 0.0f;
+    if (!rc && se == cudaSuccess)
+        for (size_t i = 0; i < k; i++) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            if (what[i] == -1) mi += ms;
+            else if (what[i] == -2) mv += ms;
+            else { if (msPerType) msPerType[what[i]] += ms; if (launchesPerType) launchesPerType[what[i]]++; }
+        }
+    for (auto &x : ev) cudaEventDestroy(x);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail("pbd_profile_step: %s", cudaGetErrorString(se));
     if (msIntegrate) *msIntegrate = mi;
     if (msVelocity) *msVelocity = mv;
-    cudaEventDestroy(a); cudaEventDestroy(b);
     e->stats.steps++;
     e->stats.projections += (unsigned long long)e->numConstraints * e->subSteps * e->maxIter;
     return 0;

@@ -137,6 +137,39 @@ __global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeAr
     project_streamed<T, CA>(pos, a, first + i, s, dt, iterZero != 0);
 }
 
+// Several (colour,type) buckets of ONE colour in a single launch: buckets of a colour touch disjoint particles, so they
+// need no ordering among themselves (the reference runs a whole colour group under one `omp parallel for`,
+// TimeStepController.cpp:275-285).  A CTA finds its segment from blockIdx and dispatches on the segment's type.
+// Used when a colour holds more than one constraint type (e.g. FEMTet + Volume in cfg3: 112 buckets but 74 colours).
+constexpr int kMultiSegments = 4;
+struct MultiArgs {
+    int nSeg;
+    int type[kMultiSegments];
+    unsigned first[kMultiSegments], count[kMultiSegments], blockStart[kMultiSegments + 1];
+    TypeArrays arrays[kMultiSegments];
+};
+
+template <bool CA>
+__global__ void __launch_bounds__(kProjectThreads) k_project_multi(float4 *pos, const __grid_constant__ MultiArgs m, float dt, int iterZero) {
+    pdl_launch_dependents();
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < kMultiSegments; k++)
+        if (k < m.nSeg && blockIdx.x >= m.blockStart[k]) s = k;
+    const unsigned i = (blockIdx.x - m.blockStart[s]) * blockDim.x + threadIdx.x;
+    if (i >= m.count[s]) return;
+    const TypeArrays &a = m.arrays[s];
+    const unsigned ci = m.first[s] + i;
+#define PM(T) case T: { const Streamed st = load_streamed<T>(a, ci); pdl_wait_after(st.b.x ^ st.b.y, st.g0.x + st.g1.x + st.s0 + st.s1); \
+                        project_streamed<T, CA>(pos, a, ci, st, dt, iterZero != 0); } break;
+    switch (m.type[s]) {
+        PM(PBD_DISTANCE) PM(PBD_DISTANCE_XPBD) PM(PBD_DIHEDRAL) PM(PBD_ISOBENDING) PM(PBD_ISOBENDING_XPBD) PM(PBD_FEMTRIANGLE)
+        PM(PBD_STRAINTRIANGLE) PM(PBD_VOLUME) PM(PBD_VOLUME_XPBD) PM(PBD_FEMTET) PM(PBD_FEMTET_XPBD) PM(PBD_STRAINTET)
+    default: break;
+    }
+#undef PM
+}
+
 // lastX = oldX; oldX = x; if (mass != 0) { v += g h; x += v h }
 __global__ void __launch_bounds__(256) k_integrate(float4 *__restrict__ pos, float4 *__restrict__ vel,
                                                    float4 *__restrict__ oldp, float4 *__restrict__ lastp, unsigned n,
