@@ -285,37 +285,53 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------------------------
+    # Dominant kernel = the bucket kernel of the type with the largest device-time share.  Its launches are timed live with
+    # CUDA events recorded between consecutive launches on the engine stream (pbd_profile_step, PDL off so that every
+    # duration is the kernel's own).  Inside the replayed graph consecutive buckets overlap (PDL), so two durations exist:
+    #   serialized  = event-timed stand-alone launch,
+    #   in-pipeline = (share of the type) x (timed step) / launches  -- what the kernel costs where it actually runs.
+    # `achieved` uses the in-pipeline duration; the serialized figure is reported next to it.
     peak, peak_src = measured_peak()
     st = eng.stats()
+    PER_PROJ = {_capi.DISTANCE: 76.0, _capi.DISTANCE_XPBD: 84.0, _capi.DIHEDRAL: 148.0, _capi.ISOBENDING: 160.0, _capi.ISOBENDING_XPBD: 168.0,
+                _capi.FEMTRIANGLE: 128.0, _capi.STRAINTRIANGLE: 124.0, _capi.VOLUME: 148.0, _capi.VOLUME_XPBD: 156.0, _capi.FEMTET: 184.0,
+                _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0}  # DESIGN.md byte table (algorithmic bytes per projection)
+    ms_step = ms_max / args.steps
     if mode_name == "persistent":
-        eng.set_mode(mode); eng.step(3); eng.sync()
-        eng.step(5); eng.sync()
-        k_ms = eng.stats().last_step_ms / 5.0
-        k_bytes = st.bytes_per_step
-        roof = {"kernel": "k_step_persistent (whole step, one cooperative launch)", "bytes_per_launch": k_bytes, "ms_per_launch": k_ms}
+        roof = {"kernel": "k_step_persistent (whole step, one cooperative launch)", "bytes_per_launch": st.bytes_per_step, "ms_per_launch": ms_step}
     else:
         eng.set_mode(_capi.MODE_LAUNCH)
         eng.step(2); eng.sync()
-        tms = np.zeros(_capi.NUM_TYPES); tl = np.zeros(_capi.NUM_TYPES)
+        tms = np.zeros(_capi.NUM_TYPES); tl = np.zeros(_capi.NUM_TYPES); tmi = tmv = 0.0
         reps = 3
         for _ in range(reps):
             ms_t_, mi, mv, l_ = eng.profile_step()
-            tms += ms_t_; tl += l_
+            tms += ms_t_; tl += l_; tmi += mi; tmv += mv
         dom = int(np.argmax(tms))
-        per_proj = {_capi.DISTANCE: 76.0, _capi.DISTANCE_XPBD: 84.0, _capi.DIHEDRAL: 148.0, _capi.ISOBENDING: 160.0, _capi.ISOBENDING_XPBD: 168.0,
-                    _capi.FEMTRIANGLE: 128.0, _capi.STRAINTRIANGLE: 124.0, _capi.VOLUME: 148.0, _capi.VOLUME_XPBD: 156.0, _capi.FEMTET: 184.0,
-                    _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0}.get(dom)  # DESIGN.md byte table
-        cnt = st.constraints_per_type[dom]
-        k_ms = float(tms[dom] / max(tl[dom], 1))
-        k_bytes = float(cnt * per_proj * args.iters * sub_steps * reps / max(tl[dom], 1)) if per_proj else None
-        roof = {"kernel": "k_project<%s>" % _capi.TYPE_NAMES[dom], "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
-                "share_of_step": float(tms[dom] / max(tms.sum() + mi + mv, 1e-9))}
+        share = float(tms[dom] / max(tms.sum() + tmi + tmv, 1e-9))
+        launches_per_step = tl[dom] / reps
+        bytes_per_launch = float(st.constraints_per_type[dom] * PER_PROJ[dom] * args.iters * sub_steps / max(launches_per_step, 1))
+        ser_ms = float(tms[dom] / max(tl[dom], 1))
+        pipe_ms = share * ms_step / max(launches_per_step, 1)
+        roof = {"kernel": "k_project<%s>" % _capi.TYPE_NAMES[dom], "bytes_per_launch": bytes_per_launch, "ms_per_launch": pipe_ms,
+                "ms_per_launch_serialized": ser_ms, "achieved_serialized": bytes_per_launch / (ser_ms * 1e-3) / 1e9,
+                "share_of_step": share, "launches_per_step": launches_per_step,
+                "shares": {_capi.TYPE_NAMES[t]: float(tms[t] / max(tms.sum() + tmi + tmv, 1e-9)) for t in range(_capi.NUM_TYPES) if tms[t] > 0}}
         eng.set_mode(mode)
-    achieved = (roof["bytes_per_launch"] / (roof["ms_per_launch"] * 1e-3)) / 1e9 if roof["bytes_per_launch"] else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": peak_src, **roof,
-                "step_achieved_gbs": st.bytes_per_step / (ms_max / args.steps * 1e-3) / 1e9,
-                "note": "algorithmic bytes per SURVEY.md 8d / DESIGN.md; particle float4s are L2-resident (16 MB), so frac can exceed 1"}
+    achieved = (roof["bytes_per_launch"] / (roof["ms_per_launch"] * 1e-3)) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram__bytes_read+write per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(WORKLOAD, {}).get(roof["kernel"])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, **roof,
+                "step_bytes": st.bytes_per_step, "step_achieved": st.bytes_per_step / (ms_step * 1e-3) / 1e9,
+                "step_frac": st.bytes_per_step / (ms_step * 1e-3) / 1e9 / peak,
+                "note": "algorithmic bytes (DESIGN.md section 3); particle float4s are L2-resident, DRAM sees only the constraint stream; "
+                        "the measured limiter is L2 sector throughput (profiles/README.md)"}
 
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) ----------------------------------------------------------------
     cpu = None
