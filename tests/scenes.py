@@ -53,5 +53,22 @@ def cfg3(m, w=101, h=21, d=21):
     bar(m, w, h, d, solid_method=2, k=1.0e6, nu=0.3, vol_k=1.0, extra_volume=True, sub_steps=10, max_iter=5)
 
 
+def mixed(m, n_cloth=24, bar_dims=(7, 4, 4), cloth_method=2, bending_method=2, solid_method=2, sub_steps=5, max_iter=1):
+    """cfg4 without the rigid bodies: a cloth and a tet solid in ONE model (two particle ranges, constraint types
+    interleaved in the colour groups), the scene shape of Demos/CouplingDemos/RigidBodyClothCouplingDemo.cpp:151-289.
+    Defaults are the reference's: cloth method 2 (FEMTriangle), 5 substeps x 1 iteration (TimeStepController.cpp:28-30)."""
+    m.add_regular_triangle_model(n_cloth, n_cloth, t=(0, 1, 0), R=RX90, scale=(5.0, 5.0))
+    m.add_regular_tet_model(bar_dims[0], bar_dims[1], bar_dims[2], t=(2.5, 3.0, 2.5), R=np.eye(3), scale=(2.0, 0.6, 0.6))
+    m.set_mass(0, 0.0); m.set_mass(n_cloth - 1, 0.0)
+    off = n_cloth * n_cloth
+    for j in range(bar_dims[1]):
+        for k in range(bar_dims[2]):
+            m.set_mass(off + j * bar_dims[2] + k, 0.0)
+    m.add_cloth_constraints(0, cloth_method, dist_k=1.0, xx=1000.0, yy=1000.0, xy=500.0, pxy=0.3, pyx=0.3)
+    m.add_bending_constraints(0, bending_method, 0.01)
+    m.add_solid_constraints(0, solid_method, k=1.0e6 if solid_method in (2, 3) else 1.0, nu=0.3, vol_k=1.0)
+    m.set_params(dt=0.005, sub_steps=sub_steps, max_iter=max_iter)
+
+
 def projections_per_step(num_constraints, sub_steps, max_iter):
     return num_constraints * sub_steps * max_iter

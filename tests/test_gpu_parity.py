@@ -35,6 +35,9 @@ SCENES = {
     "bar_straintet": (lambda m: scenes.bar(m, 9, 4, 4, 4, k=1.0, sub_steps=2, max_iter=3), 0.01, 3),
     "bar_distance_volume_xpbd": (lambda m: scenes.bar(m, 9, 4, 4, 6, k=1.0e5, vol_k=1.0e5, sub_steps=2, max_iter=3), 0.01, 3),
     "bar_fem_plus_volume": (lambda m: scenes.bar(m, 9, 4, 4, 2, k=1.0e6, extra_volume=True, sub_steps=3, max_iter=2), 0.01, 3),
+    # cfg4 without rigid bodies: cloth (FEMTriangle + IsometricBending) and a tet solid (FEMTet) in one model
+    "mixed_cloth_solid": (lambda m: scenes.mixed(m), 0.01, 3),
+    "mixed_cloth_solid_distance_volume": (lambda m: scenes.mixed(m, cloth_method=1, bending_method=1, solid_method=1, max_iter=3), 0.01, 3),
 }
 
 
@@ -78,7 +81,7 @@ def test_scene_vs_reference_f64(name, cpu_libs):
     _run(name, 0, cpu_libs, "ref")
 
 
-@pytest.mark.parametrize("name", ["cloth_isobending_xpbd", "bar_fem_plus_volume", "cfg1_50x50"])
+@pytest.mark.parametrize("name", ["cloth_isobending_xpbd", "bar_fem_plus_volume", "cfg1_50x50", "mixed_cloth_solid"])
 def test_modes_agree_bitwise(name, cpu_libs):
     """Plain launches, the replayed CUDA graph and the persistent cooperative kernel execute the same projections in the
     same dependency order, so their results must be bit-identical."""

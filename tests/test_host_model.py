@@ -36,7 +36,7 @@ def test_structure_equals_reference_golden(name):
 
 
 def test_structure_equals_oracle_on_larger_scenes(cpu_libs):
-    for build in (lambda m: scenes.cfg2(m, 120, 20), lambda m: scenes.cfg3(m, 21, 9, 9)):
+    for build in (lambda m: scenes.cfg2(m, 120, 20), lambda m: scenes.cfg3(m, 21, 9, 9), lambda m: scenes.mixed(m, 30, (9, 5, 5))):
         h = HostModel(); o = cpu_libs.CpuPbd("oracle", "f64")
         build(h); build(o)
         th, bh, _, _ = h.constraints(); to, bo, _, _ = o.constraints()
