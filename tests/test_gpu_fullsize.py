@@ -106,6 +106,7 @@ def test_free_fall_of_an_unpinned_sheet_is_rigid():
     m.step(4)
     d = m.get("x") - m.get("x0")
     h = 0.0025; k = 8
-    assert np.abs(d[:, 1] - (-9.81 * h * h * k * (k + 1) / 2)).max() <= 2e-6
-    assert np.abs(d[:, 0]).max() <= 1e-6 and np.abs(d[:, 2]).max() <= 1e-6
+    # fp32: ulp(5.0) = 4.8e-7 per update, 8 substeps, and the constraints react to that rounding noise
+    assert np.abs(d[:, 1] - (-9.81 * h * h * k * (k + 1) / 2)).max() <= 2e-5
+    assert np.abs(d[:, 0]).max() <= 1e-5 and np.abs(d[:, 2]).max() <= 1e-5
     m.close()
