@@ -295,7 +295,7 @@ def run_b200(args):
     st = eng.stats()
     PER_PROJ = {_capi.DISTANCE: 76.0, _capi.DISTANCE_XPBD: 84.0, _capi.DIHEDRAL: 148.0, _capi.ISOBENDING: 160.0, _capi.ISOBENDING_XPBD: 168.0,
                 _capi.FEMTRIANGLE: 128.0, _capi.STRAINTRIANGLE: 124.0, _capi.VOLUME: 148.0, _capi.VOLUME_XPBD: 156.0, _capi.FEMTET: 184.0,
-                _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0}  # DESIGN.md byte table (algorithmic bytes per projection)
+                _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0, _capi.SHAPEMATCHING: 240.0}  # DESIGN.md byte table (algorithmic bytes per projection)
     ms_step = ms_max / args.steps
     if mode_name == "persistent":
         roof = {"kernel": "k_step_persistent (whole step, one cooperative launch)", "bytes_per_launch": st.bytes_per_step, "ms_per_launch": ms_step}

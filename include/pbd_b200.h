@@ -34,11 +34,12 @@ typedef struct pbd_engine pbd_engine;
  *  PBD_FEMTET               4       volume, invRestMat[9], E, nu                             FEMTetConstraint             Constraints.cpp:1755-1825
  *  PBD_FEMTET_XPBD          4       volume, invRestMat[9], E, nu                  (+lambda)  XPBD_FEMTetConstraint        Constraints.cpp:1830-1906
  *  PBD_STRAINTET            4       invRestMat[9], stretchK, shearK, normStretch, normShear  StrainTetConstraint          Constraints.cpp:1912-1980
+ *  PBD_SHAPEMATCHING        4       stiffness, restCm[3], x0[4][3], w[4], numClusters[4]     ShapeMatchingConstraint (4-particle clusters) :1985-2028
  */
 enum pbd_constraint_type {
     PBD_DISTANCE = 0, PBD_DISTANCE_XPBD = 1, PBD_DIHEDRAL = 2, PBD_ISOBENDING = 3, PBD_ISOBENDING_XPBD = 4,
     PBD_FEMTRIANGLE = 5, PBD_STRAINTRIANGLE = 6, PBD_VOLUME = 7, PBD_VOLUME_XPBD = 8, PBD_FEMTET = 9,
-    PBD_FEMTET_XPBD = 10, PBD_STRAINTET = 11, PBD_NUM_TYPES = 12
+    PBD_FEMTET_XPBD = 10, PBD_STRAINTET = 11, PBD_SHAPEMATCHING = 12, PBD_NUM_TYPES = 13
 };
 
 /* particle attributes (ParticleData, Simulation/ParticleData.h:91-100); host layout = packed 3 floats per particle,

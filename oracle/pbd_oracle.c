@@ -188,6 +188,57 @@ static void svd_inversion(const mat3 *A, vec3 *sigma, mat3 *U, mat3 *VT) {
     }
 }
 
+/* MathFunctions::oneNorm / infNorm, MathFunctions.cpp:148-178 */
+static real one_norm(const mat3 *A) {
+    real m = R(0.0);
+    for (int c = 0; c < 3; c++) { real s = RFABS(A->m[0][c]) + RFABS(A->m[1][c]) + RFABS(A->m[2][c]); if (c == 0 || s > m) m = s; }
+    return m;
+}
+static real inf_norm(const mat3 *A) {
+    real m = R(0.0);
+    for (int r = 0; r < 3; r++) { real s = RFABS(A->m[r][0]) + RFABS(A->m[r][1]) + RFABS(A->m[r][2]); if (r == 0 || s > m) m = s; }
+    return m;
+}
+static inline vec3 mrow(const mat3 *a, int r) { return V(a->m[r][0], a->m[r][1], a->m[r][2]); }
+static inline void set_row(mat3 *a, int r, vec3 v) { a->m[r][0] = v.v[0]; a->m[r][1] = v.v[1]; a->m[r][2] = v.v[2]; }
+
+/* MathFunctions::polarDecompositionStable, MathFunctions.cpp:180-255 */
+static void polar_decomposition_stable(const mat3 *M, real tolerance, mat3 *Rm) {
+    mat3 Mt = transpose3(M);
+    real Mone = one_norm(M), Minf = inf_norm(M), Eone;
+    mat3 MadjTt, Et;
+    do {
+        set_row(&MadjTt, 0, vcross(mrow(&Mt, 1), mrow(&Mt, 2)));
+        set_row(&MadjTt, 1, vcross(mrow(&Mt, 2), mrow(&Mt, 0)));
+        set_row(&MadjTt, 2, vcross(mrow(&Mt, 0), mrow(&Mt, 1)));
+        real det = Mt.m[0][0] * MadjTt.m[0][0] + Mt.m[0][1] * MadjTt.m[0][1] + Mt.m[0][2] * MadjTt.m[0][2];
+        if (RFABS(det) < 1.0e-12) {
+            int index = -1;
+            for (int i = 0; i < 3; i++) { if (vsq(mrow(&MadjTt, i)) > 1.0e-12) { index = i; break; } }
+            if (index < 0) { memset(Rm, 0, sizeof(*Rm)); Rm->m[0][0] = Rm->m[1][1] = Rm->m[2][2] = R(1.0); return; }
+            set_row(&Mt, index, vcross(mrow(&Mt, (index + 1) % 3), mrow(&Mt, (index + 2) % 3)));
+            set_row(&MadjTt, (index + 1) % 3, vcross(mrow(&Mt, (index + 2) % 3), mrow(&Mt, index)));
+            set_row(&MadjTt, (index + 2) % 3, vcross(mrow(&Mt, index), mrow(&Mt, (index + 1) % 3)));
+            mat3 M2 = transpose3(&Mt);
+            Mone = one_norm(&M2); Minf = inf_norm(&M2);
+            det = Mt.m[0][0] * MadjTt.m[0][0] + Mt.m[0][1] * MadjTt.m[0][1] + Mt.m[0][2] * MadjTt.m[0][2];
+        }
+        const real MadjTone = one_norm(&MadjTt), MadjTinf = inf_norm(&MadjTt);
+        const real gamma = RSQRT(RSQRT((MadjTone * MadjTinf) / (Mone * Minf)) / RFABS(det));
+        const real g1 = gamma * R(0.5);
+        const real g2 = R(0.5) / (gamma * det);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                Et.m[i][j] = Mt.m[i][j];
+                Mt.m[i][j] = g1 * Mt.m[i][j] + g2 * MadjTt.m[i][j];
+                Et.m[i][j] -= Mt.m[i][j];
+            }
+        Eone = one_norm(&Et);
+        Mone = one_norm(&Mt); Minf = inf_norm(&Mt);
+    } while (Eone > Mone * tolerance);
+    *Rm = transpose3(&Mt);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* Stateless solver functions                                                                        */
 /* ------------------------------------------------------------------------------------------------ */
@@ -512,6 +563,41 @@ static int solve_straintriangle(vec3 p0, real w0, vec3 p1, real w1, vec3 p2, rea
     }
     return 1;
 #undef IM
+}
+
+/* PositionBasedDynamics::init_ShapeMatchingConstraint, PositionBasedDynamics.cpp:479-497 */
+static int init_shapematching(const vec3 *x0, const real *w, int n, vec3 *restCm) {
+    *restCm = VZERO;
+    real wsum = R(0.0);
+    for (int i = 0; i < n; i++) { real wi = R(1.0) / (w[i] + EPS); *restCm = vadd(*restCm, vmul(x0[i], wi)); wsum += wi; }
+    if (wsum == R(0.0)) return 0;
+    *restCm = V(restCm->v[0] / wsum, restCm->v[1] / wsum, restCm->v[2] / wsum);
+    return 1;
+}
+
+/* PositionBasedDynamics::solve_ShapeMatchingConstraint, PositionBasedDynamics.cpp:500-558 (allowStretch = false) */
+static int solve_shapematching(const vec3 *x0, const vec3 *x, const real *w, int n, vec3 restCm, real k, vec3 *corr) {
+    for (int i = 0; i < n; i++) corr[i] = VZERO;
+    vec3 cm = VZERO; real wsum = R(0.0);
+    for (int i = 0; i < n; i++) { real wi = R(1.0) / (w[i] + EPS); cm = vadd(cm, vmul(x[i], wi)); wsum += wi; }
+    if (wsum == R(0.0)) return 0;
+    cm = V(cm.v[0] / wsum, cm.v[1] / wsum, cm.v[2] / wsum);
+    mat3 A; memset(&A, 0, sizeof(A));
+    for (int i = 0; i < n; i++) {
+        vec3 q = vsub(x0[i], restCm), pp = vsub(x[i], cm);
+        real wi = R(1.0) / (w[i] + EPS);
+        pp = vmul(pp, wi);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A.m[r][c] += pp.v[r] * q.v[c];
+    }
+    mat3 Rm;
+    polar_decomposition_stable(&A, EPS, &Rm);
+    for (int i = 0; i < n; i++) {
+        vec3 q = vsub(x0[i], restCm);
+        vec3 goal = vadd(cm, V(Rm.m[0][0] * q.v[0] + Rm.m[0][1] * q.v[1] + Rm.m[0][2] * q.v[2], Rm.m[1][0] * q.v[0] + Rm.m[1][1] * q.v[1] + Rm.m[1][2] * q.v[2],
+                               Rm.m[2][0] * q.v[0] + Rm.m[2][1] * q.v[1] + Rm.m[2][2] * q.v[2]));
+        corr[i] = vmul(vsub(goal, x[i]), k);
+    }
+    return 1;
 }
 
 /* PositionBasedDynamics::init_StrainTetraConstraint, PositionBasedDynamics.cpp:691-710 */
@@ -1054,6 +1140,14 @@ static int add_constraint(Model *m, int type, const unsigned *b, const real *u) 
         c->nb = 4; mat3 inv; memset(&inv, 0, sizeof(inv));
         ok = init_straintet(x0[b[0]], x0[b[1]], x0[b[2]], x0[b[3]], &inv);
         mat3_to_params(&inv, c->p); c->p[9] = u[0]; c->p[10] = u[1]; c->p[11] = u[2]; c->p[12] = u[3]; break; }
+    case ORC_SHAPEMATCHING: { /* Constraints.cpp:1985-2001: copies of x0 and invMass are frozen into the constraint; u = [k, nc0..nc3] */
+        c->nb = 4; c->p[0] = u[0];
+        vec3 q[4]; real w[4];
+        for (int i = 0; i < 4; i++) { q[i] = x0[b[i]]; w[i] = m->invMass[b[i]]; }
+        vec3 rc; ok = init_shapematching(q, w, 4, &rc);
+        for (int k = 0; k < 3; k++) c->p[1 + k] = rc.v[k];
+        for (int i = 0; i < 4; i++) { for (int k = 0; k < 3; k++) c->p[4 + 3 * i + k] = q[i].v[k]; c->p[16 + i] = w[i]; c->p[20 + i] = u[1 + i]; }
+        break; }
     default: ok = 0; break;
     }
     for (unsigned k = 0; k < c->nb; k++) c->b[k] = b[k];
@@ -1113,7 +1207,7 @@ void orc_add_bending_constraints(unsigned tmIdx, unsigned method, double k) {
     }
 }
 
-/* SimulationModel::addSolidConstraints, SimulationModel.cpp:1242-1349 (method 5, shape matching: not restated) */
+/* SimulationModel::addSolidConstraints, SimulationModel.cpp:1242-1349 */
 void orc_add_solid_constraints(unsigned tmIdx, unsigned method, double k, double nu, double volK, int normStretch, int normShear) {
     const TetModel *tm = &G->tets[tmIdx];
     const unsigned off = tm->offset;
@@ -1134,6 +1228,12 @@ void orc_add_solid_constraints(unsigned tmIdx, unsigned method, double k, double
         for (unsigned i = 0; i < tm->nTets; i++) {
             unsigned b[4] = {tm->tets[4 * i] + off, tm->tets[4 * i + 1] + off, tm->tets[4 * i + 2] + off, tm->tets[4 * i + 3] + off};
             add_constraint(G, method == 2 ? ORC_FEMTET : ORC_FEMTET_XPBD, b, u);
+        }
+    } else if (method == 5) { /* one 4-particle cluster per tet; corrections are divided by the number of clusters at the vertex */
+        for (unsigned i = 0; i < tm->nTets; i++) {
+            unsigned b[4] = {tm->tets[4 * i] + off, tm->tets[4 * i + 1] + off, tm->tets[4 * i + 2] + off, tm->tets[4 * i + 3] + off};
+            real u[8] = {(real)k, (real)tm->vertTets[b[0] - off], (real)tm->vertTets[b[1] - off], (real)tm->vertTets[b[2] - off], (real)tm->vertTets[b[3] - off]};
+            add_constraint(G, ORC_SHAPEMATCHING, b, u);
         }
     } else if (method == 4) {
         real u[8] = {(real)k, (real)k, (real)(normStretch != 0), (real)(normStretch != 0)};
@@ -1294,6 +1394,13 @@ static void solve_position_constraint(Model *m, Constraint *c, unsigned iter, re
         vec3 ks = V(c->p[9], c->p[9], c->p[9]), kh = V(c->p[10], c->p[10], c->p[10]);
         res = solve_straintet(x[b[0]], w[b[0]], x[b[1]], w[b[1]], x[b[2]], w[b[2]], x[b[3]], w[b[3]], &inv, ks, kh, c->p[11] != 0, c->p[12] != 0, &corr[0], &corr[1], &corr[2], &corr[3]);
         break; }
+    case ORC_SHAPEMATCHING: { /* Constraints.cpp:2003-2028: uses the frozen m_x0 / m_w copies; 1/numClusters averaging */
+        vec3 q0[4], xs[4]; real ws[4];
+        for (int i = 0; i < 4; i++) { q0[i] = V(c->p[4 + 3 * i], c->p[5 + 3 * i], c->p[6 + 3 * i]); xs[i] = x[b[i]]; ws[i] = c->p[16 + i]; }
+        if (solve_shapematching(q0, xs, ws, 4, V(c->p[1], c->p[2], c->p[3]), c->p[0], corr))
+            for (int i = 0; i < 4; i++)
+                if (ws[i] != R(0.0)) x[b[i]] = vadd(x[b[i]], vmul(corr[i], (real)(1.0 / (unsigned)c->p[20 + i])));
+        return; }
     default: break;
     }
     if (res)
@@ -1381,6 +1488,10 @@ int orc_kat_solve(int type, const double *xd, const double *wd, const double *pd
     case ORC_FEMTET: { mat3 inv = params_to_mat3(p + 1); res = solve_femtet(X[0], W[0], X[1], W[1], X[2], W[2], X[3], W[3], p[0], &inv, p[10], p[11], handleInversion, &C[0], &C[1], &C[2], &C[3]); break; }
     case ORC_FEMTET_XPBD: { mat3 inv = params_to_mat3(p + 1); res = solve_femtet_xpbd(X[0], W[0], X[1], W[1], X[2], W[2], X[3], W[3], p[0], &inv, p[10], p[11], handleInversion, dt, &lam, &C[0], &C[1], &C[2], &C[3]); break; }
     case ORC_STRAINTET: { mat3 inv = params_to_mat3(p); res = solve_straintet(X[0], W[0], X[1], W[1], X[2], W[2], X[3], W[3], &inv, V(p[9], p[9], p[9]), V(p[10], p[10], p[10]), p[11] != 0, p[12] != 0, &C[0], &C[1], &C[2], &C[3]); break; }
+    case ORC_SHAPEMATCHING: { /* raw solver answer (before the 1/numClusters averaging of the constraint class); w argument ignored: frozen copies in p */
+        vec3 q0[4]; real ws[4];
+        for (int i = 0; i < 4; i++) { q0[i] = V(p[4 + 3 * i], p[5 + 3 * i], p[6 + 3 * i]); ws[i] = p[16 + i]; }
+        res = solve_shapematching(q0, X, ws, 4, V(p[1], p[2], p[3]), p[0], C); break; }
     default: return -1;
     }
     *lambda = lam;

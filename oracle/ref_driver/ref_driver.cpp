@@ -126,6 +126,7 @@ int ref_add_constraint(int type, const unsigned *b, const double *p) {
     case T_FEMTET: return m.addFEMTetConstraint(b[0], b[1], b[2], b[3], (Real)p[0], (Real)p[1]);
     case T_FEMTET_XPBD: return m.addFEMTetConstraint_XPBD(b[0], b[1], b[2], b[3], (Real)p[0], (Real)p[1]);
     case T_STRAINTET: return m.addStrainTetConstraint(b[0], b[1], b[2], b[3], (Real)p[0], (Real)p[1], p[2] != 0, p[3] != 0);
+    case T_SHAPEMATCHING: { const unsigned nc[4] = {(unsigned)p[1], (unsigned)p[2], (unsigned)p[3], (unsigned)p[4]}; return m.addShapeMatchingConstraint(4, b, nc, (Real)p[0]); }
     default: return -1;
     }
 }
@@ -304,6 +305,10 @@ int ref_kat_solve(int type, const double *x, const double *w, const double *p, d
     case T_FEMTET: res = PositionBasedDynamics::solve_FEMTetraConstraint(X[0], W[0], X[1], W[1], X[2], W[2], X[3], W[3], (Real)p[0], m3(p + 1), (Real)p[10], (Real)p[11], handleInversion != 0, C[0], C[1], C[2], C[3]); break;
     case T_FEMTET_XPBD: res = XPBD::solve_FEMTetraConstraint(X[0], W[0], X[1], W[1], X[2], W[2], X[3], W[3], (Real)p[0], m3(p + 1), (Real)p[10], (Real)p[11], handleInversion != 0, (Real)dt, lam, C[0], C[1], C[2], C[3]); break;
     case T_STRAINTET: res = PositionBasedDynamics::solve_StrainTetraConstraint(X[0], W[0], X[1], W[1], X[2], W[2], X[3], W[3], m3(p), (Real)p[9] * Vector3r::Ones(), (Real)p[10] * Vector3r::Ones(), p[11] != 0, p[12] != 0, C[0], C[1], C[2], C[3]); break;
+    case T_SHAPEMATCHING: {  // raw solver answer; frozen x0 / w copies come from p (layout of ref_get_constraint)
+        Vector3r q0[4]; Real ws[4];
+        for (int i = 0; i < 4; i++) { q0[i] = v3(p + 4 + 3 * i); ws[i] = (Real)p[16 + i]; }
+        res = PositionBasedDynamics::solve_ShapeMatchingConstraint(q0, X, ws, 4, v3(p + 1), (Real)p[0], false, C); break; }
     default: return -1;
     }
     *lambda = lam;

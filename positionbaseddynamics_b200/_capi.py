@@ -11,10 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbd_b200.so")
 
 (DISTANCE, DISTANCE_XPBD, DIHEDRAL, ISOBENDING, ISOBENDING_XPBD, FEMTRIANGLE, STRAINTRIANGLE, VOLUME, VOLUME_XPBD,
- FEMTET, FEMTET_XPBD, STRAINTET) = range(12)
-NUM_TYPES = 12
+ FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING) = range(13)
+NUM_TYPES = 13
 TYPE_NAMES = ["Distance", "Distance_XPBD", "Dihedral", "IsometricBending", "IsometricBending_XPBD", "FEMTriangle",
-              "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet"]
+              "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching"]
 ATTR_X, ATTR_V, ATTR_X0, ATTR_OLDX, ATTR_LASTX = range(5)
 MODE_GRAPH, MODE_PERSISTENT, MODE_LAUNCH = 0, 1, 2
 

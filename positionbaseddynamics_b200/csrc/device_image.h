@@ -13,7 +13,7 @@
 namespace pbdk {
 
 constexpr int kMaxMat = 5;   // material parameters per type (stiffness, Young's moduli, Poisson ratios, flags)
-constexpr int kMaxGeoV = 4;  // float4 geometry arrays per type
+constexpr int kMaxGeoV = 6;  // float4 geometry arrays per type
 constexpr int kMaxGeoS = 2;  // scalar geometry arrays per type
 
 // Particle placement in the device arrays.  Layout 1 ("de-interleaved") puts the even-numbered particles first and the
@@ -65,6 +65,7 @@ inline TypeShape type_shape(int t) {
     case PBD_FEMTET:          return {4, 12, 2, 2, 2, false};
     case PBD_FEMTET_XPBD:     return {4, 12, 2, 2, 2, true};
     case PBD_STRAINTET:       return {4, 13, 2, 1, 4, false};
+    case PBD_SHAPEMATCHING:   return {4, 24, 6, 0, 1, false};
     default:                  return {0, 0, 0, 0, 0, false};
     }
 }
@@ -85,6 +86,7 @@ inline double algorithmic_bytes(int t, int isoVariant) {
     case PBD_FEMTET:          return 16 + 64 + 40 + 64;
     case PBD_FEMTET_XPBD:     return 16 + 64 + 40 + 64 + 8;
     case PBD_STRAINTET:       return 16 + 64 + 36 + 64;
+    case PBD_SHAPEMATCHING:   return 16 + 64 + 96 + 64;  // restCm + frozen x0[4] + w[4] + numClusters[4]
     default:                  return 0;
     }
 }

@@ -568,6 +568,19 @@ static int flatten(pbd_engine *e) {
             }
             for (int k = 0; k < 4; k++) matSlot[k] = 9 + k;
             break;
+        case PBD_SHAPEMATCHING:  // restCm | x0[0..3] packed in 3 float4 | w | numClusters ; stiffness is the material slot
+            for (int k = 0; k < 6; k++) gv[k].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) {
+                gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), 0.0f);
+                gv[1][i] = make_float4(P(i, 4), P(i, 5), P(i, 6), P(i, 7));
+                gv[2][i] = make_float4(P(i, 8), P(i, 9), P(i, 10), P(i, 11));
+                gv[3][i] = make_float4(P(i, 12), P(i, 13), P(i, 14), P(i, 15));
+                gv[4][i] = make_float4(P(i, 16), P(i, 17), P(i, 18), P(i, 19));
+                gv[5][i] = make_float4(P(i, 20), P(i, 21), P(i, 22), P(i, 23));
+                for (int k = 20; k < 24; k++) if (!(P(i, k) >= 1.0f)) return fail("ShapeMatching constraint: numClusters must be >= 1");
+            }
+            matSlot[0] = 0;
+            break;
         default: return fail("flatten: constraint type %d has no kernel", t);
         }
         d.arrays.variant = variant;
@@ -633,7 +646,7 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
     switch (b.type) {
         LB(PBD_DISTANCE) LB(PBD_DISTANCE_XPBD) LB(PBD_DIHEDRAL) LB(PBD_ISOBENDING) LB(PBD_ISOBENDING_XPBD)
         LB(PBD_FEMTRIANGLE) LB(PBD_STRAINTRIANGLE) LB(PBD_VOLUME) LB(PBD_VOLUME_XPBD) LB(PBD_FEMTET)
-        LB(PBD_FEMTET_XPBD) LB(PBD_STRAINTET)
+        LB(PBD_FEMTET_XPBD) LB(PBD_STRAINTET) LB(PBD_SHAPEMATCHING)
     default: return fail("no kernel for constraint type %d", b.type);
     }
 #undef LB

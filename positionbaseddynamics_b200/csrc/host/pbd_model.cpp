@@ -436,6 +436,28 @@ bool SimulationModel::addStrainTetConstraint(unsigned int i1, unsigned int i2, u
     return pushConstraint(PBD_STRAINTET, b, p, ok);
 }
 
+// ShapeMatchingConstraint::initConstraint (Constraints.cpp:1985-2001) + init_ShapeMatchingConstraint
+// (PositionBasedDynamics.cpp:479-497): rest positions and inverse masses are frozen into the constraint.
+bool SimulationModel::addShapeMatchingConstraint(unsigned int numberOfParticles, const unsigned int particleIndices[], const unsigned int numClusters[], Real stiffness) {
+    if (numberOfParticles != 4) return false;  // the accelerated path covers the tetrahedral clusters of addSolidConstraints
+    const ParticleData &pd = m_particles;
+    Real p[24];
+    p[0] = stiffness;
+    double cm[3] = {0, 0, 0}, wsum = 0.0;
+    for (int i = 0; i < 4; i++) {
+        const Vector3r &x0 = pd.m_x0[particleIndices[i]];
+        const Real w = pd.m_invMasses[particleIndices[i]];
+        const double wi = 1.0 / ((double)w + kEps);
+        for (int k = 0; k < 3; k++) { cm[k] += x0[k] * wi; p[4 + 3 * i + k] = x0[k]; }
+        wsum += wi;
+        p[16 + i] = w;
+        p[20 + i] = (Real)numClusters[i];
+    }
+    const bool ok = wsum != 0.0;
+    for (int k = 0; k < 3; k++) p[1 + k] = ok ? (Real)(cm[k] / wsum) : 0.0f;
+    return pushConstraint(PBD_SHAPEMATCHING, particleIndices, p, ok);
+}
+
 // SimulationModel::addClothConstraints (SimulationModel.cpp:1125-1184)
 void SimulationModel::addClothConstraints(const TriangleModel *tm, unsigned int clothMethod, Real distanceStiffness, Real xxStiffness, Real yyStiffness,
                                           Real xyStiffness, Real xyPoissonRatio, Real yxPoissonRatio, bool normalizeStretch, bool normalizeShear) {
@@ -478,8 +500,7 @@ void SimulationModel::addBendingConstraints(const TriangleModel *tm, unsigned in
     }
 }
 
-// SimulationModel::addSolidConstraints (SimulationModel.cpp:1242-1349).  Method 5 (shape matching) is not on the
-// accelerated path yet and adds nothing.
+// SimulationModel::addSolidConstraints (SimulationModel.cpp:1242-1349)
 void SimulationModel::addSolidConstraints(const TetModel *tm, unsigned int solidMethod, Real stiffness, Real poissonRatio, Real volumeStiffness,
                                           bool normalizeStretch, bool /*normalizeShear*/) {
     const IndexedTetMesh &mesh = tm->getParticleMesh();
@@ -494,6 +515,14 @@ void SimulationModel::addSolidConstraints(const TetModel *tm, unsigned int solid
         for (unsigned int i = 0; i < nTets; i++) {
             if (solidMethod == 1) addVolumeConstraint(tets[4 * i] + offset, tets[4 * i + 1] + offset, tets[4 * i + 2] + offset, tets[4 * i + 3] + offset, volumeStiffness);
             else addVolumeConstraint_XPBD(tets[4 * i] + offset, tets[4 * i + 1] + offset, tets[4 * i + 2] + offset, tets[4 * i + 3] + offset, volumeStiffness);
+        }
+    } else if (solidMethod == 5) {
+        const std::vector<unsigned int> &vt = mesh.getVertexTetCounts();
+        for (unsigned int i = 0; i < nTets; i++) {
+            const unsigned int v[4] = {tets[4 * i] + offset, tets[4 * i + 1] + offset, tets[4 * i + 2] + offset, tets[4 * i + 3] + offset};
+            // divide the correction by the number of clusters containing the vertex (SimulationModel.cpp:1322-1325)
+            const unsigned int nc[4] = {vt[v[0] - offset], vt[v[1] - offset], vt[v[2] - offset], vt[v[3] - offset]};
+            addShapeMatchingConstraint(4, v, nc, stiffness);
         }
     } else if (solidMethod >= 2 && solidMethod <= 4) {
         for (unsigned int i = 0; i < nTets; i++) {
@@ -524,6 +553,7 @@ void SimulationModel::setClothNormalizeStretch(bool v) { setParam(PBD_STRAINTRIA
 void SimulationModel::setClothNormalizeShear(bool v) { setParam(PBD_STRAINTRIANGLE, 8, v ? 1.0f : 0.0f); }
 void SimulationModel::setSolidStiffness(Real v) {
     setParam(PBD_FEMTET, 10, v); setParam(PBD_FEMTET_XPBD, 10, v); setParam(PBD_STRAINTET, 9, v); setParam(PBD_STRAINTET, 10, v);
+    setParam(PBD_SHAPEMATCHING, 0, v);
 }
 void SimulationModel::setSolidPoissonRatio(Real v) { setParam(PBD_FEMTET, 11, v); setParam(PBD_FEMTET_XPBD, 11, v); }
 void SimulationModel::setSolidVolumeStiffness(Real v) { setParam(PBD_VOLUME, 1, v); setParam(PBD_VOLUME_XPBD, 1, v); }

@@ -208,6 +208,8 @@ public:
     bool addFEMTetConstraint_XPBD(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stiffness, Real poissonRatio);
     bool addStrainTetConstraint(unsigned int p1, unsigned int p2, unsigned int p3, unsigned int p4, Real stretchStiffness, Real shearStiffness,
                                 bool normalizeStretch, bool normalizeShear);
+    // clusters of exactly 4 particles (what addSolidConstraints method 5 creates); other cluster sizes are rejected
+    bool addShapeMatchingConstraint(unsigned int numberOfParticles, const unsigned int particleIndices[], const unsigned int numClusters[], Real stiffness);
 
     void addClothConstraints(const TriangleModel *tm, unsigned int clothMethod, Real distanceStiffness, Real xxStiffness, Real yyStiffness,
                              Real xyStiffness, Real xyPoissonRatio, Real yxPoissonRatio, bool normalizeStretch, bool normalizeShear);

@@ -99,6 +99,7 @@ int pbdm_add_constraint(pbdm_model *m, int type, const unsigned *b, const float 
     case PBD_FEMTET: return M.addFEMTetConstraint(b[0], b[1], b[2], b[3], a[0], a[1]);
     case PBD_FEMTET_XPBD: return M.addFEMTetConstraint_XPBD(b[0], b[1], b[2], b[3], a[0], a[1]);
     case PBD_STRAINTET: return M.addStrainTetConstraint(b[0], b[1], b[2], b[3], a[0], a[1], a[2] != 0, a[3] != 0);
+    case PBD_SHAPEMATCHING: { const unsigned nc[4] = {(unsigned)a[1], (unsigned)a[2], (unsigned)a[3], (unsigned)a[4]}; return M.addShapeMatchingConstraint(4, b, nc, a[0]); }
     default: return 0;
     }
 }

@@ -116,6 +116,9 @@ __device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &
         inv.m[2][2] = s.s0;
         if (T == PBD_STRAINTET) project_straintet(p0, p1, p2, p3, inv, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i) != 0.0f, matv(a, 3, i) != 0.0f);
         else project_femtet<(T == PBD_FEMTET_XPBD)>(p0, p1, p2, p3, s.s1, inv, matv(a, 0, i), matv(a, 1, i), dt, lam);
+    } else if (T == PBD_SHAPEMATCHING) {
+        project_shapematching(p0, p1, p2, p3, __ldg(a.gv[0] + i), __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), __ldg(a.gv[4] + i),
+                              __ldg(a.gv[5] + i), matv(a, 0, i));
     }
 
     if (XPBD) __stcg(a.lambda + i, lam);
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(kProjectThreads) k_project_multi(float4 *pos, 
                         project_streamed<T, CA>(pos, a, ci, st, dt, iterZero != 0); } break;
     switch (m.type[s]) {
         PM(PBD_DISTANCE) PM(PBD_DISTANCE_XPBD) PM(PBD_DIHEDRAL) PM(PBD_ISOBENDING) PM(PBD_ISOBENDING_XPBD) PM(PBD_FEMTRIANGLE)
-        PM(PBD_STRAINTRIANGLE) PM(PBD_VOLUME) PM(PBD_VOLUME_XPBD) PM(PBD_FEMTET) PM(PBD_FEMTET_XPBD) PM(PBD_STRAINTET)
+        PM(PBD_STRAINTRIANGLE) PM(PBD_VOLUME) PM(PBD_VOLUME_XPBD) PM(PBD_FEMTET) PM(PBD_FEMTET_XPBD) PM(PBD_STRAINTET) PM(PBD_SHAPEMATCHING)
     default: break;
     }
 #undef PM

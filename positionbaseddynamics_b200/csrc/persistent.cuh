@@ -102,7 +102,7 @@ template <int N, class F> __device__ __forceinline__ void static_for(F &&f) { st
 // per-type shape of the staged data: bodies, 16-byte streamed slots per constraint
 template <int T> struct Staged {
     static constexpr int NB = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 2 : ((T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) ? 3 : 4);
-    static constexpr int NS = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 1 : ((T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) ? 4 : 2);
+    static constexpr int NS = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD || T == PBD_SHAPEMATCHING) ? 1 : ((T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) ? 4 : 2);
     static constexpr bool XPBD = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
 };
 template <int T, int THREADS> struct PerThread {
@@ -132,6 +132,7 @@ constexpr unsigned kMaskAll = (1u << PBD_NUM_TYPES) - 1u;
     case PBD_FEMTET:          if constexpr ((MASK) & type_bit(PBD_FEMTET))          { constexpr int T = PBD_FEMTET;          __VA_ARGS__ } break; \
     case PBD_FEMTET_XPBD:     if constexpr ((MASK) & type_bit(PBD_FEMTET_XPBD))     { constexpr int T = PBD_FEMTET_XPBD;     __VA_ARGS__ } break; \
     case PBD_STRAINTET:       if constexpr ((MASK) & type_bit(PBD_STRAINTET))       { constexpr int T = PBD_STRAINTET;       __VA_ARGS__ } break; \
+    case PBD_SHAPEMATCHING:   if constexpr ((MASK) & type_bit(PBD_SHAPEMATCHING))   { constexpr int T = PBD_SHAPEMATCHING;   __VA_ARGS__ } break; \
     default: break;                                                                                                      \
     }
 
@@ -251,6 +252,11 @@ __device__ __forceinline__ void project_pass(float4 *pos, const TypeArrays &a, c
                 inv.m[2][2] = sc.x;
                 if (T == PBD_STRAINTET) project_straintet(p0, p1, p2, p3, inv, matv(a, 0, i), matv(a, 1, i), matv(a, 2, i) != 0.0f, matv(a, 3, i) != 0.0f);
                 else project_femtet<(T == PBD_FEMTET_XPBD)>(p0, p1, p2, p3, sc.y, inv, matv(a, 0, i), matv(a, 1, i), dt, lam);
+            }
+
+            else if (T == PBD_SHAPEMATCHING) {  // only the indices are staged; the 96 B of frozen rest data stream straight from global
+                project_shapematching(p0, p1, p2, p3, __ldg(a.gv[0] + i), __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), __ldg(a.gv[4] + i),
+                                      __ldg(a.gv[5] + i), matv(a, 0, i));
             }
 
             if (Staged<T>::XPBD) __stcg(a.lambda + i, lam);

@@ -626,4 +626,118 @@ __device__ __forceinline__ void project_straintriangle(float4 &q0, float4 &q1, f
     apply(q0, c0); apply(q1, c1); apply(q2, c2);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shape matching on 4-particle clusters.  ShapeMatchingConstraint::solvePositionConstraint (Constraints.cpp:2003-2028),
+// PositionBasedDynamics::solve_ShapeMatchingConstraint (PositionBasedDynamics.cpp:500-558, allowStretch = false),
+// MathFunctions::polarDecompositionStable (MathFunctions.cpp:180-255).  x0[] and w[] are the copies frozen into the
+// constraint at creation (Constraints.cpp:1985-2001); corrections are divided by the number of clusters at the vertex.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float one_norm_cols(const M3 &A) {  // max column sum
+    const float s0 = fabsf(A.m[0][0]) + fabsf(A.m[1][0]) + fabsf(A.m[2][0]);
+    const float s1 = fabsf(A.m[0][1]) + fabsf(A.m[1][1]) + fabsf(A.m[2][1]);
+    const float s2 = fabsf(A.m[0][2]) + fabsf(A.m[1][2]) + fabsf(A.m[2][2]);
+    return fmaxf(s0, fmaxf(s1, s2));
+}
+__device__ __forceinline__ float inf_norm_rows(const M3 &A) {  // max row sum
+    const float s0 = fabsf(A.m[0][0]) + fabsf(A.m[0][1]) + fabsf(A.m[0][2]);
+    const float s1 = fabsf(A.m[1][0]) + fabsf(A.m[1][1]) + fabsf(A.m[1][2]);
+    const float s2 = fabsf(A.m[2][0]) + fabsf(A.m[2][1]) + fabsf(A.m[2][2]);
+    return fmaxf(s0, fmaxf(s1, s2));
+}
+__device__ __forceinline__ V3 row3(const M3 &A, int r) { return mk(A.m[r][0], A.m[r][1], A.m[r][2]); }
+__device__ __forceinline__ void set_row3(M3 &A, int r, V3 v) { A.m[r][0] = v.x; A.m[r][1] = v.y; A.m[r][2] = v.z; }
+
+// Mt holds M^T on entry; returns the rotation R = (converged Mt)^T
+__device__ __noinline__ void polar_decomposition_stable(M3 Mt, float tolerance, M3 &R) {
+    // ||M||_1 = ||M^T||_inf and vice versa
+    float Mone = inf_norm_rows(Mt), Minf = one_norm_cols(Mt), Eone;
+    M3 Adj;
+    int guard = 0;
+    do {
+        set_row3(Adj, 0, cross(row3(Mt, 1), row3(Mt, 2)));
+        set_row3(Adj, 1, cross(row3(Mt, 2), row3(Mt, 0)));
+        set_row3(Adj, 2, cross(row3(Mt, 0), row3(Mt, 1)));
+        float det = Mt.m[0][0] * Adj.m[0][0] + Mt.m[0][1] * Adj.m[0][1] + Mt.m[0][2] * Adj.m[0][2];
+        if (fabsf(det) < 1.0e-12f) {
+            int index = -1;
+            if (sq(row3(Adj, 0)) > 1.0e-12f) index = 0;
+            else if (sq(row3(Adj, 1)) > 1.0e-12f) index = 1;
+            else if (sq(row3(Adj, 2)) > 1.0e-12f) index = 2;
+            if (index < 0) {
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) R.m[i][j] = (i == j) ? 1.0f : 0.0f;
+                return;
+            }
+            // replace the degenerate row by the cross product of the other two, refresh the affected adjugate rows
+            if (index == 0) { set_row3(Mt, 0, cross(row3(Mt, 1), row3(Mt, 2))); set_row3(Adj, 1, cross(row3(Mt, 2), row3(Mt, 0))); set_row3(Adj, 2, cross(row3(Mt, 0), row3(Mt, 1))); }
+            else if (index == 1) { set_row3(Mt, 1, cross(row3(Mt, 2), row3(Mt, 0))); set_row3(Adj, 2, cross(row3(Mt, 0), row3(Mt, 1))); set_row3(Adj, 0, cross(row3(Mt, 1), row3(Mt, 2))); }
+            else { set_row3(Mt, 2, cross(row3(Mt, 0), row3(Mt, 1))); set_row3(Adj, 0, cross(row3(Mt, 1), row3(Mt, 2))); set_row3(Adj, 1, cross(row3(Mt, 2), row3(Mt, 0))); }
+            Mone = inf_norm_rows(Mt); Minf = one_norm_cols(Mt);
+            det = Mt.m[0][0] * Adj.m[0][0] + Mt.m[0][1] * Adj.m[0][1] + Mt.m[0][2] * Adj.m[0][2];
+        }
+        const float AdjOne = one_norm_cols(Adj), AdjInf = inf_norm_rows(Adj);
+        const float gamma = sqrtf(sqrtf((AdjOne * AdjInf) / (Mone * Minf)) / fabsf(det));
+        const float g1 = gamma * 0.5f;
+        const float g2 = 0.5f / (gamma * det);
+        M3 E;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const float old = Mt.m[i][j];
+                Mt.m[i][j] = g1 * old + g2 * Adj.m[i][j];
+                E.m[i][j] = old - Mt.m[i][j];
+            }
+        Eone = one_norm_cols(E);
+        Mone = one_norm_cols(Mt); Minf = inf_norm_rows(Mt);
+    } while (Eone > Mone * tolerance && ++guard < 64);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) R.m[i][j] = Mt.m[j][i];
+}
+
+__device__ __forceinline__ void project_shapematching(float4 &q0, float4 &q1, float4 &q2, float4 &q3, float4 rc, float4 a0, float4 a1,
+                                                      float4 a2, float4 w, float4 nc, float k) {
+    const V3 x[4] = {xyz(q0), xyz(q1), xyz(q2), xyz(q3)};
+    const V3 x0[4] = {mk(a0.x, a0.y, a0.z), mk(a0.w, a1.x, a1.y), mk(a1.z, a1.w, a2.x), mk(a2.y, a2.z, a2.w)};
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+    const V3 restCm = mk(rc.x, rc.y, rc.z);
+    V3 cm = mk(0.f, 0.f, 0.f);
+    float wsum = 0.0f;
+    float wi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { wi[i] = 1.0f / (ww[i] + PBD_EPS); cm = cm + x[i] * wi[i]; wsum += wi[i]; }
+    if (wsum == 0.0f) return;
+    cm = cm * (1.0f / wsum);
+    M3 At;  // A^T, A = sum w_i (x_i - cm)(x0_i - restCm)^T
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) At.m[r][c] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const V3 q = x0[i] - restCm;
+        const V3 p = (x[i] - cm) * wi[i];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) At.m[c][r] += comp(p, r) * comp(q, c);
+    }
+    M3 R;
+    polar_decomposition_stable(At, PBD_EPS, R);
+    const float inc[4] = {1.0f / nc.x, 1.0f / nc.y, 1.0f / nc.z, 1.0f / nc.w};
+    float4 *qs[4] = {&q0, &q1, &q2, &q3};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const V3 q = x0[i] - restCm;
+        const V3 goal = cm + mk(R.m[0][0] * q.x + R.m[0][1] * q.y + R.m[0][2] * q.z, R.m[1][0] * q.x + R.m[1][1] * q.y + R.m[1][2] * q.z,
+                                R.m[2][0] * q.x + R.m[2][1] * q.y + R.m[2][2] * q.z);
+        const V3 corr = (goal - x[i]) * k;
+        if (ww[i] != 0.0f) { qs[i]->x += inc[i] * corr.x; qs[i]->y += inc[i] * corr.y; qs[i]->z += inc[i] * corr.z; }  // tests the frozen m_w, not the live invMass
+    }
+}
+
 }  // namespace pbdk

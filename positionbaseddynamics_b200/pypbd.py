@@ -129,6 +129,9 @@ class SimulationModel:
     def addFEMTetConstraint_XPBD(self, p1, p2, p3, p4, k, nu): return bool(self._host.add_constraint(_capi.FEMTET_XPBD, [p1, p2, p3, p4], [k, nu]))
     def addStrainTetConstraint(self, p1, p2, p3, p4, ks, kh, ns, nsh): return bool(self._host.add_constraint(_capi.STRAINTET, [p1, p2, p3, p4], [ks, kh, float(ns), float(nsh)]))
 
+    def addShapeMatchingConstraint(self, n, indices, numClusters, k):
+        return bool(self._host.add_constraint(_capi.SHAPEMATCHING, list(indices)[:4], [k] + [float(c) for c in list(numClusters)[:4]])) if n == 4 else False
+
     def initConstraintGroups(self): self._host.init_groups()
 
     def getConstraintGroups(self):

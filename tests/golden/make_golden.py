@@ -17,12 +17,12 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import pyoracle  # noqa: E402
 from oracle.pyoracle import (DISTANCE, DISTANCE_XPBD, DIHEDRAL, ISOBENDING, ISOBENDING_XPBD, FEMTRIANGLE, STRAINTRIANGLE,  # noqa: E402
-                             VOLUME, VOLUME_XPBD, FEMTET, FEMTET_XPBD, STRAINTET)
+                             VOLUME, VOLUME_XPBD, FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING)
 import scenes  # noqa: E402
 from parity_util import perturb  # noqa: E402
 
 SOLVE_TYPES = [DISTANCE, DISTANCE_XPBD, DIHEDRAL, ISOBENDING, ISOBENDING_XPBD, FEMTRIANGLE, STRAINTRIANGLE, VOLUME, VOLUME_XPBD,
-               FEMTET, FEMTET_XPBD, STRAINTET]
+               FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING]
 INIT_TYPES = [ISOBENDING, FEMTRIANGLE, STRAINTRIANGLE, FEMTET, STRAINTET]
 
 
@@ -54,6 +54,8 @@ def material(rng, ctype):
         return [rng.choice([1.0e6, 1.0e3, 1.0]), rng.choice([0.3, 0.45, 0.0])]
     if ctype == STRAINTET:
         return [1.0, 0.7, float(rng.randint(2)), float(rng.randint(2))]
+    if ctype == SHAPEMATCHING:
+        return [rng.choice([1.0, 0.5]), 1.0, 1.0, 1.0, 1.0]  # stiffness, numClusters = 1 (raw solver answer == applied correction)
     raise ValueError(ctype)
 
 
@@ -74,13 +76,15 @@ def make_kat(ref, n_per_type=24, seed=1234):
             _, _, params, _ = ref.constraints()
             p = params[0]
             w = rng.choice([1.0, 0.5, 2.0, 0.0], size=4, p=[0.5, 0.2, 0.15, 0.15])
+            if ctype == SHAPEMATCHING:
+                w[:] = 1.0  # the constraint uses the inverse masses frozen at creation (all 1 here), not these
             amp = rng.choice([0.02, 0.2, 0.0], p=[0.5, 0.4, 0.1])
             x = x0 + rng.uniform(-amp, amp, (4, 3))
             if ctype in (FEMTET, FEMTET_XPBD) and c % 4 == 3:   # inverted element -> SVD branch
                 x[3] = x[0] + (x[0] - x[3]) * 0.7
             if ctype in (DISTANCE, DISTANCE_XPBD) and c % 8 == 7:  # coincident points (d <= 1e-6 early-out / zero normal)
                 x[1] = x[0]
-            if c % 12 == 11:
+            if c % 12 == 11 and ctype != SHAPEMATCHING:
                 w[:] = 0.0  # all static
             lam0 = rng.choice([0.0, rng.uniform(-1e-3, 1e-3)])
             hinv = (c % 4 == 3) or (c % 5 == 0)
@@ -130,6 +134,7 @@ STRUCT_SCENES = {
     "bar_fem_vol_9x4x4": lambda m: scenes.bar(m, 9, 4, 4, 2, extra_volume=True),
     "bar_strain_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 4),
     "bar_xpbd_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 6, k=1e5, vol_k=1e5),
+    "bar_shapematching_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 5, k=0.5),
     "bar_femx_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 3),
 }
 
@@ -145,6 +150,7 @@ TRAJ_SCENES = {
     "bar_fem": (lambda m: scenes.bar(m, 7, 4, 4, 2, k=1e6, sub_steps=2, max_iter=3), 0.01, 3),
     "bar_femx": (lambda m: scenes.bar(m, 7, 4, 4, 3, k=1e4, sub_steps=2, max_iter=3), 0.01, 1),  # XPBD-FEM is chaotic beyond one step
     "bar_strain": (lambda m: scenes.bar(m, 7, 4, 4, 4, k=1.0, sub_steps=2, max_iter=3), 0.01, 3),
+    "bar_shapematching": (lambda m: scenes.bar(m, 7, 4, 4, 5, k=0.5, sub_steps=2, max_iter=3), 0.02, 3),
     "bar_xpbd": (lambda m: scenes.bar(m, 7, 4, 4, 6, k=1e5, vol_k=1e5, sub_steps=2, max_iter=3), 0.01, 3),
     "bar_fem_vol": (lambda m: scenes.bar(m, 7, 4, 4, 2, k=1e6, extra_volume=True, sub_steps=3, max_iter=2), 0.01, 3),
     "cloth_second_order_12": (lambda m: scenes.cloth(m, 12, 12, 1, 0, max_iter=3, sub_steps=2, vel_method=1), 0.02, 4),

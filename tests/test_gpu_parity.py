@@ -33,6 +33,7 @@ SCENES = {
     # by 7e-5 relative after ONE step of this scene and by O(1) after three (DESIGN.md "Parity"); one step, E = 1e4.
     "bar_femtet_xpbd": (lambda m: scenes.bar(m, 7, 4, 4, 3, k=1.0e4, sub_steps=2, max_iter=3), 0.01, 1),
     "bar_straintet": (lambda m: scenes.bar(m, 9, 4, 4, 4, k=1.0, sub_steps=2, max_iter=3), 0.01, 3),
+    "bar_shapematching": (lambda m: scenes.bar(m, 9, 4, 4, 5, k=0.5, sub_steps=2, max_iter=3), 0.02, 3),
     "bar_distance_volume_xpbd": (lambda m: scenes.bar(m, 9, 4, 4, 6, k=1.0e5, vol_k=1.0e5, sub_steps=2, max_iter=3), 0.01, 3),
     "bar_fem_plus_volume": (lambda m: scenes.bar(m, 9, 4, 4, 2, k=1.0e6, extra_volume=True, sub_steps=3, max_iter=2), 0.01, 3),
     # cfg4 without rigid bodies: cloth (FEMTriangle + IsometricBending) and a tet solid (FEMTet) in one model
@@ -133,7 +134,7 @@ def test_known_answers_against_reference_golden():
             assert err <= 2e-3, (int(T[i]), int(i), err, got[j], ref)
         eng.close()
     print("GPU known answers, worst relative error per type:", {_capi.TYPE_NAMES[k]: "%.1e" % v for k, v in sorted(worst.items())})
-    assert len(worst) == 12
+    assert len(worst) == 13
 
 
 def test_engine_level_drop_in(cpu_libs):

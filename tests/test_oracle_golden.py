@@ -9,7 +9,7 @@ import pytest
 
 import scenes
 from golden.make_golden import STRUCT_SCENES, TRAJ_SCENES
-from oracle.pyoracle import NPARAMS, ISOBENDING, ISOBENDING_XPBD
+from oracle.pyoracle import NPARAMS, ISOBENDING, ISOBENDING_XPBD, SHAPEMATCHING
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOLS = {"f32": 3e-5, "f64": 1e-9}
