@@ -35,11 +35,16 @@ typedef struct pbd_engine pbd_engine;
  *  PBD_FEMTET_XPBD          4       volume, invRestMat[9], E, nu                  (+lambda)  XPBD_FEMTetConstraint        Constraints.cpp:1830-1906
  *  PBD_STRAINTET            4       invRestMat[9], stretchK, shearK, normStretch, normShear  StrainTetConstraint          Constraints.cpp:1912-1980
  *  PBD_SHAPEMATCHING        4       stiffness, restCm[3], x0[4][3], w[4], numClusters[4]     ShapeMatchingConstraint (4-particle clusters) :1985-2028
+ *  PBD_BALLJOINT            2 (rigid body, rigid body)      jointInfo[3x4] column by column  BallJoint                    Constraints.cpp:54-125
+ *  PBD_RB_PARTICLE_BALLJOINT 2 (rigid body, particle)       jointInfo[3x2] column by column  RigidBodyParticleBallJoint   Constraints.cpp:925-987
+ *  (joints: only the local connector columns are read, the global ones are recomputed at every solve as
+ *   updateConstraint does; rigid bodies must be uploaded with pbd_set_rigid_bodies before joints are added)
  */
 enum pbd_constraint_type {
     PBD_DISTANCE = 0, PBD_DISTANCE_XPBD = 1, PBD_DIHEDRAL = 2, PBD_ISOBENDING = 3, PBD_ISOBENDING_XPBD = 4,
     PBD_FEMTRIANGLE = 5, PBD_STRAINTRIANGLE = 6, PBD_VOLUME = 7, PBD_VOLUME_XPBD = 8, PBD_FEMTET = 9,
-    PBD_FEMTET_XPBD = 10, PBD_STRAINTET = 11, PBD_SHAPEMATCHING = 12, PBD_NUM_TYPES = 13
+    PBD_FEMTET_XPBD = 10, PBD_STRAINTET = 11, PBD_SHAPEMATCHING = 12,
+    PBD_BALLJOINT = 13, PBD_RB_PARTICLE_BALLJOINT = 14, PBD_NUM_TYPES = 15
 };
 
 /* particle attributes (ParticleData, Simulation/ParticleData.h:91-100); host layout = packed 3 floats per particle,
@@ -76,6 +81,14 @@ int pbd_set_particles(pbd_engine *e, unsigned n, const float *x, const float *x0
 int pbd_set_attr(pbd_engine *e, int attr, const float *src);  /* host -> device, n*3 floats */
 int pbd_get_attr(pbd_engine *e, int attr, float *dst);        /* device -> host, n*3 floats; synchronises */
 int pbd_set_masses(pbd_engine *e, const float *mass);
+
+/* Rigid bodies taking part in the coloured sweep through BallJoint / RigidBodyParticleBallJoint (SURVEY.md 8f-1;
+ * Simulation/RigidBody.h:84-120 initBody with explicit mass and principal inertia).  mass[n], x[3n], q[4n] as (w,x,y,z),
+ * inertia[3n] (principal moments), v[3n] / omega[3n] may be NULL (= 0).  old/last state = current, like initBody.
+ * pbd_get_rigid_bodies: any output may be NULL. */
+int pbd_set_rigid_bodies(pbd_engine *e, unsigned n, const float *mass, const float *x, const float *q, const float *inertia,
+                         const float *v, const float *omega);
+int pbd_get_rigid_bodies(pbd_engine *e, float *x, float *q, float *v, float *omega);
 
 /* Constraints.  `bodies`: count*numBodies(type) particle indices; `params`: count*numParams(type) floats in the
  * layout above; `ids`: the constraint's index in the reference's SimulationModel::m_constraints (insertion order),

@@ -40,6 +40,14 @@ int pbdm_get_particles(pbdm_model *m, int attr, float *out);       /* n*3 floats
 int pbdm_set_particles(pbdm_model *m, int attr, const float *in);  /* n*3 floats */
 const float *pbdm_vertices(pbdm_model *m);  /* zero-copy view of m_x (pyPBD getVertices); pulls from the device first */
 
+/* rigid bodies coupled to particles through ball joints: RigidBody::initBody(mass, x, inertiaTensor, rotation)
+ * (Simulation/RigidBody.h:84-120, q = (w,x,y,z)), SimulationModel::addBallJoint / addRigidBodyParticleBallJoint
+ * (SimulationModel.cpp:306-317, 449-460) via pbdm_add_constraint(PBD_BALLJOINT, {rb0, rb1}, pos[3]) and
+ * pbdm_add_constraint(PBD_RB_PARTICLE_BALLJOINT, {rb, particle}, NULL). */
+unsigned pbdm_add_rigid_body(pbdm_model *m, float mass, const float *x3, const float *inertia3, const float *q4);
+unsigned pbdm_num_rigid_bodies(pbdm_model *m);
+void pbdm_get_rigid_bodies(pbdm_model *m, float *out13);  /* per body: x(3) q(w,x,y,z) v(3) omega(3) */
+
 /* constraints */
 int pbdm_add_constraint(pbdm_model *m, int type, const unsigned *bodies, const float *args);  /* args = the add<X>Constraint arguments after the indices */
 void pbdm_add_cloth_constraints(pbdm_model *m, unsigned triModel, unsigned clothMethod, float distanceStiffness, float xxStiffness, float yyStiffness,

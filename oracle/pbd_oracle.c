@@ -92,6 +92,36 @@ static inline mat3 transpose3(const mat3 *a) {
 }
 static inline vec3 mcol(const mat3 *a, int c) { return V(a->m[0][c], a->m[1][c], a->m[2][c]); }
 
+/* quaternion (w, x, y, z); Eigen semantics for product, conjugate, matrix() and normalize() */
+typedef struct { real w, x, y, z; } quat;
+static inline quat qmul(quat a, quat b) {
+    quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+static inline quat qconj(quat a) { quat r = {a.w, -a.x, -a.y, -a.z}; return r; }
+static inline quat qnormalize(quat a) {
+    real n = RSQRT(a.w * a.w + a.x * a.x + a.y * a.y + a.z * a.z);
+    quat r = {a.w / n, a.x / n, a.y / n, a.z / n};
+    return r;
+}
+static inline mat3 qmatrix(quat q) {
+    mat3 m;
+    const real tx = R(2.0) * q.x, ty = R(2.0) * q.y, tz = R(2.0) * q.z;
+    const real twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    m.m[0][0] = R(1.0) - (tyy + tzz); m.m[0][1] = txy - twz; m.m[0][2] = txz + twy;
+    m.m[1][0] = txy + twz; m.m[1][1] = R(1.0) - (txx + tzz); m.m[1][2] = tyz - twx;
+    m.m[2][0] = txz - twy; m.m[2][1] = tyz + twx; m.m[2][2] = R(1.0) - (txx + tyy);
+    return m;
+}
+static inline vec3 mvec(const mat3 *a, vec3 v) {
+    return V(a->m[0][0] * v.v[0] + a->m[0][1] * v.v[1] + a->m[0][2] * v.v[2], a->m[1][0] * v.v[0] + a->m[1][1] * v.v[1] + a->m[1][2] * v.v[2],
+             a->m[2][0] * v.v[0] + a->m[2][1] * v.v[1] + a->m[2][2] * v.v[2]);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* MathFunctions (PositionBasedDynamics/MathFunctions.cpp)                                           */
 /* ------------------------------------------------------------------------------------------------ */
@@ -806,8 +836,18 @@ typedef struct {
     unsigned *vertTets; /* number of tets per vertex */
 } TetModel;
 
+/* Simulation/RigidBody.h:17-68 (state used on this path) */
+typedef struct {
+    real mass, invMass;
+    vec3 x, lastX, oldX, x0, v, a, omega, torque;
+    vec3 inertia, inertiaInv;
+    mat3 rot, inertiaW, inertiaInvW;
+    quat q, lastQ, oldQ, q0;
+} RigidBody;
+
 typedef struct {
     unsigned n, cap;
+    RigidBody *rbs; unsigned nRb;
     vec3 *x0, *x, *v, *a, *oldX, *lastX;
     real *mass, *invMass;
     Constraint *cons; unsigned nCons, capCons;
@@ -825,7 +865,7 @@ static void model_free(Model *m) {
     free(m->cons);
     for (unsigned i = 0; i < m->nTris; i++) { free(m->tris[i].faces); free(m->tris[i].edges); }
     for (unsigned i = 0; i < m->nTetModels; i++) { free(m->tets[i].tets); free(m->tets[i].edges); free(m->tets[i].vertTets); }
-    free(m->tris); free(m->tets); free(m->groupOff); free(m->groupIds);
+    free(m->tris); free(m->tets); free(m->groupOff); free(m->groupIds); free(m->rbs);
     free(m);
 }
 
@@ -1076,6 +1116,92 @@ void orc_add_tet_model(unsigned nPoints, unsigned nTets, const double *pts, cons
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* rigid bodies and the two joints that couple them to particles                     */
+/* ------------------------------------------------------------------------------------------------ */
+/* RigidBody::rotationUpdated + updateInertiaW, RigidBody.h:190-207 */
+static void rb_rotation_updated(RigidBody *b) {
+    if (b->mass == R(0.0)) return;
+    b->rot = qmatrix(b->q);
+    mat3 rt = transpose3(&b->rot), d, t;
+    memset(&d, 0, sizeof(d));
+    for (int k = 0; k < 3; k++) d.m[k][k] = b->inertia.v[k];
+    t = mul3(&b->rot, &d); b->inertiaW = mul3(&t, &rt);
+    for (int k = 0; k < 3; k++) d.m[k][k] = b->inertiaInv.v[k];
+    t = mul3(&b->rot, &d); b->inertiaInvW = mul3(&t, &rt);
+}
+
+/* RigidBody::initBody(mass, x, inertiaTensor, rotation, ...), RigidBody.h:84-120 */
+unsigned orc_add_rigid_body(double mass, const double *x, const double *inertia, const double *q) {
+    Model *m = G;
+    m->rbs = (RigidBody *)realloc(m->rbs, (size_t)(m->nRb + 1) * sizeof(RigidBody));
+    RigidBody *b = &m->rbs[m->nRb];
+    memset(b, 0, sizeof(*b));
+    b->mass = (real)mass; b->invMass = ((real)mass != R(0.0)) ? R(1.0) / (real)mass : R(0.0);
+    b->x = b->x0 = b->lastX = b->oldX = V((real)x[0], (real)x[1], (real)x[2]);
+    b->inertia = V((real)inertia[0], (real)inertia[1], (real)inertia[2]);
+    b->inertiaInv = V(R(1.0) / b->inertia.v[0], R(1.0) / b->inertia.v[1], R(1.0) / b->inertia.v[2]);
+    quat qq = {(real)q[0], (real)q[1], (real)q[2], (real)q[3]};
+    b->q = b->q0 = b->lastQ = b->oldQ = qq;
+    b->rot = qmatrix(qq);
+    rb_rotation_updated(b);
+    m->groupsInit = 0;
+    return m->nRb++;
+}
+unsigned orc_num_rigid_bodies(void) { return G->nRb; }
+void orc_get_rigid_bodies(double *out) {
+    for (unsigned i = 0; i < G->nRb; i++) {
+        const RigidBody *b = &G->rbs[i];
+        double *o = out + 13 * i;
+        for (int k = 0; k < 3; k++) { o[k] = b->x.v[k]; o[7 + k] = b->v.v[k]; o[10 + k] = b->omega.v[k]; }
+        o[3] = b->q.w; o[4] = b->q.x; o[5] = b->q.y; o[6] = b->q.z;
+    }
+}
+
+/* PositionBasedRigidBodyDynamics::computeMatrixK, PositionBasedRigidBodyDynamics.cpp:11-45 */
+static void compute_matrix_k(vec3 connector, real invMass, vec3 x, const mat3 *J, mat3 *K) {
+    if (invMass != R(0.0)) {
+        const vec3 v = vsub(connector, x);
+        const real a = v.v[0], b = v.v[1], c = v.v[2];
+        const real j11 = J->m[0][0], j12 = J->m[0][1], j13 = J->m[0][2], j22 = J->m[1][1], j23 = J->m[1][2], j33 = J->m[2][2];
+        K->m[0][0] = c * c * j22 - b * c * (j23 + j23) + b * b * j33 + invMass;
+        K->m[0][1] = -(c * c * j12) + a * c * j23 + b * c * j13 - a * b * j33;
+        K->m[0][2] = b * c * j12 - a * c * j22 - b * b * j13 + a * b * j23;
+        K->m[1][0] = K->m[0][1];
+        K->m[1][1] = c * c * j11 - a * c * (j13 + j13) + a * a * j33 + invMass;
+        K->m[1][2] = -(b * c * j11) + a * c * j12 + a * b * j13 - a * a * j23;
+        K->m[2][0] = K->m[0][2];
+        K->m[2][1] = K->m[1][2];
+        K->m[2][2] = b * b * j11 - a * b * (j12 + j12) + a * a * j22 + invMass;
+    } else memset(K, 0, sizeof(*K));
+}
+/* (K1 + K2).llt().solve(rhs): 3x3 Cholesky */
+static vec3 llt_solve(const mat3 *A, vec3 rhs) {
+    real l00 = RSQRT(A->m[0][0]);
+    real l10 = A->m[1][0] / l00, l20 = A->m[2][0] / l00;
+    real l11 = RSQRT(A->m[1][1] - l10 * l10);
+    real l21 = (A->m[2][1] - l20 * l10) / l11;
+    real l22 = RSQRT(A->m[2][2] - l20 * l20 - l21 * l21);
+    real y0 = rhs.v[0] / l00;
+    real y1 = (rhs.v[1] - l10 * y0) / l11;
+    real y2 = (rhs.v[2] - l20 * y0 - l21 * y1) / l22;
+    real z2 = y2 / l22;
+    real z1 = (y1 - l21 * z2) / l11;
+    real z0 = (y0 - l10 * z1 - l20 * z2) / l00;
+    return V(z0, z1, z2);
+}
+/* apply a positional + rotational correction to a rigid body (BallJoint::solvePositionConstraint, Constraints.cpp:106-121) */
+static void rb_apply(RigidBody *b, vec3 r, vec3 pt) { /* r = connector - x, pt = impulse-like vector (sign included) */
+    if (b->mass == R(0.0)) return;
+    const vec3 ot = mvec(&b->inertiaInvW, vcross(r, pt));
+    quat otQ = {R(0.0), ot.v[0], ot.v[1], ot.v[2]};
+    quat dq = qmul(otQ, b->q);
+    b->x = vadd(b->x, vmul(pt, b->invMass));
+    b->q.w += (real)(0.5 * dq.w); b->q.x += (real)(0.5 * dq.x); b->q.y += (real)(0.5 * dq.y); b->q.z += (real)(0.5 * dq.z);
+    b->q = qnormalize(b->q);
+    rb_rotation_updated(b);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* constraint factories: <X>Constraint::initConstraint + SimulationModel::add<X>Constraint            */
 /* (SimulationModel.cpp:565-806: push_back only when initConstraint returned true; groups invalidated)*/
 /* ------------------------------------------------------------------------------------------------ */
@@ -1140,6 +1266,23 @@ static int add_constraint(Model *m, int type, const unsigned *b, const real *u) 
         c->nb = 4; mat3 inv; memset(&inv, 0, sizeof(inv));
         ok = init_straintet(x0[b[0]], x0[b[1]], x0[b[2]], x0[b[3]], &inv);
         mat3_to_params(&inv, c->p); c->p[9] = u[0]; c->p[10] = u[1]; c->p[11] = u[2]; c->p[12] = u[3]; break; }
+    case ORC_BALLJOINT: { /* BallJoint::initConstraint, Constraints.cpp:54-70 + init_BallJoint, PositionBasedRigidBodyDynamics.cpp:160-186; u = joint position */
+        c->nb = 2;
+        if (b[0] >= m->nRb || b[1] >= m->nRb) { ok = 0; break; }
+        const RigidBody *r0 = &m->rbs[b[0]], *r1 = &m->rbs[b[1]];
+        vec3 pos = V(u[0], u[1], u[2]);
+        mat3 r0T = qmatrix(r0->q), r1T = qmatrix(r1->q); r0T = transpose3(&r0T); r1T = transpose3(&r1T);
+        vec3 l0 = mvec(&r0T, vsub(pos, r0->x)), l1 = mvec(&r1T, vsub(pos, r1->x));
+        for (int k = 0; k < 3; k++) { c->p[k] = l0.v[k]; c->p[3 + k] = l1.v[k]; c->p[6 + k] = pos.v[k]; c->p[9 + k] = pos.v[k]; }
+        break; }
+    case ORC_RB_PARTICLE_BALLJOINT: { /* RigidBodyParticleBallJoint::initConstraint, Constraints.cpp:925-938 + init (PositionBasedRigidBodyDynamics.cpp:2130-2147) */
+        c->nb = 2;
+        if (b[0] >= m->nRb || b[1] >= m->n) { ok = 0; break; }
+        const RigidBody *r0 = &m->rbs[b[0]];
+        mat3 r0T = qmatrix(r0->q); r0T = transpose3(&r0T);
+        vec3 l0 = mvec(&r0T, vsub(m->x[b[1]], r0->x));
+        for (int k = 0; k < 3; k++) { c->p[k] = l0.v[k]; c->p[3 + k] = m->x[b[1]].v[k]; }
+        break; }
     case ORC_SHAPEMATCHING: { /* Constraints.cpp:1985-2001: copies of x0 and invMass are frozen into the constraint; u = [k, nc0..nc3] */
         c->nb = 4; c->p[0] = u[0];
         vec3 q[4]; real w[4];
@@ -1254,7 +1397,8 @@ void orc_set_params(double dt, unsigned subSteps, unsigned maxIter, int velMetho
 void orc_init_groups(void) {
     Model *m = G;
     if (m->groupsInit) return;
-    const unsigned nc = m->nCons, nb = m->n;
+    /* rigid-body and particle indices share ONE index space without offset (SimulationModel.cpp:1041,1058,1070) */
+    const unsigned nc = m->nCons, nb = m->n + m->nRb;
     unsigned char **mapping = NULL; unsigned nGroups = 0, capGroups = 0;
     unsigned *colour = (unsigned *)malloc((size_t)(nc ? nc : 1) * sizeof(unsigned));
     unsigned *count = NULL;
@@ -1327,7 +1471,7 @@ void orc_tet_get_edges(unsigned tm, unsigned *out) { memcpy(out, G->tets[tm].edg
 void orc_tet_get_tets(unsigned tm, unsigned *out) { memcpy(out, G->tets[tm].tets, (size_t)4 * G->tets[tm].nTets * sizeof(unsigned)); }
 
 static int nparams_of(int type) {
-    static const int n[ORC_NUM_TYPES] = {2, 2, 2, 17, 17, 10, 9, 2, 2, 12, 12, 13, 24};
+    static const int n[ORC_NUM_TYPES] = {2, 2, 2, 17, 17, 10, 9, 2, 2, 12, 12, 13, 24, 12, 6};
     return (type >= 0 && type < ORC_NUM_TYPES) ? n[type] : 0;
 }
 int orc_get_constraint(unsigned i, unsigned *bodies, double *p, double *lambda) {
@@ -1394,6 +1538,33 @@ static void solve_position_constraint(Model *m, Constraint *c, unsigned iter, re
         vec3 ks = V(c->p[9], c->p[9], c->p[9]), kh = V(c->p[10], c->p[10], c->p[10]);
         res = solve_straintet(x[b[0]], w[b[0]], x[b[1]], w[b[1]], x[b[2]], w[b[2]], x[b[3]], w[b[3]], &inv, ks, kh, c->p[11] != 0, c->p[12] != 0, &corr[0], &corr[1], &corr[2], &corr[3]);
         break; }
+    case ORC_BALLJOINT: { /* BallJoint::updateConstraint + solvePositionConstraint (Constraints.cpp:72-125), solve_BallJoint (PositionBasedRigidBodyDynamics.cpp:212-262) */
+        RigidBody *r0 = &m->rbs[b[0]], *r1 = &m->rbs[b[1]];
+        mat3 R0 = qmatrix(r0->q), R1 = qmatrix(r1->q);
+        vec3 c0 = vadd(mvec(&R0, V(c->p[0], c->p[1], c->p[2])), r0->x), c1 = vadd(mvec(&R1, V(c->p[3], c->p[4], c->p[5])), r1->x);
+        for (int k = 0; k < 3; k++) { c->p[6 + k] = c0.v[k]; c->p[9 + k] = c1.v[k]; }
+        mat3 K1, K2, K;
+        compute_matrix_k(c0, r0->invMass, r0->x, &r0->inertiaInvW, &K1);
+        compute_matrix_k(c1, r1->invMass, r1->x, &r1->inertiaInvW, &K2);
+        for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) K.m[a][d] = K1.m[a][d] + K2.m[a][d];
+        vec3 pt = llt_solve(&K, vsub(c1, c0));
+        const vec3 ra = vsub(c0, r0->x), rb_ = vsub(c1, r1->x);  /* both lever arms from the state before either body moves */
+        if (r0->invMass != R(0.0)) rb_apply(r0, ra, pt);
+        if (r1->invMass != R(0.0)) rb_apply(r1, rb_, vneg(pt));
+        return; }
+    case ORC_RB_PARTICLE_BALLJOINT: { /* Constraints.cpp:940-987, solve_RigidBodyParticleBallJoint (PositionBasedRigidBodyDynamics.cpp:2168-2217) */
+        RigidBody *r0 = &m->rbs[b[0]];
+        const unsigned pi = b[1];
+        mat3 R0 = qmatrix(r0->q);
+        vec3 c0 = vadd(mvec(&R0, V(c->p[0], c->p[1], c->p[2])), r0->x);
+        for (int k = 0; k < 3; k++) c->p[3 + k] = c0.v[k];
+        mat3 K;
+        compute_matrix_k(c0, r0->invMass, r0->x, &r0->inertiaInvW, &K);
+        if (w[pi] != R(0.0)) { K.m[0][0] += w[pi]; K.m[1][1] += w[pi]; K.m[2][2] += w[pi]; }
+        vec3 pt = llt_solve(&K, vsub(x[pi], c0));
+        if (r0->invMass != R(0.0)) rb_apply(r0, vsub(c0, r0->x), pt);
+        if (m->mass[pi] != R(0.0) && w[pi] != R(0.0)) x[pi] = vadd(x[pi], vmul(pt, -w[pi]));
+        return; }
     case ORC_SHAPEMATCHING: { /* Constraints.cpp:2003-2028: uses the frozen m_x0 / m_w copies; 1/numClusters averaging */
         vec3 q0[4], xs[4]; real ws[4];
         for (int i = 0; i < 4; i++) { q0[i] = V(c->p[4 + 3 * i], c->p[5 + 3 * i], c->p[6 + 3 * i]); xs[i] = x[b[i]]; ws[i] = c->p[16 + i]; }
@@ -1427,8 +1598,25 @@ static void step_once(Model *m) {
     const int n = (int)m->n;
     /* TimeStep::clearAccelerations, TimeStep.cpp:28-62 */
     for (int i = 0; i < n; i++) if (m->mass[i] != R(0.0)) m->a[i] = m->gravity;
+    for (unsigned i = 0; i < m->nRb; i++) if (m->rbs[i].mass != R(0.0)) m->rbs[i].a = m->gravity;
     const real h = hOld / (real)m->subSteps;
     for (unsigned s = 0; s < m->subSteps; s++) {
+        for (unsigned i = 0; i < m->nRb; i++) { /* TimeStepController.cpp:97-107, TimeIntegration.cpp:7-19, 22-39 */
+            RigidBody *b = &m->rbs[i];
+            b->lastX = b->oldX; b->oldX = b->x;
+            if (b->mass != R(0.0)) { b->v = vadd(b->v, vmul(b->a, h)); b->x = vadd(b->x, vmul(b->v, h)); }
+            b->lastQ = b->oldQ; b->oldQ = b->q;
+            if (b->mass != R(0.0)) {
+                vec3 t = vsub(b->torque, vcross(b->omega, mvec(&b->inertiaW, b->omega)));
+                b->omega = vadd(b->omega, vmul(mvec(&b->inertiaInvW, t), h));
+                quat wq = {R(0.0), b->omega.v[0], b->omega.v[1], b->omega.v[2]};
+                quat dq = qmul(wq, b->q);
+                const double hh = (double)h * 0.5;
+                b->q.w += (real)(hh * dq.w); b->q.x += (real)(hh * dq.x); b->q.y += (real)(hh * dq.y); b->q.z += (real)(hh * dq.z);
+                b->q = qnormalize(b->q);
+            }
+            rb_rotation_updated(b);
+        }
 #pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) { /* :112-118 + TimeIntegration::semiImplicitEuler, TimeIntegration.cpp:7-19 */
             m->lastX[i] = m->oldX[i];
@@ -1439,6 +1627,18 @@ static void step_once(Model *m) {
             }
         }
         position_constraint_projection(m, h);
+        for (unsigned i = 0; i < m->nRb; i++) { /* TimeStepController.cpp:139-152, TimeIntegration.cpp:42-66, 69-95 (angular: first order in both modes) */
+            RigidBody *b = &m->rbs[i];
+            if (b->mass == R(0.0)) continue;
+            if (m->velMethod == 0) b->v = vmul(vsub(b->x, b->oldX), (real)(1.0 / h));
+            else {
+                vec3 t;
+                for (int k = 0; k < 3; k++) t.v[k] = (real)(1.5 * b->x.v[k]) - (real)(2.0 * b->oldX.v[k]) + (real)(0.5 * b->lastX.v[k]);
+                b->v = vmul(t, (real)(1.0 / h));
+            }
+            quat rel = qmul(b->q, qconj(b->oldQ));
+            b->omega = vmul(V(rel.x, rel.y, rel.z), (real)(2.0 / h));
+        }
 #pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) { /* :155-162 + TimeIntegration.cpp:42-51 / 69-79 */
             if (m->mass[i] == R(0.0)) continue;

@@ -37,7 +37,9 @@ enum {
     ORC_FEMTET_XPBD = 10,    /* same + lambda                                                 Constraints.cpp:1830-1906 */
     ORC_STRAINTET = 11,      /* bodies 4; params [invRestMat(3x3 rm), stretchK, shearK, normStretch, normShear] :1912-1980 */
     ORC_SHAPEMATCHING = 12,  /* bodies 4; params [stiffness, restCm(3), x0(4x3), w(4), numClusters(4)]  :1985-2028 */
-    ORC_NUM_TYPES = 13
+    ORC_BALLJOINT = 13,      /* bodies (rb, rb); params [local connector 0 (3), local connector 1 (3)]   Constraints.cpp:54-125 */
+    ORC_RB_PARTICLE_BALLJOINT = 14, /* bodies (rb, particle); params [local connector in the rigid body (3)]  Constraints.cpp:925-987 */
+    ORC_NUM_TYPES = 15
 };
 #define ORC_MAX_PARAMS 24
 
@@ -62,6 +64,10 @@ void orc_add_bending_constraints(unsigned triModel, unsigned method, double k);
 void orc_add_solid_constraints(unsigned tetModel, unsigned method, double k, double nu, double volK,
                                int normStretch, int normShear);
 int orc_add_constraint(int type, const unsigned *bodies, const double *p);
+/* rigid bodies (Simulation/RigidBody.h:84-110 initBody with explicit mass / principal inertia); q = (w, x, y, z) */
+unsigned orc_add_rigid_body(double mass, const double *x, const double *inertia, const double *q);
+unsigned orc_num_rigid_bodies(void);
+void orc_get_rigid_bodies(double *out); /* per body: x(3) q(w,x,y,z) v(3) omega(3) = 13 doubles */
 
 void orc_set_params(double dt, unsigned subSteps, unsigned maxIter, int velMethod, const double *g);
 void orc_init_groups(void);

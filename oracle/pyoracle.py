@@ -17,11 +17,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 # flat constraint type codes (include/pbd_b200.h, oracle/pbd_oracle.h)
 DISTANCE, DISTANCE_XPBD, DIHEDRAL, ISOBENDING, ISOBENDING_XPBD, FEMTRIANGLE, STRAINTRIANGLE, VOLUME, \
-    VOLUME_XPBD, FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING = range(13)
+    VOLUME_XPBD, FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING, BALLJOINT, RB_PARTICLE_BALLJOINT = range(15)
 TYPE_NAMES = ["Distance", "Distance_XPBD", "Dihedral", "IsometricBending", "IsometricBending_XPBD", "FEMTriangle",
-              "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching"]
-NPARAMS = [2, 2, 2, 17, 17, 10, 9, 2, 2, 12, 12, 13, 24]
-NBODIES = [2, 2, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4]
+              "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching", "BallJoint",
+              "RigidBodyParticleBallJoint"]
+NPARAMS = [2, 2, 2, 17, 17, 10, 9, 2, 2, 12, 12, 13, 24, 12, 6]
+NBODIES = [2, 2, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 2, 2]
 MAX_PARAMS = 24
 
 _D = C.c_double
@@ -110,6 +111,24 @@ class CpuPbd:
         b = np.zeros(4, dtype=np.uint32); b[:len(bodies)] = bodies
         p = np.zeros(8, dtype=np.float64); p[:len(params)] = params
         return self.f("add_constraint")(ctype, _up(b), _dp(p))
+
+    # -- rigid bodies and the joints coupling them to particles ---------------------------------
+    def add_rigid_body(self, mass, x, inertia, q=(1, 0, 0, 0)):
+        """q = (w, x, y, z); inertia = principal moments (RigidBody::initBody, RigidBody.h:84-120)."""
+        self.f("add_rigid_body").restype = C.c_uint
+        return self.f("add_rigid_body")(_D(mass), _dp(_f64(x)), _dp(_f64(inertia)), _dp(_f64(q)))
+
+    def add_ball_joint(self, rb0, rb1, pos):
+        return self.add_constraint(BALLJOINT, [rb0, rb1], list(pos))
+
+    def add_rb_particle_ball_joint(self, rb, particle):
+        return self.add_constraint(RB_PARTICLE_BALLJOINT, [rb, particle], [])
+
+    def rigid_bodies(self):
+        """[n, 13]: x(3) q(w,x,y,z) v(3) omega(3)."""
+        self.f("num_rigid_bodies").restype = C.c_uint
+        n = self.f("num_rigid_bodies")()
+        out = np.zeros((max(n, 1), 13)); self.f("get_rigid_bodies")(_dp(out)); return out[:n]
 
     def set_params(self, dt=0.005, sub_steps=5, max_iter=1, vel_method=0, gravity=(0, -9.81, 0)):
         self.f("set_params")(_D(dt), sub_steps, max_iter, vel_method, _dp(_f64(gravity)))

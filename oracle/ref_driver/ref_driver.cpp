@@ -14,6 +14,8 @@
 #include "Simulation/TimeManager.h"
 #include "Simulation/TimeStepController.h"
 #include "Simulation/Constraints.h"
+#include "Simulation/RigidBody.h"
+#include "Utils/IndexedFaceMesh.h"
 #include "PositionBasedDynamics/PositionBasedDynamics.h"
 #include "PositionBasedDynamics/XPBD.h"
 #include "PositionBasedDynamics/MathFunctions.h"
@@ -34,7 +36,7 @@ using namespace PBD;
 // shared flat-constraint type codes (same numbering as include/pbd_b200.h and oracle/pbd_oracle.h)
 enum { T_DISTANCE = 0, T_DISTANCE_XPBD, T_DIHEDRAL, T_ISOBENDING, T_ISOBENDING_XPBD, T_FEMTRIANGLE,
        T_STRAINTRIANGLE, T_VOLUME, T_VOLUME_XPBD, T_FEMTET, T_FEMTET_XPBD, T_STRAINTET, T_SHAPEMATCHING,
-       T_UNKNOWN = -1 };
+       T_BALLJOINT, T_RB_PARTICLE_BALLJOINT, T_UNKNOWN = -1 };
 
 static SimulationModel *g_model = nullptr;
 
@@ -97,6 +99,33 @@ void ref_add_tet_model(unsigned nPoints, unsigned nTets, const double *pts, cons
 }
 void ref_set_mass(unsigned i, double m) { g_model->getParticles().setMass(i, (Real)m); }
 
+// RigidBody::initBody(mass, x, inertiaTensor, rotation, vertices, mesh) (Simulation/RigidBody.h:84-120); q = (w,x,y,z).
+// The geometry is irrelevant on this path; a one-triangle mesh satisfies the signature.
+unsigned ref_add_rigid_body(double mass, const double *x, const double *inertia, const double *q) {
+    VertexData vd;
+    vd.addVertex(Vector3r(0, 0, 0)); vd.addVertex(Vector3r(1, 0, 0)); vd.addVertex(Vector3r(0, 1, 0));
+    Utilities::IndexedFaceMesh mesh;
+    mesh.initMesh(3, 3, 1);
+    const unsigned tri[3] = {0, 1, 2};
+    mesh.addFace(tri);
+    mesh.buildNeighbors();
+    RigidBody *rb = new RigidBody();
+    rb->initBody((Real)mass, v3(x), v3(inertia), Quaternionr((Real)q[0], (Real)q[1], (Real)q[2], (Real)q[3]), vd, mesh);
+    g_model->getRigidBodies().push_back(rb);
+    g_model->m_groupsInitialized = false;
+    return (unsigned)g_model->getRigidBodies().size() - 1;
+}
+unsigned ref_num_rigid_bodies() { return (unsigned)g_model->getRigidBodies().size(); }
+void ref_get_rigid_bodies(double *out) {
+    auto &rbs = g_model->getRigidBodies();
+    for (size_t i = 0; i < rbs.size(); i++) {
+        double *o = out + 13 * i;
+        const RigidBody &b = *rbs[i];
+        for (int k = 0; k < 3; k++) { o[k] = b.getPosition()[k]; o[7 + k] = b.getVelocity()[k]; o[10 + k] = b.getAngularVelocity()[k]; }
+        o[3] = b.getRotation().w(); o[4] = b.getRotation().x(); o[5] = b.getRotation().y(); o[6] = b.getRotation().z();
+    }
+}
+
 void ref_add_cloth_constraints(unsigned triModel, unsigned method, double distK, double xx, double yy, double xy,
                                double pxy, double pyx, int normStretch, int normShear) {
     g_model->addClothConstraints(g_model->getTriangleModels()[triModel], method, (Real)distK, (Real)xx, (Real)yy,
@@ -126,6 +155,8 @@ int ref_add_constraint(int type, const unsigned *b, const double *p) {
     case T_FEMTET: return m.addFEMTetConstraint(b[0], b[1], b[2], b[3], (Real)p[0], (Real)p[1]);
     case T_FEMTET_XPBD: return m.addFEMTetConstraint_XPBD(b[0], b[1], b[2], b[3], (Real)p[0], (Real)p[1]);
     case T_STRAINTET: return m.addStrainTetConstraint(b[0], b[1], b[2], b[3], (Real)p[0], (Real)p[1], p[2] != 0, p[3] != 0);
+    case T_BALLJOINT: return m.addBallJoint(b[0], b[1], v3(p));
+    case T_RB_PARTICLE_BALLJOINT: return m.addRigidBodyParticleBallJoint(b[0], b[1]);
     case T_SHAPEMATCHING: { const unsigned nc[4] = {(unsigned)p[1], (unsigned)p[2], (unsigned)p[3], (unsigned)p[4]}; return m.addShapeMatchingConstraint(4, b, nc, (Real)p[0]); }
     default: return -1;
     }
@@ -219,6 +250,8 @@ static int typeCode(Constraint *c) {
     if (id == XPBD_FEMTetConstraint::TYPE_ID) return T_FEMTET_XPBD;
     if (id == StrainTetConstraint::TYPE_ID) return T_STRAINTET;
     if (id == ShapeMatchingConstraint::TYPE_ID) return T_SHAPEMATCHING;
+    if (id == BallJoint::TYPE_ID) return T_BALLJOINT;
+    if (id == RigidBodyParticleBallJoint::TYPE_ID) return T_RB_PARTICLE_BALLJOINT;
     return T_UNKNOWN;
 }
 
@@ -246,6 +279,8 @@ int ref_get_constraint(unsigned i, unsigned *bodies, double *p, double *lambda) 
     case T_FEMTET_XPBD: { auto *d = static_cast<XPBD_FEMTetConstraint *>(c); p[n++] = d->m_volume; putM(d->m_invRestMat, 3, 3); p[n++] = d->m_stiffness; p[n++] = d->m_poissonRatio; *lambda = d->m_lambda; break; }
     case T_STRAINTET: { auto *d = static_cast<StrainTetConstraint *>(c); putM(d->m_invRestMat, 3, 3);
         p[n++] = d->m_stretchStiffness; p[n++] = d->m_shearStiffness; p[n++] = d->m_normalizeStretch; p[n++] = d->m_normalizeShear; break; }
+    case T_BALLJOINT: { auto *d = static_cast<BallJoint *>(c); for (int col = 0; col < 4; col++) for (int k = 0; k < 3; k++) p[n++] = d->m_jointInfo(k, col); break; }
+    case T_RB_PARTICLE_BALLJOINT: { auto *d = static_cast<RigidBodyParticleBallJoint *>(c); for (int col = 0; col < 2; col++) for (int k = 0; k < 3; k++) p[n++] = d->m_jointInfo(k, col); break; }
     case T_SHAPEMATCHING: { auto *d = static_cast<ShapeMatchingConstraint *>(c); p[n++] = d->m_stiffness;
         for (int k = 0; k < 3; k++) p[n++] = d->m_restCm[k];
         for (int q = 0; q < 4; q++) for (int k = 0; k < 3; k++) p[n++] = d->m_x0[q][k];

@@ -11,16 +11,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbd_b200.so")
 
 (DISTANCE, DISTANCE_XPBD, DIHEDRAL, ISOBENDING, ISOBENDING_XPBD, FEMTRIANGLE, STRAINTRIANGLE, VOLUME, VOLUME_XPBD,
- FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING) = range(13)
-NUM_TYPES = 13
+ FEMTET, FEMTET_XPBD, STRAINTET, SHAPEMATCHING, BALLJOINT, RB_PARTICLE_BALLJOINT) = range(15)
+NUM_TYPES = 15
 TYPE_NAMES = ["Distance", "Distance_XPBD", "Dihedral", "IsometricBending", "IsometricBending_XPBD", "FEMTriangle",
-              "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching"]
+              "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching", "BallJoint",
+              "RigidBodyParticleBallJoint"]
 ATTR_X, ATTR_V, ATTR_X0, ATTR_OLDX, ATTR_LASTX = range(5)
 MODE_GRAPH, MODE_PERSISTENT, MODE_LAUNCH = 0, 1, 2
 
 # every symbol include/pbd_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "pbd_set_particles", "pbd_set_attr",
-           "pbd_get_attr", "pbd_set_masses", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
+           "pbd_get_attr", "pbd_set_masses", "pbd_set_rigid_bodies", "pbd_get_rigid_bodies", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
            "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_get_num_groups", "pbd_get_groups",
            "pbd_set_params", "pbd_set_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host",
            "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step"]
@@ -60,6 +61,8 @@ def lib():
         _lib.pbd_set_attr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.pbd_get_attr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.pbd_set_masses.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.pbd_set_rigid_bodies.argtypes = [C.c_void_p, C.c_uint] + [C.c_void_p] * 6
+        _lib.pbd_get_rigid_bodies.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         _lib.pbd_add_constraints.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.pbd_set_groups.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
         _lib.pbd_get_num_groups.argtypes = [C.c_void_p, C.POINTER(C.c_uint)]
@@ -142,6 +145,23 @@ class Engine:
     def set_masses(self, mass):
         mass = _f32(mass).reshape(-1); assert len(mass) == self.n
         _ck(lib().pbd_set_masses(self._h, _ptr(mass)))
+
+    # rigid bodies ----------------------------------------------------------------------------------
+    def set_rigid_bodies(self, mass, x, q, inertia, v=None, omega=None):
+        """q rows = (w, x, y, z); inertia rows = principal moments."""
+        mass = _f32(mass).reshape(-1); self.n_rb = len(mass)
+        x = _f32(x).reshape(-1, 3); q = _f32(q).reshape(-1, 4); inertia = _f32(inertia).reshape(-1, 3)
+        v = _f32(v).reshape(-1, 3) if v is not None else None
+        omega = _f32(omega).reshape(-1, 3) if omega is not None else None
+        _ck(lib().pbd_set_rigid_bodies(self._h, self.n_rb, _ptr(mass), _ptr(x), _ptr(q), _ptr(inertia), _ptr(v), _ptr(omega)))
+
+    def get_rigid_bodies(self):
+        """[n, 13]: x(3) q(w,x,y,z) v(3) omega(3)."""
+        n = getattr(self, "n_rb", 0)
+        x = np.zeros((max(n, 1), 3), np.float32); q = np.zeros((max(n, 1), 4), np.float32)
+        v = np.zeros((max(n, 1), 3), np.float32); w = np.zeros((max(n, 1), 3), np.float32)
+        _ck(lib().pbd_get_rigid_bodies(self._h, _ptr(x), _ptr(q), _ptr(v), _ptr(w)))
+        return np.concatenate([x, q, v, w], axis=1)[:n]
 
     # constraints -----------------------------------------------------------------------------------
     def clear_constraints(self):

@@ -38,6 +38,8 @@ struct TypeArrays {
     const float *mat[kMaxMat]; // per-constraint material arrays, or nullptr -> matU (uniform over the type)
     float matU[kMaxMat];
     float *lambda;             // XPBD multipliers (m_lambda), zeroed at the first sweep of each substep
+    float4 *rbX, *rbQ;         // joint types only: rigid-body positions (xyz, invMass) and rotations (x,y,z,w)
+    const float4 *rbIinv;      // joint types only: inverse principal moments
     int variant;               // PBD_ISOBENDING*: 0 = rank-1 Kp form, 1 = full 4x4 Q
 };
 
@@ -66,6 +68,8 @@ inline TypeShape type_shape(int t) {
     case PBD_FEMTET_XPBD:     return {4, 12, 2, 2, 2, true};
     case PBD_STRAINTET:       return {4, 13, 2, 1, 4, false};
     case PBD_SHAPEMATCHING:   return {4, 24, 6, 0, 1, false};
+    case PBD_BALLJOINT:       return {2, 12, 2, 0, 0, false};
+    case PBD_RB_PARTICLE_BALLJOINT: return {2, 6, 1, 0, 0, false};
     default:                  return {0, 0, 0, 0, 0, false};
     }
 }
@@ -86,7 +90,9 @@ inline double algorithmic_bytes(int t, int isoVariant) {
     case PBD_FEMTET:          return 16 + 64 + 40 + 64;
     case PBD_FEMTET_XPBD:     return 16 + 64 + 40 + 64 + 8;
     case PBD_STRAINTET:       return 16 + 64 + 36 + 64;
-    case PBD_SHAPEMATCHING:   return 16 + 64 + 96 + 64;  // restCm + frozen x0[4] + w[4] + numClusters[4]
+    case PBD_SHAPEMATCHING:   return 16 + 64 + 96 + 64;
+    case PBD_BALLJOINT:       return 8 + 2 * 48 + 32 + 2 * 32;   // two rigid bodies (x, q, Iinv) read, (x, q) written
+    case PBD_RB_PARTICLE_BALLJOINT: return 8 + 48 + 16 + 16 + 32 + 16;  // restCm + frozen x0[4] + w[4] + numClusters[4]
     default:                  return 0;
     }
 }

@@ -74,6 +74,9 @@ struct pbd_engine {
     // particles
     unsigned n = 0;
     DevBuf pos, vel, oldp, lastp, pos0, stage, massStage;
+    // rigid bodies coupled through joints: float4 arrays X(xyz,invMass) Q(x,y,z,w) V(xyz,mass) W(omega) + history + inertia
+    unsigned nRb = 0;
+    DevBuf rbX, rbQ, rbV, rbW, rbOldX, rbLastX, rbOldQ, rbLastQ, rbI, rbIinv;
     float *pinned = nullptr; size_t pinnedBytes = 0;
     // constraints (host copy, insertion order) and groups
     HostType host[PBD_NUM_TYPES];
@@ -156,7 +159,8 @@ extern "C" int pbd_destroy(pbd_engine *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
-    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->massStage, &e->dBuckets, &e->dTypeArrays, &e->dBarrier}) b->release();
+    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->massStage, &e->dBuckets, &e->dTypeArrays, &e->dBarrier, &e->dTrace,
+                    &e->rbX, &e->rbQ, &e->rbV, &e->rbW, &e->rbOldX, &e->rbLastX, &e->rbOldQ, &e->rbLastQ, &e->rbI, &e->rbIinv}) b->release();
     for (auto &d : e->dev) {
         for (auto &b : d.idx) b.release();
         for (auto &b : d.gv) b.release();
@@ -259,6 +263,51 @@ extern "C" int pbd_get_attr(pbd_engine *e, int attr, float *dst) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// rigid bodies (host arrays are tiny: plain synchronous copies)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int pbd_set_rigid_bodies(pbd_engine *e, unsigned n, const float *mass, const float *x, const float *q, const float *inertia,
+                                    const float *v, const float *omega) {
+    if (!e || (n && (!mass || !x || !q || !inertia))) return fail("pbd_set_rigid_bodies: null argument");
+    CKE(use(e));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n != e->nRb) { e->imageDirty = true; e->groupsSet = e->groupsSet && n == e->nRb; }
+    drop_graph(e);
+    e->nRb = n;
+    if (n == 0) return 0;
+    std::vector<float4> X(n), Q(n), V(n), W(n), I(n), Ii(n);
+    for (unsigned i = 0; i < n; i++) {
+        const float m = mass[i];
+        X[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], (m != 0.0f) ? 1.0f / m : 0.0f);
+        Q[i] = make_float4(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], q[4 * i]);  // (w,x,y,z) -> (x,y,z,w)
+        V[i] = v ? make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], m) : make_float4(0.f, 0.f, 0.f, m);
+        W[i] = omega ? make_float4(omega[3 * i], omega[3 * i + 1], omega[3 * i + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        I[i] = make_float4(inertia[3 * i], inertia[3 * i + 1], inertia[3 * i + 2], 0.f);
+        Ii[i] = make_float4(1.0f / inertia[3 * i], 1.0f / inertia[3 * i + 1], 1.0f / inertia[3 * i + 2], 0.f);  // RigidBody::setInertiaTensor (RigidBody.h:416-420)
+    }
+    const size_t b = (size_t)n * sizeof(float4);
+    struct { DevBuf *d; const std::vector<float4> *h; } up[] = {{&e->rbX, &X}, {&e->rbQ, &Q}, {&e->rbV, &V}, {&e->rbW, &W}, {&e->rbOldX, &X}, {&e->rbLastX, &X},
+                                                              {&e->rbOldQ, &Q}, {&e->rbLastQ, &Q}, {&e->rbI, &I}, {&e->rbIinv, &Ii}};
+    for (auto &u : up) { CKE(u.d->alloc(b)); CK(cudaMemcpy(u.d->p, u.h->data(), b, cudaMemcpyHostToDevice)); }
+    e->imageDirty = true;  // joint type arrays hold the rigid-body pointers
+    return 0;
+}
+
+extern "C" int pbd_get_rigid_bodies(pbd_engine *e, float *x, float *q, float *v, float *omega) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    CK(cudaStreamSynchronize(e->stream));
+    const unsigned n = e->nRb;
+    if (n == 0) return 0;
+    std::vector<float4> t(n);
+    const size_t b = (size_t)n * sizeof(float4);
+    if (x) { CK(cudaMemcpy(t.data(), e->rbX.p, b, cudaMemcpyDeviceToHost)); for (unsigned i = 0; i < n; i++) { x[3 * i] = t[i].x; x[3 * i + 1] = t[i].y; x[3 * i + 2] = t[i].z; } }
+    if (q) { CK(cudaMemcpy(t.data(), e->rbQ.p, b, cudaMemcpyDeviceToHost)); for (unsigned i = 0; i < n; i++) { q[4 * i] = t[i].w; q[4 * i + 1] = t[i].x; q[4 * i + 2] = t[i].y; q[4 * i + 3] = t[i].z; } }
+    if (v) { CK(cudaMemcpy(t.data(), e->rbV.p, b, cudaMemcpyDeviceToHost)); for (unsigned i = 0; i < n; i++) { v[3 * i] = t[i].x; v[3 * i + 1] = t[i].y; v[3 * i + 2] = t[i].z; } }
+    if (omega) { CK(cudaMemcpy(t.data(), e->rbW.p, b, cudaMemcpyDeviceToHost)); for (unsigned i = 0; i < n; i++) { omega[3 * i] = t[i].x; omega[3 * i + 1] = t[i].y; omega[3 * i + 2] = t[i].z; } }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // constraints and groups
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int pbd_clear_constraints(pbd_engine *e) {
@@ -275,8 +324,11 @@ extern "C" int pbd_add_constraints(pbd_engine *e, int type, unsigned count, cons
     if (type < 0 || type >= PBD_NUM_TYPES) return fail("pbd_add_constraints: unknown constraint type %d", type);
     if (count && (!bodies || !params)) return fail("pbd_add_constraints: null arrays");
     const TypeShape s = type_shape(type);
-    for (size_t i = 0; i < (size_t)count * s.nBodies; i++)
-        if (bodies[i] >= e->n) return fail("pbd_add_constraints: particle index %u out of range (n=%u)", bodies[i], e->n);
+    for (size_t i = 0; i < (size_t)count * s.nBodies; i++) {
+        const bool isRb = (type == PBD_BALLJOINT) || (type == PBD_RB_PARTICLE_BALLJOINT && (i % 2) == 0);
+        if (isRb) { if (bodies[i] >= e->nRb) return fail("pbd_add_constraints: rigid-body index %u out of range (%u bodies; call pbd_set_rigid_bodies first)", bodies[i], e->nRb); }
+        else if (bodies[i] >= e->n) return fail("pbd_add_constraints: particle index %u out of range (n=%u)", bodies[i], e->n);
+    }
     HostType &h = e->host[type];
     for (unsigned i = 0; i < count; i++) h.ids.push_back(ids ? ids[i] : e->numConstraints + i);
     h.bodies.insert(h.bodies.end(), bodies, bodies + (size_t)count * s.nBodies);
@@ -338,7 +390,8 @@ extern "C" int pbd_color_first_fit(pbd_engine *e) {
         off[id + 1] = (unsigned)bodies.size();
     }
     std::vector<unsigned> colour;
-    const unsigned nColours = pbd_b200::firstFitColouring(e->n, N, off.data(), bodies.data(), colour);
+    // rigid-body and particle indices share one index space without offset (SimulationModel.cpp:1041,1058,1070)
+    const unsigned nColours = pbd_b200::firstFitColouring(e->n + e->nRb, N, off.data(), bodies.data(), colour);
     std::vector<unsigned> goff(nColours + 1, 0);
     for (unsigned id = 0; id < N; id++) goff[colour[id] + 1]++;
     for (unsigned c = 0; c < nColours; c++) goff[c + 1] += goff[c];
@@ -441,7 +494,7 @@ static int flatten(pbd_engine *e) {
         }
         for (int t = 0; t < PBD_NUM_TYPES; t++) {
             if (tmp[t].empty()) continue;
-            if (e->sortBuckets) {  // order inside a colour is free: sort by lowest particle index for gather locality
+            if (e->sortBuckets && t != PBD_BALLJOINT && t != PBD_RB_PARTICLE_BALLJOINT) {  // order inside a colour is free: sort by lowest particle index for gather locality
                 const int nb = type_shape(t).nBodies;
                 const unsigned *bod = e->host[t].bodies.data();
                 std::vector<std::pair<unsigned, unsigned>> keyed(tmp[t].size());
@@ -462,7 +515,9 @@ static int flatten(pbd_engine *e) {
 
     // debug-grade safety: inside a colour no particle may be used twice (race freedom by construction)
     {
-        std::vector<unsigned> stamp(e->n, 0xffffffffu);
+        // particles and rigid bodies are stamped in separate index spaces (the reference's colouring shares one, which only
+        // ever over-separates; a body really used twice in a colour would be a race here)
+        std::vector<unsigned> stamp((size_t)e->n + e->nRb, 0xffffffffu);
         size_t bi = 0;
         for (unsigned g = 0; g < nGroups; g++) {
             for (; bi < e->buckets.size() && e->buckets[bi].colour == g; bi++) {
@@ -471,8 +526,10 @@ static int flatten(pbd_engine *e) {
                 for (unsigned i = 0; i < b.count; i++) {
                     const unsigned *bd = &e->host[b.type].bodies[(size_t)order[b.type][b.first + i] * nb];
                     for (int k = 0; k < nb; k++) {
-                        if (stamp[bd[k]] == g) return fail("colour group %u uses particle %u twice: the groups are not a valid colouring", g, bd[k]);
-                        stamp[bd[k]] = g;
+                        const bool isRb = (b.type == PBD_BALLJOINT) || (b.type == PBD_RB_PARTICLE_BALLJOINT && k == 0);
+                        const size_t slot = isRb ? (size_t)e->n + bd[k] : bd[k];
+                        if (stamp[slot] == g) return fail("colour group %u uses %s %u twice: the groups are not a valid colouring", g, isRb ? "rigid body" : "particle", bd[k]);
+                        stamp[slot] = g;
                     }
                 }
             }
@@ -493,7 +550,11 @@ static int flatten(pbd_engine *e) {
         if (cnt == 0) continue;
         for (unsigned i = 0; i < cnt; i++) d.order[i] = h.ids[order[t][i]];
         auto P = [&](unsigned i, int k) { return h.params[(size_t)order[t][i] * s.nParams + k]; };
-        auto B = [&](unsigned i, int k) { return particle_slot(h.bodies[(size_t)order[t][i] * s.nBodies + k], e->n, e->layout); };
+        auto B = [&](unsigned i, int k) {
+            const unsigned raw = h.bodies[(size_t)order[t][i] * s.nBodies + k];
+            const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && k == 0);
+            return isRb ? raw : particle_slot(raw, e->n, e->layout);
+        };
 
         // indices
         if (s.nBodies == 2) {
@@ -568,6 +629,11 @@ static int flatten(pbd_engine *e) {
             }
             for (int k = 0; k < 4; k++) matSlot[k] = 9 + k;
             break;
+        case PBD_BALLJOINT: case PBD_RB_PARTICLE_BALLJOINT:  // local connectors (jointInfo columns 0 [and 1]); global columns are recomputed per solve
+            gv[0].resize(cnt);
+            for (unsigned i = 0; i < cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), 0.0f);
+            if (t == PBD_BALLJOINT) { gv[1].resize(cnt); for (unsigned i = 0; i < cnt; i++) gv[1][i] = make_float4(P(i, 3), P(i, 4), P(i, 5), 0.0f); }
+            break;
         case PBD_SHAPEMATCHING:  // restCm | x0[0..3] packed in 3 float4 | w | numClusters ; stiffness is the material slot
             for (int k = 0; k < 6; k++) gv[k].resize(cnt);
             for (unsigned i = 0; i < cnt; i++) {
@@ -584,6 +650,9 @@ static int flatten(pbd_engine *e) {
         default: return fail("flatten: constraint type %d has no kernel", t);
         }
         d.arrays.variant = variant;
+        if (t == PBD_BALLJOINT || t == PBD_RB_PARTICLE_BALLJOINT) {
+            d.arrays.rbX = (float4 *)e->rbX.p; d.arrays.rbQ = (float4 *)e->rbQ.p; d.arrays.rbIinv = (const float4 *)e->rbIinv.p;
+        }
         for (int k = 0; k < kMaxGeoV; k++) if (!gv[k].empty()) { CKE(upload_vec(d.gv[k], gv[k], e->stream)); d.arrays.gv[k] = (const float4 *)d.gv[k].p; }
         for (int k = 0; k < kMaxGeoS; k++) if (!gs[k].empty()) { CKE(upload_vec(d.gs[k], gs[k], e->stream)); d.arrays.gs[k] = (const float *)d.gs[k].p; }
         // material parameters: one uniform per type when every constraint agrees, else a per-constraint array
@@ -646,7 +715,7 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
     switch (b.type) {
         LB(PBD_DISTANCE) LB(PBD_DISTANCE_XPBD) LB(PBD_DIHEDRAL) LB(PBD_ISOBENDING) LB(PBD_ISOBENDING_XPBD)
         LB(PBD_FEMTRIANGLE) LB(PBD_STRAINTRIANGLE) LB(PBD_VOLUME) LB(PBD_VOLUME_XPBD) LB(PBD_FEMTET)
-        LB(PBD_FEMTET_XPBD) LB(PBD_STRAINTET) LB(PBD_SHAPEMATCHING)
+        LB(PBD_FEMTET_XPBD) LB(PBD_STRAINTET) LB(PBD_SHAPEMATCHING) LB(PBD_BALLJOINT) LB(PBD_RB_PARTICLE_BALLJOINT)
     default: return fail("no kernel for constraint type %d", b.type);
     }
 #undef LB
@@ -707,7 +776,10 @@ static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long lo
     const float invH = (float)(1.0 / (double)h);
     const unsigned n = e->n;
     unsigned long long L = 0;
+    RbState rb{(float4 *)e->rbX.p, (float4 *)e->rbQ.p, (float4 *)e->rbV.p, (float4 *)e->rbW.p, (float4 *)e->rbOldX.p, (float4 *)e->rbLastX.p,
+               (float4 *)e->rbOldQ.p, (float4 *)e->rbLastQ.p, (const float4 *)e->rbI.p, (const float4 *)e->rbIinv.p, e->nRb};
     for (unsigned sub = 0; sub < e->subSteps; sub++) {
+        if (e->nRb) { CK(launch_particles(e, s, k_rb_integrate, e->nRb, rb, h, e->g[0], e->g[1], e->g[2])); L++; }
         if (n) {
             CK(launch_particles(e, s, k_integrate, n, (float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e)));
             L++;
@@ -723,6 +795,7 @@ static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long lo
             CK(launch_particles(e, s, k_velocity, n, (const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod));
             L++;
         }
+        if (e->nRb) { CK(launch_particles(e, s, k_rb_velocity, e->nRb, rb, invH, (float)(2.0 / (double)h), e->velMethod)); L++; }
     }
     *launches = L;
     return 0;
@@ -747,6 +820,8 @@ static int launch_persistent(pbd_engine *e, cudaStream_t s, PersistentArgs &pa) 
 }
 
 static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
+    if (e->nRb || e->dev[PBD_BALLJOINT].count || e->dev[PBD_RB_PARTICLE_BALLJOINT].count)
+        return fail("PBD_MODE_PERSISTENT does not cover rigid-body coupling (BallJoint / RigidBodyParticleBallJoint); use PBD_MODE_GRAPH");
     const float h = e->dt / (float)e->subSteps;
     const float invH = (float)(1.0 / (double)h);
     PersistentArgs pa;
@@ -909,7 +984,9 @@ extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegr
     CK(cudaStreamSynchronize(e->stream));
     // One event between every pair of consecutive launches, all recorded in stream order without host synchronisation
     // (a host sync per launch would time the idle-launch latency, not the kernel); read back after one final sync.
-    const size_t nLaunch = (size_t)e->subSteps * (2 + (size_t)e->maxIter * e->buckets.size());
+    const size_t nLaunch = (size_t)e->subSteps * (4 + (size_t)e->maxIter * e->buckets.size());
+    RbState rb{(float4 *)e->rbX.p, (float4 *)e->rbQ.p, (float4 *)e->rbV.p, (float4 *)e->rbW.p, (float4 *)e->rbOldX.p, (float4 *)e->rbLastX.p,
+               (float4 *)e->rbOldQ.p, (float4 *)e->rbLastQ.p, (const float4 *)e->rbI.p, (const float4 *)e->rbIinv.p, e->nRb};
     std::vector<cudaEvent_t> ev(nLaunch + 1);
     for (auto &x : ev) CK(cudaEventCreate(&x));
     std::vector<int> what(nLaunch);  // >= 0: type, -1 integrate, -2 velocity
@@ -922,6 +999,7 @@ extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegr
     int rc = 0;
     CK(cudaEventRecord(ev[0], e->stream));
     for (unsigned sub = 0; sub < e->subSteps && !rc; sub++) {
+        if (e->nRb) { k_rb_integrate<<<nblk(e->nRb, 32), 32, 0, e->stream>>>(rb, h, e->g[0], e->g[1], e->g[2]); what[k] = -1; cudaEventRecord(ev[++k], e->stream); }
         if (n) {
             k_integrate<<<nblk(n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], track_last(e));
             what[k] = -1; cudaEventRecord(ev[++k], e->stream);
@@ -936,6 +1014,7 @@ extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegr
             k_velocity<<<nblk(n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod);
             what[k] = -2; cudaEventRecord(ev[++k], e->stream);
         }
+        if (e->nRb && !rc) { k_rb_velocity<<<nblk(e->nRb, 32), 32, 0, e->stream>>>(rb, invH, (float)(2.0 / (double)h), e->velMethod); what[k] = -2; cudaEventRecord(ev[++k], e->stream); }
     }
     e->usePDL = pdl;
     cudaError_t se = cudaStreamSynchronize(e->stream);

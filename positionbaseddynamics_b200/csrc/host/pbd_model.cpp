@@ -144,6 +144,8 @@ SimulationModel::SimulationModel() {}
 SimulationModel::~SimulationModel() { cleanup(); }
 
 void SimulationModel::cleanup() {
+    for (auto *b : m_rigidBodies) delete b;
+    m_rigidBodies.clear(); rigidBodiesDirty = true;
     for (auto *t : m_triangleModels) delete t;
     for (auto *t : m_tetModels) delete t;
     m_triangleModels.clear(); m_tetModels.clear();
@@ -154,6 +156,8 @@ void SimulationModel::cleanup() {
 }
 
 void SimulationModel::reset() {
+    for (auto *b : m_rigidBodies) { b->m_x = b->m_x0; b->m_q = b->m_q0; b->m_v = Vector3r(); b->m_omega = Vector3r(); }
+    rigidBodiesDirty = true;
     ParticleData &pd = m_particles;
     for (unsigned int i = 0; i < pd.size(); i++) {
         pd.m_x[i] = pd.m_x0[i]; pd.m_oldX[i] = pd.m_x0[i]; pd.m_lastX[i] = pd.m_x0[i];
@@ -248,6 +252,45 @@ void SimulationModel::addRegularTetModel(int width, int height, int depth, const
     for (unsigned int i = offset; i < offset + (unsigned int)points.size(); i++) m_particles.setMass(i, 1.0f);
 }
 
+void RigidBody::initBody(Real mass, const Vector3r &x, const Vector3r &inertiaTensor, const Quaternionr &rotation) {
+    m_mass = mass; m_invMass = (mass != 0.0f) ? 1.0f / mass : 0.0f;  // RigidBody::setMass (RigidBody.h:277-284)
+    m_x = m_x0 = x; m_v = Vector3r(); m_omega = Vector3r();
+    m_inertiaTensor = inertiaTensor; m_q = m_q0 = rotation;
+}
+
+// world -> body space of a point, R(q)^T (p - x), evaluated in double
+static void toLocal(const RigidBody &b, const double p[3], Real out[3]) {
+    const double w = b.m_q.w, x = b.m_q.x, y = b.m_q.y, z = b.m_q.z;
+    const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)},
+                            {2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)},
+                            {2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)}};
+    const double d[3] = {p[0] - b.m_x[0], p[1] - b.m_x[1], p[2] - b.m_x[2]};
+    for (int c = 0; c < 3; c++) out[c] = (Real)(R[0][c] * d[0] + R[1][c] * d[1] + R[2][c] * d[2]);
+}
+
+// BallJoint::initConstraint + init_BallJoint (Constraints.cpp:54-70, PositionBasedRigidBodyDynamics.cpp:160-186):
+// jointInfo = [connector in body 0 | connector in body 1 | global | global]
+bool SimulationModel::addBallJoint(unsigned int rbIndex1, unsigned int rbIndex2, const Vector3r &pos) {
+    if (rbIndex1 >= m_rigidBodies.size() || rbIndex2 >= m_rigidBodies.size()) return false;
+    const double p[3] = {pos[0], pos[1], pos[2]};
+    Real info[12];
+    toLocal(*m_rigidBodies[rbIndex1], p, info); toLocal(*m_rigidBodies[rbIndex2], p, info + 3);
+    for (int k = 0; k < 3; k++) info[6 + k] = info[9 + k] = pos[k];
+    const unsigned int b[2] = {rbIndex1, rbIndex2};
+    return pushConstraint(PBD_BALLJOINT, b, info, true);
+}
+// RigidBodyParticleBallJoint::initConstraint (Constraints.cpp:925-938): connector = the particle's CURRENT position
+bool SimulationModel::addRigidBodyParticleBallJoint(unsigned int rbIndex, unsigned int particleIndex) {
+    if (rbIndex >= m_rigidBodies.size() || particleIndex >= m_particles.size()) return false;
+    const Vector3r &x = static_cast<const ParticleData &>(m_particles).getPosition(particleIndex);
+    const double p[3] = {x[0], x[1], x[2]};
+    Real info[6];
+    toLocal(*m_rigidBodies[rbIndex], p, info);
+    for (int k = 0; k < 3; k++) info[3 + k] = x[k];
+    const unsigned int b[2] = {rbIndex, particleIndex};
+    return pushConstraint(PBD_RB_PARTICLE_BALLJOINT, b, info, true);
+}
+
 void SimulationModel::initConstraintGroups() {
     if (m_groupsInitialized) return;
     const unsigned int N = numConstraints();
@@ -259,7 +302,8 @@ void SimulationModel::initConstraintGroups() {
         off[c + 1] = (unsigned int)bodies.size();
     }
     std::vector<unsigned int> colour;
-    const unsigned int nColours = firstFitColouring(m_particles.size(), N, off.data(), bodies.data(), colour);
+    // rigid-body and particle indices share one index space without offset (SimulationModel.cpp:1041,1058,1070)
+    const unsigned int nColours = firstFitColouring(m_particles.size() + (unsigned int)m_rigidBodies.size(), N, off.data(), bodies.data(), colour);
     m_constraintGroups.assign(nColours, std::vector<unsigned int>());
     for (unsigned int c = 0; c < N; c++) m_constraintGroups[colour[c]].push_back(c);
     m_groupsInitialized = true;
@@ -607,6 +651,20 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
             if ((pd.dirtyMask >> a) & 1u) { if (pbd_set_attr(m_engine, a, &(*src[a])[0][0])) return fail("pbd_set_attr"); }
         pd.dirtyMask = 0;
     }
+    SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
+    if (rebind || model.rigidBodiesDirty || rbs.size() != m_boundRigidBodies) {
+        const unsigned int nr = (unsigned int)rbs.size();
+        std::vector<float> mass(nr), x(3 * nr), q(4 * nr), I(3 * nr), v(3 * nr), w(3 * nr);
+        for (unsigned int i = 0; i < nr; i++) {
+            const RigidBody &b = *rbs[i];
+            mass[i] = b.m_mass;
+            for (int k = 0; k < 3; k++) { x[3 * i + k] = b.m_x[k]; I[3 * i + k] = b.m_inertiaTensor[k]; v[3 * i + k] = b.m_v[k]; w[3 * i + k] = b.m_omega[k]; }
+            q[4 * i] = b.m_q.w; q[4 * i + 1] = b.m_q.x; q[4 * i + 2] = b.m_q.y; q[4 * i + 3] = b.m_q.z;
+        }
+        if (pbd_set_rigid_bodies(m_engine, nr, mass.data(), x.data(), q.data(), I.data(), v.data(), w.data())) return fail("pbd_set_rigid_bodies");
+        if (nr != m_boundRigidBodies) m_boundGeneration = 0;  // joints reference the body arrays: re-send the constraints
+        m_boundRigidBodies = nr; model.rigidBodiesDirty = false;
+    }
     if (rebind || m_boundGeneration != model.constraintGeneration()) {
         model.initConstraintGroups();  // TimeStepController.cpp:256
         if (pbd_clear_constraints(m_engine)) return fail("pbd_clear_constraints");
@@ -645,6 +703,17 @@ bool TimeStepController::step(SimulationModel &model) {
         m_sent = now; m_sentValid = true;
     }
     if (pbd_step(m_engine, 1)) return fail("pbd_step");
+    if (!model.getRigidBodies().empty()) {  // a handful of bodies: mirror their state right away
+        SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
+        const unsigned int nr = (unsigned int)rbs.size();
+        std::vector<float> x(3 * nr), q(4 * nr), v(3 * nr), w(3 * nr);
+        if (pbd_get_rigid_bodies(m_engine, x.data(), q.data(), v.data(), w.data())) return fail("pbd_get_rigid_bodies");
+        for (unsigned int i = 0; i < nr; i++) {
+            RigidBody &b = *rbs[i];
+            for (int k = 0; k < 3; k++) { b.m_x[k] = x[3 * i + k]; b.m_v[k] = v[3 * i + k]; b.m_omega[k] = w[3 * i + k]; }
+            b.m_q = Quaternionr(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+        }
+    }
     ParticleData &pd = model.getParticles();
     pd.aheadMask |= (1u << PBD_ATTR_X) | (1u << PBD_ATTR_V) | (1u << PBD_ATTR_OLDX) | (1u << PBD_ATTR_LASTX);
     m_tm.setTime(m_tm.getTime() + m_tm.getTimeStepSize());  // TimeStepController.cpp:239

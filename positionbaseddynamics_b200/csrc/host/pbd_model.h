@@ -154,6 +154,28 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// RigidBody (Simulation/RigidBody.h): the state that takes part in the coloured sweep through BallJoint /
+// RigidBodyParticleBallJoint.  Geometry, contacts and the other joint types stay with the reference.
+// ---------------------------------------------------------------------------------------------------------
+struct Quaternionr { Real w, x, y, z; Quaternionr(Real w_ = 1, Real x_ = 0, Real y_ = 0, Real z_ = 0) : w(w_), x(x_), y(y_), z(z_) {} };
+class RigidBody {
+public:
+    // initBody(mass, x, inertiaTensor, rotation, ...) of the reference without the mesh arguments (RigidBody.h:84-120)
+    void initBody(Real mass, const Vector3r &x, const Vector3r &inertiaTensor, const Quaternionr &rotation);
+    Real getMass() const { return m_mass; }
+    Real getInvMass() const { return m_invMass; }
+    const Vector3r &getPosition() const { return m_x; }
+    const Vector3r &getPosition0() const { return m_x0; }
+    const Vector3r &getVelocity() const { return m_v; }
+    const Vector3r &getAngularVelocity() const { return m_omega; }
+    const Quaternionr &getRotation() const { return m_q; }
+    const Vector3r &getInertiaTensor() const { return m_inertiaTensor; }
+    Real m_mass = 0, m_invMass = 0;
+    Vector3r m_x, m_x0, m_v, m_omega, m_inertiaTensor;
+    Quaternionr m_q, m_q0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // Constraint storage: per-type SoA in the flat parameter layout of include/pbd_b200.h, plus the global insertion
 // order (the reference's m_constraints vector) as (type, local index) pairs.
 // ---------------------------------------------------------------------------------------------------------
@@ -165,6 +187,7 @@ struct TypeStore { std::vector<unsigned int> ids, bodies; std::vector<Real> para
 
 class SimulationModel {
 public:
+    typedef std::vector<RigidBody *> RigidBodyVector;
     typedef std::vector<TriangleModel *> TriangleModelVector;
     typedef std::vector<TetModel *> TetModelVector;
     typedef std::vector<std::vector<unsigned int>> ConstraintGroupVector;
@@ -175,6 +198,10 @@ public:
     void reset();    // SimulationModel.cpp:270-304: x = x0 = oldX = lastX, v = a = 0
     void cleanup();  // SimulationModel.cpp:105-126
 
+    RigidBodyVector &getRigidBodies() { return m_rigidBodies; }  // the caller pushes bodies, the model deletes them (SimulationModel.cpp:105-126)
+    bool addBallJoint(unsigned int rbIndex1, unsigned int rbIndex2, const Vector3r &pos);                  // SimulationModel.cpp:306-317
+    bool addRigidBodyParticleBallJoint(unsigned int rbIndex, unsigned int particleIndex);                  // SimulationModel.cpp:449-460
+    mutable bool rigidBodiesDirty = true;   // host copy newer than the device copy
     ParticleData &getParticles() { return m_particles; }
     TriangleModelVector &getTriangleModels() { return m_triangleModels; }
     TetModelVector &getTetModels() { return m_tetModels; }
@@ -241,6 +268,7 @@ private:
     bool pushConstraint(int type, const unsigned int *bodies, const Real *params, bool ok);
     void setParam(int type, int slot, Real val);
     ParticleData m_particles;
+    RigidBodyVector m_rigidBodies;
     TriangleModelVector m_triangleModels;
     TetModelVector m_tetModels;
     TypeStore m_store[PBD_NUM_TYPES];
@@ -306,7 +334,7 @@ private:
     bool m_sentValid = false;
     const SimulationModel *m_boundModel = nullptr;
     uint64_t m_boundGeneration = 0;
-    unsigned int m_boundParticles = 0;
+    unsigned int m_boundParticles = 0, m_boundRigidBodies = 0;
 };
 
 }  // namespace pbd_b200

@@ -84,9 +84,28 @@ const float *pbdm_vertices(pbdm_model *m) {
     return x.empty() ? nullptr : &x[0][0];
 }
 
+unsigned pbdm_add_rigid_body(pbdm_model *m, float mass, const float *x3, const float *inertia3, const float *q4) {
+    RigidBody *rb = new RigidBody();
+    rb->initBody(mass, v3(x3), v3(inertia3), q4 ? Quaternionr(q4[0], q4[1], q4[2], q4[3]) : Quaternionr());
+    m->model.getRigidBodies().push_back(rb);
+    m->model.m_groupsInitialized = false; m->model.rigidBodiesDirty = true;
+    return (unsigned)m->model.getRigidBodies().size() - 1;
+}
+unsigned pbdm_num_rigid_bodies(pbdm_model *m) { return (unsigned)m->model.getRigidBodies().size(); }
+void pbdm_get_rigid_bodies(pbdm_model *m, float *out) {
+    const auto &rbs = m->model.getRigidBodies();
+    for (size_t i = 0; i < rbs.size(); i++) {
+        float *o = out + 13 * i; const RigidBody &b = *rbs[i];
+        for (int k = 0; k < 3; k++) { o[k] = b.m_x[k]; o[7 + k] = b.m_v[k]; o[10 + k] = b.m_omega[k]; }
+        o[3] = b.m_q.w; o[4] = b.m_q.x; o[5] = b.m_q.y; o[6] = b.m_q.z;
+    }
+}
+
 int pbdm_add_constraint(pbdm_model *m, int type, const unsigned *b, const float *a) {
     SimulationModel &M = m->model;
     switch (type) {
+    case PBD_BALLJOINT: return M.addBallJoint(b[0], b[1], v3(a));
+    case PBD_RB_PARTICLE_BALLJOINT: return M.addRigidBodyParticleBallJoint(b[0], b[1]);
     case PBD_DISTANCE: return M.addDistanceConstraint(b[0], b[1], a[0]);
     case PBD_DISTANCE_XPBD: return M.addDistanceConstraint_XPBD(b[0], b[1], a[0]);
     case PBD_DIHEDRAL: return M.addDihedralConstraint(b[0], b[1], b[2], b[3], a[0]);

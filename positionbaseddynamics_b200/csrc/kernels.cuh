@@ -57,7 +57,12 @@ template <int T>
 __device__ __forceinline__ Streamed load_streamed(const TypeArrays &a, unsigned i) {
     Streamed s;
     s.g0 = make_float4(0.f, 0.f, 0.f, 0.f); s.g1 = s.g0; s.s0 = 0.0f; s.s1 = 0.0f;
-    if (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) {
+    if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) {
+        const uint2 b = __ldg(a.idx2 + i);
+        s.b = make_uint4(b.x, b.y, 0u, 0u);
+        s.g0 = __ldg(a.gv[0] + i);
+        if (T == PBD_BALLJOINT) s.g1 = __ldg(a.gv[1] + i);
+    } else if (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) {
         const uint2 b = __ldg(a.idx2 + i);
         s.b = make_uint4(b.x, b.y, 0u, 0u);
         s.s0 = __ldg(a.gs[0] + i);
@@ -76,9 +81,28 @@ __device__ __forceinline__ Streamed load_streamed(const TypeArrays &a, unsigned 
 }
 
 // Gather -> project -> scatter for constraint i (index into the type's arrays) whose streamed part is already here.
+// Joints couple rigid bodies (their own small state arrays, L2 only) with each other or with a particle.
+template <int T>
+__device__ __forceinline__ void project_joint(float4 *pos, const TypeArrays &a, const Streamed &s) {
+    float4 X0 = __ldcg(a.rbX + s.b.x), Q0 = __ldcg(a.rbQ + s.b.x);
+    const float4 I0 = __ldg(a.rbIinv + s.b.x);
+    if (T == PBD_BALLJOINT) {
+        float4 X1 = __ldcg(a.rbX + s.b.y), Q1 = __ldcg(a.rbQ + s.b.y);
+        const float4 I1 = __ldg(a.rbIinv + s.b.y);
+        project_balljoint(X0, Q0, mk(I0.x, I0.y, I0.z), X1, Q1, mk(I1.x, I1.y, I1.z), mk(s.g0.x, s.g0.y, s.g0.z), mk(s.g1.x, s.g1.y, s.g1.z));
+        if (X1.w != 0.0f) { __stcg(a.rbX + s.b.y, X1); __stcg(a.rbQ + s.b.y, Q1); }
+    } else {
+        float4 p = __ldcg(pos + s.b.y);
+        project_rb_particle_balljoint(X0, Q0, mk(I0.x, I0.y, I0.z), p, mk(s.g0.x, s.g0.y, s.g0.z));
+        stp(pos + s.b.y, p);
+    }
+    if (X0.w != 0.0f) { __stcg(a.rbX + s.b.x, X0); __stcg(a.rbQ + s.b.x, Q0); }
+}
+
 template <int T, bool CA>
 __device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &a, unsigned i, const Streamed &s, float dt,
                                                  bool iterZero) {
+    if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) { project_joint<T>(pos, a, s); return; }
     constexpr bool XPBD = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
     constexpr int NB = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 2 : ((T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) ? 3 : 4);
     float4 p0 = ldp<CA>(pos + s.b.x), p1 = ldp<CA>(pos + s.b.y), p2, p3;
@@ -167,7 +191,7 @@ __global__ void __launch_bounds__(kProjectThreads) k_project_multi(float4 *pos, 
                         project_streamed<T, CA>(pos, a, ci, st, dt, iterZero != 0); } break;
     switch (m.type[s]) {
         PM(PBD_DISTANCE) PM(PBD_DISTANCE_XPBD) PM(PBD_DIHEDRAL) PM(PBD_ISOBENDING) PM(PBD_ISOBENDING_XPBD) PM(PBD_FEMTRIANGLE)
-        PM(PBD_STRAINTRIANGLE) PM(PBD_VOLUME) PM(PBD_VOLUME_XPBD) PM(PBD_FEMTET) PM(PBD_FEMTET_XPBD) PM(PBD_STRAINTET) PM(PBD_SHAPEMATCHING)
+        PM(PBD_STRAINTRIANGLE) PM(PBD_VOLUME) PM(PBD_VOLUME_XPBD) PM(PBD_FEMTET) PM(PBD_FEMTET_XPBD) PM(PBD_STRAINTET) PM(PBD_SHAPEMATCHING) PM(PBD_BALLJOINT) PM(PBD_RB_PARTICLE_BALLJOINT)
     default: break;
     }
 #undef PM
@@ -191,6 +215,56 @@ __global__ void __launch_bounds__(256) k_integrate(float4 *__restrict__ pos, flo
         __stcs(vel + i, v);
         __stcg(pos + i, x);
     }
+}
+
+// Rigid-body prologue / epilogue (a handful of bodies: one thread each).
+//   integrate: TimeStepController.cpp:97-107 + TimeIntegration::semiImplicitEuler / semiImplicitEulerRotation (TimeIntegration.cpp:7-39)
+//   velocity : TimeStepController.cpp:139-152 + velocityUpdate*/angularVelocityUpdate* (TimeIntegration.cpp:42-95; the angular update is
+//              first order in both modes, as in the reference)
+struct RbState { float4 *X, *Q, *V, *W, *oldX, *lastX, *oldQ, *lastQ; const float4 *I, *Iinv; unsigned n; };
+
+__global__ void k_rb_integrate(RbState r, float h, float gx, float gy, float gz) {
+    pdl_launch_dependents();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n) return;
+    pdl_wait();
+    float4 X = r.X[i], Q = r.Q[i], V = r.V[i], W = r.W[i];
+    r.lastX[i] = r.oldX[i]; r.oldX[i] = X;
+    r.lastQ[i] = r.oldQ[i]; r.oldQ[i] = Q;
+    if (V.w != 0.0f) {  // V.w = mass
+        V.x += gx * h; V.y += gy * h; V.z += gz * h;
+        X.x += V.x * h; X.y += V.y * h; X.z += V.z * h;
+        const M3 R = qmatrix(Q);
+        const float4 I = r.I[i], Ii = r.Iinv[i];
+        const M3 Iw = world_tensor(R, mk(I.x, I.y, I.z)), Jw = world_tensor(R, mk(Ii.x, Ii.y, Ii.z));
+        V3 om = mk(W.x, W.y, W.z);
+        const V3 t = -cross(om, mvec(Iw, om));  // torque = 0
+        om = om + mvec(Jw, t) * h;
+        const float4 dq = qmul(make_float4(om.x, om.y, om.z, 0.0f), Q);
+        const float hh = h * 0.5f;
+        Q = qnormalize(make_float4(Q.x + hh * dq.x, Q.y + hh * dq.y, Q.z + hh * dq.z, Q.w + hh * dq.w));
+        W.x = om.x; W.y = om.y; W.z = om.z;
+        r.X[i] = X; r.Q[i] = Q; r.V[i] = V; r.W[i] = W;
+    }
+}
+
+__global__ void k_rb_velocity(RbState r, float invH, float twoInvH, int secondOrder) {
+    pdl_launch_dependents();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n) return;
+    pdl_wait();
+    float4 V = r.V[i];
+    if (V.w == 0.0f) return;
+    const float4 X = __ldcg(r.X + i), Q = __ldcg(r.Q + i), o = r.oldX[i], oq = r.oldQ[i];
+    if (!secondOrder) { V.x = invH * (X.x - o.x); V.y = invH * (X.y - o.y); V.z = invH * (X.z - o.z); }
+    else {
+        const float4 l = r.lastX[i];
+        V.x = invH * (1.5f * X.x - 2.0f * o.x + 0.5f * l.x); V.y = invH * (1.5f * X.y - 2.0f * o.y + 0.5f * l.y); V.z = invH * (1.5f * X.z - 2.0f * o.z + 0.5f * l.z);
+    }
+    const float4 rel = qmul(Q, make_float4(-oq.x, -oq.y, -oq.z, oq.w));
+    float4 W = r.W[i];
+    W.x = rel.x * twoInvH; W.y = rel.y * twoInvH; W.z = rel.z * twoInvH;
+    r.V[i] = V; r.W[i] = W;
 }
 
 // v = (1/h)(x - oldX)   or   (1/h)(1.5 x - 2 oldX + 0.5 lastX)

@@ -115,7 +115,7 @@ constexpr unsigned type_bit(int t) { return 1u << t; }
 constexpr unsigned kMaskClothXPBD = type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_ISOBENDING_XPBD);
 constexpr unsigned kMaskLight = type_bit(PBD_DISTANCE) | type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_DIHEDRAL) | type_bit(PBD_ISOBENDING) |
                                 type_bit(PBD_ISOBENDING_XPBD) | type_bit(PBD_VOLUME) | type_bit(PBD_VOLUME_XPBD) | type_bit(PBD_FEMTRIANGLE);
-constexpr unsigned kMaskAll = (1u << PBD_NUM_TYPES) - 1u;
+constexpr unsigned kMaskAll = (1u << PBD_BALLJOINT) - 1u;  // every particle constraint type; rigid-body joints are not staged (graph mode only)
 
 // dispatch a statement on the runtime type, restricted to the compiled-in mask (T is a constant inside the statement)
 #define PBD_FOR_TYPE(MASK, type, ...)                                                                                    \

@@ -740,4 +740,119 @@ __device__ __forceinline__ void project_shapematching(float4 &q0, float4 &q1, fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Rigid bodies in the coloured sweep.  Quaternions are float4 (x, y, z, w) with Eigen's semantics.
+//   PositionBasedRigidBodyDynamics::computeMatrixK (PositionBasedRigidBodyDynamics.cpp:11-45)
+//   solve_BallJoint (:212-262), solve_RigidBodyParticleBallJoint (:2168-2217), update_* (:188-210, 2149-2166)
+//   RigidBody::rotationUpdated / updateInertiaW (Simulation/RigidBody.h:190-207): the world-space inverse inertia is a pure
+//   function of the (normalised) rotation, so it is rebuilt from q where needed instead of being stored.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 qmul(float4 a, float4 b) {  // Hamilton product, (x,y,z,w)
+    float4 r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+__device__ __forceinline__ float4 qnormalize(float4 q) {
+    const float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    return make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+}
+__device__ __forceinline__ M3 qmatrix(float4 q) {
+    M3 m;
+    const float tx = 2.0f * q.x, ty = 2.0f * q.y, tz = 2.0f * q.z;
+    const float twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    m.m[0][0] = 1.0f - (tyy + tzz); m.m[0][1] = txy - twz; m.m[0][2] = txz + twy;
+    m.m[1][0] = txy + twz; m.m[1][1] = 1.0f - (txx + tzz); m.m[1][2] = tyz - twx;
+    m.m[2][0] = txz - twy; m.m[2][1] = tyz + twx; m.m[2][2] = 1.0f - (txx + tyy);
+    return m;
+}
+__device__ __forceinline__ V3 mvec(const M3 &a, V3 v) {
+    return mk(a.m[0][0] * v.x + a.m[0][1] * v.y + a.m[0][2] * v.z, a.m[1][0] * v.x + a.m[1][1] * v.y + a.m[1][2] * v.z,
+              a.m[2][0] * v.x + a.m[2][1] * v.y + a.m[2][2] * v.z);
+}
+__device__ __forceinline__ M3 world_tensor(const M3 &R, V3 d) {  // R diag(d) R^T
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r.m[i][j] = R.m[i][0] * d.x * R.m[j][0] + R.m[i][1] * d.y * R.m[j][1] + R.m[i][2] * d.z * R.m[j][2];
+    return r;
+}
+__device__ __forceinline__ void matrix_k(V3 connector, float invMass, V3 x, const M3 &J, M3 &K) {
+    if (invMass != 0.0f) {
+        const V3 v = connector - x;
+        const float a = v.x, b = v.y, c = v.z;
+        const float j11 = J.m[0][0], j12 = J.m[0][1], j13 = J.m[0][2], j22 = J.m[1][1], j23 = J.m[1][2], j33 = J.m[2][2];
+        K.m[0][0] = c * c * j22 - b * c * (j23 + j23) + b * b * j33 + invMass;
+        K.m[0][1] = -(c * c * j12) + a * c * j23 + b * c * j13 - a * b * j33;
+        K.m[0][2] = b * c * j12 - a * c * j22 - b * b * j13 + a * b * j23;
+        K.m[1][0] = K.m[0][1];
+        K.m[1][1] = c * c * j11 - a * c * (j13 + j13) + a * a * j33 + invMass;
+        K.m[1][2] = -(b * c * j11) + a * c * j12 + a * b * j13 - a * a * j23;
+        K.m[2][0] = K.m[0][2];
+        K.m[2][1] = K.m[1][2];
+        K.m[2][2] = b * b * j11 - a * b * (j12 + j12) + a * a * j22 + invMass;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) K.m[i][j] = 0.0f;
+    }
+}
+__device__ __forceinline__ V3 llt_solve3(const M3 &A, V3 rhs) {  // (K1 + K2).llt().solve(rhs)
+    const float l00 = sqrtf(A.m[0][0]);
+    const float l10 = A.m[1][0] / l00, l20 = A.m[2][0] / l00;
+    const float l11 = sqrtf(A.m[1][1] - l10 * l10);
+    const float l21 = (A.m[2][1] - l20 * l10) / l11;
+    const float l22 = sqrtf(A.m[2][2] - l20 * l20 - l21 * l21);
+    const float y0 = rhs.x / l00;
+    const float y1 = (rhs.y - l10 * y0) / l11;
+    const float y2 = (rhs.z - l20 * y0 - l21 * y1) / l22;
+    const float z2 = y2 / l22;
+    const float z1 = (y1 - l21 * z2) / l11;
+    const float z0 = (y0 - l10 * z1 - l20 * z2) / l00;
+    return mk(z0, z1, z2);
+}
+// x += invMass pt ; q += 1/2 (0, J (r x pt)) q ; normalise   (BallJoint::solvePositionConstraint, Constraints.cpp:106-121)
+__device__ __forceinline__ void rb_correct(float4 &X, float4 &Q, const M3 &J, V3 r, V3 pt) {
+    const V3 ot = mvec(J, cross(r, pt));
+    const float4 dq = qmul(make_float4(ot.x, ot.y, ot.z, 0.0f), Q);
+    X.x += X.w * pt.x; X.y += X.w * pt.y; X.z += X.w * pt.z;
+    Q = qnormalize(make_float4(Q.x + 0.5f * dq.x, Q.y + 0.5f * dq.y, Q.z + 0.5f * dq.z, Q.w + 0.5f * dq.w));
+}
+
+// BallJoint between rigid bodies (X0,Q0) and (X1,Q1); l0/l1 = connectors in body space
+__device__ __forceinline__ void project_balljoint(float4 &X0, float4 &Q0, V3 Iinv0, float4 &X1, float4 &Q1, V3 Iinv1, V3 l0, V3 l1) {
+    const M3 R0 = qmatrix(Q0), R1 = qmatrix(Q1);
+    const V3 x0 = xyz(X0), x1 = xyz(X1);
+    const V3 c0 = mvec(R0, l0) + x0, c1 = mvec(R1, l1) + x1;  // update_BallJoint
+    const M3 J0 = world_tensor(R0, Iinv0), J1 = world_tensor(R1, Iinv1);
+    M3 K0, K1, K;
+    matrix_k(c0, X0.w, x0, J0, K0);
+    matrix_k(c1, X1.w, x1, J1, K1);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) K.m[i][j] = K0.m[i][j] + K1.m[i][j];
+    const V3 pt = llt_solve3(K, c1 - c0);
+    if (X0.w != 0.0f) rb_correct(X0, Q0, J0, c0 - x0, pt);
+    if (X1.w != 0.0f) rb_correct(X1, Q1, J1, c1 - x1, -pt);
+}
+
+// RigidBodyParticleBallJoint: rigid body (X0,Q0) and particle p (xyz, invMass)
+__device__ __forceinline__ void project_rb_particle_balljoint(float4 &X0, float4 &Q0, V3 Iinv0, float4 &p, V3 l0) {
+    const M3 R0 = qmatrix(Q0);
+    const V3 x0 = xyz(X0);
+    const V3 c0 = mvec(R0, l0) + x0;
+    const M3 J0 = world_tensor(R0, Iinv0);
+    M3 K;
+    matrix_k(c0, X0.w, x0, J0, K);
+    if (p.w != 0.0f) { K.m[0][0] += p.w; K.m[1][1] += p.w; K.m[2][2] += p.w; }
+    const V3 pt = llt_solve3(K, xyz(p) - c0);
+    if (X0.w != 0.0f) rb_correct(X0, Q0, J0, c0 - x0, pt);
+    if (p.w != 0.0f) { p.x -= p.w * pt.x; p.y -= p.w * pt.y; p.z -= p.w * pt.z; }
+}
+
 }  // namespace pbdk

@@ -12,7 +12,7 @@ MODEL_SYMBOLS = [
     "pbdm_model_create", "pbdm_model_destroy", "pbdm_model_reset", "pbdm_model_cleanup", "pbdm_add_regular_triangle_model",
     "pbdm_add_regular_tet_model", "pbdm_add_triangle_model", "pbdm_add_tet_model", "pbdm_num_particles", "pbdm_set_mass",
     "pbdm_get_mass", "pbdm_get_inv_mass", "pbdm_get_masses", "pbdm_get_particle", "pbdm_set_particle", "pbdm_get_particles", "pbdm_set_particles",
-    "pbdm_vertices", "pbdm_add_constraint", "pbdm_add_cloth_constraints", "pbdm_add_bending_constraints",
+    "pbdm_vertices", "pbdm_add_rigid_body", "pbdm_num_rigid_bodies", "pbdm_get_rigid_bodies", "pbdm_add_constraint", "pbdm_add_cloth_constraints", "pbdm_add_bending_constraints",
     "pbdm_add_solid_constraints", "pbdm_num_constraints", "pbdm_get_constraint", "pbdm_get_constraints",
     "pbdm_init_constraint_groups", "pbdm_num_groups", "pbdm_get_groups", "pbdm_set_model_param", "pbdm_num_triangle_models",
     "pbdm_tri_num_edges", "pbdm_tri_num_faces", "pbdm_tri_index_offset", "pbdm_tri_get_edges", "pbdm_tri_get_faces",
@@ -58,6 +58,9 @@ def _l():
         L.pbdm_get_particles.argtypes = [_vp, C.c_int, _vp]; L.pbdm_set_particles.argtypes = [_vp, C.c_int, _vp]
         L.pbdm_vertices.argtypes = one
         L.pbdm_add_constraint.argtypes = [_vp, C.c_int, _vp, _vp]
+        L.pbdm_add_rigid_body.argtypes = [_vp, _F, _vp, _vp, _vp]; L.pbdm_add_rigid_body.restype = C.c_uint
+        L.pbdm_num_rigid_bodies.argtypes = one; L.pbdm_num_rigid_bodies.restype = C.c_uint
+        L.pbdm_get_rigid_bodies.argtypes = [_vp, _vp]
         L.pbdm_add_cloth_constraints.argtypes = [_vp, C.c_uint, C.c_uint, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int]
         L.pbdm_add_bending_constraints.argtypes = [_vp, C.c_uint, C.c_uint, _F]
         L.pbdm_add_solid_constraints.argtypes = [_vp, C.c_uint, C.c_uint, _F, _F, _F, C.c_int, C.c_int]
@@ -154,6 +157,19 @@ class HostModel:
         b = np.zeros(4, dtype=np.uint32); b[:len(bodies)] = bodies
         a = np.zeros(8, dtype=np.float32); a[:len(args)] = args
         return _l().pbdm_add_constraint(self._h, ctype, _p(b), _p(a))
+
+    def add_rigid_body(self, mass, x, inertia, q=(1, 0, 0, 0)):
+        return _l().pbdm_add_rigid_body(self._h, float(mass), _p(_f32(x)), _p(_f32(inertia)), _p(_f32(q)))
+
+    def add_ball_joint(self, rb0, rb1, pos):
+        return self.add_constraint(_capi.BALLJOINT, [rb0, rb1], list(pos))
+
+    def add_rb_particle_ball_joint(self, rb, particle):
+        return self.add_constraint(_capi.RB_PARTICLE_BALLJOINT, [rb, particle], [])
+
+    def rigid_bodies(self):
+        n = _l().pbdm_num_rigid_bodies(self._h)
+        out = np.zeros((max(n, 1), 13), dtype=np.float32); _l().pbdm_get_rigid_bodies(self._h, _p(out)); return out[:n]
 
     def set_params(self, dt=0.005, sub_steps=5, max_iter=1, vel_method=0, gravity=(0, -9.81, 0)):
         self._params = dict(dt=dt, sub_steps=sub_steps, max_iter=max_iter, vel_method=vel_method, gravity=tuple(gravity))

@@ -135,6 +135,7 @@ STRUCT_SCENES = {
     "bar_strain_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 4),
     "bar_xpbd_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 6, k=1e5, vol_k=1e5),
     "bar_shapematching_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 5, k=0.5),
+    "cfg4_small_coupling": lambda m: scenes.cfg4(m, 14, (5, 3, 3)),
     "bar_femx_6x3x3": lambda m: scenes.bar(m, 6, 3, 3, 3),
 }
 
@@ -154,6 +155,7 @@ TRAJ_SCENES = {
     "bar_xpbd": (lambda m: scenes.bar(m, 7, 4, 4, 6, k=1e5, vol_k=1e5, sub_steps=2, max_iter=3), 0.01, 3),
     "bar_fem_vol": (lambda m: scenes.bar(m, 7, 4, 4, 2, k=1e6, extra_volume=True, sub_steps=3, max_iter=2), 0.01, 3),
     "cloth_second_order_12": (lambda m: scenes.cloth(m, 12, 12, 1, 0, max_iter=3, sub_steps=2, vel_method=1), 0.02, 4),
+    "cfg4_small_coupling": (lambda m: scenes.cfg4(m, 14, (5, 3, 3), cloth_method=1), 0.0, 10),
 }
 
 
@@ -171,7 +173,9 @@ def main():
         off, ids = ref.groups()
         st[name + "/types"] = t; st[name + "/bodies"] = b; st[name + "/params"] = p; st[name + "/group_off"] = off; st[name + "/group_ids"] = ids
         st[name + "/x0"] = ref.get("x0")
-        if name.startswith("c"):
+        if "coupling" in name:
+            st[name + "/rigid_bodies"] = ref.rigid_bodies()
+        if name.startswith("cloth") or name.startswith("cfg1"):
             st[name + "/tri_edges"] = ref.tri_edges(0); st[name + "/tri_faces"] = ref.tri_faces(0)
         if name.startswith("bar"):
             st[name + "/tet_edges"] = ref.tet_edges(0); st[name + "/tet_tets"] = ref.tet_tets(0)
@@ -185,6 +189,8 @@ def main():
             tr["%s/%s/start" % (name, prec)] = xs
             ref.step(steps)
             tr["%s/%s/x" % (name, prec)] = ref.get("x"); tr["%s/%s/v" % (name, prec)] = ref.get("v")
+            if "coupling" in name:
+                tr["%s/%s/rb" % (name, prec)] = ref.rigid_bodies()
             assert np.isfinite(ref.get("x")).all(), name
             moved = np.abs(ref.get("x") - xs).max()
             assert moved > 1e-5, (name, "nothing moved")

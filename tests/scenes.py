@@ -70,5 +70,43 @@ def mixed(m, n_cloth=24, bar_dims=(7, 4, 4), cloth_method=2, bending_method=2, s
     m.set_params(dt=0.005, sub_steps=sub_steps, max_iter=max_iter)
 
 
+def box_inertia(mass, w, h, d):
+    """computeInertiaTensorBox (Demos/CouplingDemos/RigidBodyClothCouplingDemo.cpp:140-146)."""
+    return (mass / 12.0 * (h * h + d * d), mass / 12.0 * (w * w + d * d), mass / 12.0 * (w * w + h * h))
+
+
+def coupling_rig(m, n_cols, n_rows, half=5.0):
+    """The 12-body / 8-BallJoint / 4-RigidBodyParticleBallJoint rig of RigidBodyClothCouplingDemo.cpp:151-289: four chains
+    (static anchor + two dynamic boxes) at the corners, the top box of each chain pinned to a cloth corner particle.
+    Must be called after the cloth (particle indices 0, n_cols-1, n_rows*n_cols-1, (n_rows-1)*n_cols)."""
+    width, height, depth = 0.4, 2.0, 0.4  # demo globals (RigidBodyClothCouplingDemo.cpp:33-35)
+    corners = [(-half, -half), (half, -half), (half, half), (-half, half)]
+    for cx, cz in corners:
+        r0 = m.add_rigid_body(0.0, (cx, 0.0, cz), box_inertia(1.0, 0.5, 0.5, 0.5))
+        r1 = m.add_rigid_body(1.0, (cx, 1.0, cz), box_inertia(1.0, width, height, depth))
+        r2 = m.add_rigid_body(1.0, (cx, 3.0, cz), box_inertia(1.0, width, height, depth))
+        m.add_ball_joint(r0, r1, (cx, 0.0, cz))
+        m.add_ball_joint(r1, r2, (cx, 2.0, cz))
+    for rb, particle in zip((2, 5, 8, 11), (0, n_cols - 1, n_rows * n_cols - 1, (n_rows - 1) * n_cols)):
+        m.add_rb_particle_ball_joint(rb, particle)
+
+
+def cfg4(m, n_cloth=224, bar_dims=(51, 21, 11), cloth_method=2, with_rig=True, sub_steps=5, max_iter=1):
+    """cfg4: 224x224 cloth (99,458 triangles; FEMTriangle + IsometricBending) + 51x21x11 tet block (50,000 tets, FEMTet) +
+    the rigid coupling rig; reference defaults 5 substeps x 1 iteration."""
+    m.add_regular_triangle_model(n_cloth, n_cloth, t=(-5, 4, -5), R=RX90, scale=(10.0, 10.0))
+    m.add_regular_tet_model(bar_dims[0], bar_dims[1], bar_dims[2], t=(0.0, 7.0, 0.0), R=np.eye(3), scale=(4.0, 1.5, 1.0))
+    off = n_cloth * n_cloth
+    for j in range(bar_dims[1]):
+        for k in range(bar_dims[2]):
+            m.set_mass(off + j * bar_dims[2] + k, 0.0)
+    m.add_cloth_constraints(0, cloth_method, dist_k=1.0, xx=1000.0, yy=1000.0, xy=500.0, pxy=0.3, pyx=0.3)
+    m.add_bending_constraints(0, 2, 0.01)
+    m.add_solid_constraints(0, 2, k=1.0e6, nu=0.3)
+    if with_rig:
+        coupling_rig(m, n_cloth, n_cloth)
+    m.set_params(dt=0.005, sub_steps=sub_steps, max_iter=max_iter)
+
+
 def projections_per_step(num_constraints, sub_steps, max_iter):
     return num_constraints * sub_steps * max_iter

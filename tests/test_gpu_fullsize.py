@@ -110,3 +110,20 @@ def test_free_fall_of_an_unpinned_sheet_is_rigid():
     assert np.abs(d[:, 1] - (-9.81 * h * h * k * (k + 1) / 2)).max() <= 2e-5
     assert np.abs(d[:, 0]).max() <= 1e-5 and np.abs(d[:, 2]).max() <= 1e-5
     m.close()
+
+
+def test_cfg4_full_size_vs_fp64(cpu_libs):
+    """cfg4 at the benchmark size: 224x224 cloth (FEMTriangle + IsometricBending) + 51x21x11 tet block (FEMTet) + the rigid
+    coupling rig, 5 substeps x 1 iteration; two steps against the fp64 checker."""
+    cpu = cpu_libs.CpuPbd("oracle", "f64"); cpu.set_threads(16)
+    gpu = _gpu(scenes.cfg4)
+    scenes.cfg4(cpu)
+    assert gpu.num_constraints() == cpu.num_constraints()
+    og, ig = gpu.groups(); oc, ic = cpu.groups()
+    assert (og == oc).all() and (ig == ic).all()
+    gpu.step(2); cpu.step(2)
+    e = rel_position_error(gpu.get("x"), cpu.get("x"))
+    erb = np.abs(gpu.rigid_bodies().astype(np.float64)[:, :7] - cpu.rigid_bodies()[:, :7]).max()
+    print("cfg4 full size: %d constraints, %d colours, particles rel %.2e, rigid bodies abs %.2e" % (gpu.num_constraints(), len(og) - 1, e, erb))
+    assert e <= 1e-4 and erb <= 1e-4
+    gpu.close()

@@ -232,3 +232,51 @@ def test_empty_and_constraint_free_models():
     expect = -9.81 * h * h * 10
     assert np.allclose(x[:, 1] - x0[:, 1], expect, rtol=1e-4, atol=5e-7), (x[:, 1] - x0[:, 1], expect)  # fp32 ulp of x (~1) is 6e-8
     m.close()
+
+
+def test_rigid_body_coupling_scene(cpu_libs):
+    """cloth + tet solid + the 12-body coupling rig (BallJoint, RigidBodyParticleBallJoint) inside
+    the coloured sweep; particles AND rigid-body state against the fp64 checker."""
+    from positionbaseddynamics_b200.model import HostModel
+    kind = "ref" if have_ref("f64") else "oracle"
+    gpu = HostModel(); cpu = cpu_libs.CpuPbd(kind, "f64")
+    for m in (gpu, cpu):
+        scenes.cfg4(m, 20, (6, 4, 3))
+    for _ in range(4):
+        gpu.step(5); cpu.step(5)
+    e = rel_position_error(gpu.get("x"), cpu.get("x"))
+    rg, rc = gpu.rigid_bodies().astype(np.float64), cpu.rigid_bodies()
+    e_rb_x = np.abs(rg[:, :3] - rc[:, :3]).max() / np.abs(rc[:, :3]).max()
+    e_rb_q = np.abs(rg[:, 3:7] - rc[:, 3:7]).max()
+    print("coupling (%s): particles rel %.2e, rigid-body x rel %.2e, q abs %.2e, |omega| max %.3f" % (kind, e, e_rb_x, e_rb_q, np.abs(rc[:, 10:]).max()))
+    assert e <= TOL and e_rb_x <= TOL and e_rb_q <= 1e-4
+    assert np.abs(rc[:, 7:]).max() > 1e-3  # the rig actually moves
+    # static anchors (mass 0) never move
+    assert (rg[0, :3] == np.array([-5.0, 0.0, -5.0])).all()
+    gpu.close()
+
+
+def test_engine_level_drop_in_with_rigid_bodies(cpu_libs):
+    """The C-ABI call sequence of INTEGRATION.md for a coupled model: pbd_set_rigid_bodies before the joints are added."""
+    from positionbaseddynamics_b200 import _capi
+    cpu = cpu_libs.CpuPbd("oracle", "f64")
+    scenes.cfg4(cpu, 16, (5, 3, 3))
+    types, bodies, params, _ = cpu.constraints()
+    off, ids = cpu.groups()
+    mass, _ = cpu.masses()
+    rb = cpu.rigid_bodies()
+    eng = _capi.Engine(0)
+    eng.set_particles(cpu.get("x"), mass, x0=cpu.get("x0"))
+    rb_mass = [0.0 if i % 3 == 0 else 1.0 for i in range(12)]
+    inertia = [scenes.box_inertia(1.0, 0.5, 0.5, 0.5) if i % 3 == 0 else scenes.box_inertia(1.0, 0.4, 2.0, 0.4) for i in range(12)]
+    eng.set_rigid_bodies(rb_mass, rb[:, :3], rb[:, 3:7], inertia)
+    eng.add_flat(types, bodies, params)
+    eng.set_groups(off, ids)
+    eng.set_params(dt=0.005, sub_steps=5, max_iter=1)
+    eng.step(6); eng.sync(); cpu.step(6)
+    assert rel_position_error(eng.get_attr(_capi.ATTR_X), cpu.get("x")) <= TOL
+    assert np.abs(eng.get_rigid_bodies()[:, :7] - cpu.rigid_bodies()[:, :7]).max() <= 1e-4
+    eng.set_mode(_capi.MODE_PERSISTENT)
+    with pytest.raises(_capi.PbdError):
+        eng.step(1)
+    eng.close()

@@ -82,10 +82,13 @@ def test_structure_matches_reference(name, cpu_libs):
     t, b, p, nb = o.constraints()
     off, ids = o.groups()
     assert (t == d[name + "/types"]).all()
-    assert (b == d[name + "/bodies"]).all()
+    nbod = np.array([2 if tt >= 13 or tt < 2 else 4 for tt in t])
+    assert all((b[i][:nbod[i]] == d[name + "/bodies"][i][:nbod[i]]).all() for i in range(len(t)))
     assert (off == d[name + "/group_off"]).all() and (ids == d[name + "/group_ids"]).all()
     ref_p = d[name + "/params"]
     assert np.abs(p - ref_p).max() <= 1e-9 * _scale(ref_p)
+    if name + "/rigid_bodies" in d:
+        assert np.abs(o.rigid_bodies() - d[name + "/rigid_bodies"]).max() <= 1e-12
     assert np.abs(o.get("x0") - d[name + "/x0"]).max() <= 1e-12
     if name + "/tri_edges" in d:
         assert (o.tri_edges(0) == d[name + "/tri_edges"]).all() and (o.tri_faces(0) == d[name + "/tri_faces"]).all()
@@ -104,9 +107,12 @@ def test_trajectories_match_reference(name, prec, cpu_libs):
     o.step(steps)
     x_ref = d["%s/%s/x" % (name, prec)]
     err = np.abs(o.get("x") - x_ref).max() / _scale(x_ref)
+    if "%s/%s/rb" % (name, prec) in d:
+        rb_ref = d["%s/%s/rb" % (name, prec)]
+        err = max(err, np.abs(o.rigid_bodies() - rb_ref).max() / _scale(rb_ref))
     tol = 1e-9 if prec == "f64" else 2e-5
-    if prec == "f32" and "isobend" in name:
-        tol = 2e-3  # fp32 cancellation noise of the reference's own bending evaluation (see DESIGN.md "Parity")
+    if prec == "f32" and ("isobend" in name or "coupling" in name):  # cfg4 uses IsometricBending (PBD) on the cloth
+        tol = 2e-3 if "isobend" in name else 1e-2  # fp32 cancellation noise of the reference's own bending evaluation (see DESIGN.md "Parity")
     if prec == "f32" and ("dihedral" in name or "femx" in name):
         tol = 2e-4  # acos near a flat hinge / sqrt(2U') near the rest state: ill-conditioned in fp32 on both sides
     assert err <= tol, (name, prec, err)
