@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--size", type=int, default=1000, help="cloth is size x size particles (cfg2 = 1000)")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "launch"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 is the BASELINE.json metric configuration (default); cfg1/cfg3 are side measurements for DESIGN.md")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -53,6 +53,10 @@ def build_scene(m, size, iters):
         scenes.cfg1(m, 50); return 1, 5
     if WORKLOAD == "cfg3":
         scenes.cfg3(m); return 10, 5
+    if WORKLOAD == "cfg4":
+        scenes.cfg4(m); return 5, 1
+    if WORKLOAD == "cfg5":
+        scenes.cfg2(m, 500, iters); return 1, iters  # one 500x500 cloth per GPU (run with --gpus 8)
     scenes.cfg2(m, size, iters); return 1, iters
 
 
@@ -63,6 +67,13 @@ def workload_config(size, iters, n_gpus):
     if WORKLOAD == "cfg3":
         return {"workload": "cfg3", "scene": "tet bar 101x21x21 = 200,000 tets, FEMTet(E=1e6, nu=0.3) + Volume per tet", "sub_steps": 10, "iterations": 5,
                 "dt": 0.005, "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus, "l2": "L2-resident working set (~16 MB); latency-bound config"}
+    if WORKLOAD == "cfg4":
+        return {"workload": "cfg4", "scene": "224x224 cloth (FEMTriangle + IsometricBending) + 51x21x11 tet block (FEMTet) + 12 rigid bodies / 8 BallJoints / "
+                                             "4 RigidBodyParticleBallJoints", "sub_steps": 5, "iterations": 1, "dt": 0.005, "replicas": n_gpus,
+                "parallelism": "replica x%d" % n_gpus, "l2": "L2-resident working set; latency-bound config"}
+    if WORKLOAD == "cfg5":
+        return {"workload": "cfg5", "scene": "one 500x500 cloth per GPU, Distance_XPBD + IsometricBending_XPBD", "sub_steps": 1, "iterations": iters, "dt": 0.005,
+                "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus, "l2": "per-sweep constraint stream 48 MB: L2-resident"}
     return {"workload": "cfg2", "scene": "cloth %dx%d particles, Distance_XPBD(k=1e5)+IsometricBending_XPBD(k=100)" % (size, size),
             "sub_steps": 1, "iterations": iters, "dt": 0.005, "replicas": n_gpus, "parallelism": "replica x%d" % n_gpus,
             "l2": "inputs larger than L2: the per-sweep constraint stream (~192 MB at 1000x1000) exceeds the 126 MB L2"}
@@ -204,6 +215,11 @@ def run_b200(args):
     build_s = time.time() - t0
     eng = _capi.Engine(local)
     eng.set_particles(x0, mass)
+    rb = hm.rigid_bodies()
+    if len(rb):  # cfg4: the coupling rig (tests/scenes.py:coupling_rig)
+        import scenes as _sc
+        eng.set_rigid_bodies([0.0 if i % 3 == 0 else 1.0 for i in range(len(rb))], rb[:, :3], rb[:, 3:7],
+                             [_sc.box_inertia(1.0, 0.5, 0.5, 0.5) if i % 3 == 0 else _sc.box_inertia(1.0, 0.4, 2.0, 0.4) for i in range(len(rb))])
     eng.add_flat(types, bodies, params)
     eng.set_groups(off, ids)
     eng.set_params(dt=0.005, sub_steps=sub_steps, max_iter=args.iters)
@@ -228,7 +244,7 @@ def run_b200(args):
     # pick the execution mode on a short probe unless forced
     if args.mode == "auto":
         probe = {}
-        for name in ("graph", "persistent"):
+        for name in (("graph",) if len(rb) else ("graph", "persistent")):
             try:
                 ms, _ = timed(modes[name], 3, 2)
                 probe[name] = ms
@@ -310,7 +326,7 @@ def run_b200(args):
         dom = int(np.argmax(tms))
         share = float(tms[dom] / max(tms.sum() + tmi + tmv, 1e-9))
         launches_per_step = tl[dom] / reps
-        bytes_per_launch = float(st.constraints_per_type[dom] * PER_PROJ[dom] * args.iters * sub_steps / max(launches_per_step, 1))
+        bytes_per_launch = float(st.constraints_per_type[dom] * PER_PROJ.get(dom, 0.0) * args.iters * sub_steps / max(launches_per_step, 1))
         ser_ms = float(tms[dom] / max(tl[dom], 1))
         pipe_ms = share * ms_step / max(launches_per_step, 1)
         roof = {"kernel": "k_project<%s>" % _capi.TYPE_NAMES[dom], "bytes_per_launch": bytes_per_launch, "ms_per_launch": pipe_ms,
