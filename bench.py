@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1000, help="cloth is size x size particles (cfg2 = 1000)")
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "launch"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "launch", "tiled"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 is the BASELINE.json metric configuration (default); cfg1/cfg3 are side measurements for DESIGN.md")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,7 +226,7 @@ def run_b200(args):
     del types, bodies, params
     hm.close()
 
-    modes = {"graph": _capi.MODE_GRAPH, "persistent": _capi.MODE_PERSISTENT, "launch": _capi.MODE_LAUNCH}
+    modes = {"graph": _capi.MODE_GRAPH, "persistent": _capi.MODE_PERSISTENT, "launch": _capi.MODE_LAUNCH, "tiled": _capi.MODE_TILED}
     proj_per_step = ncons * sub_steps * args.iters
 
     def timed(mode, steps, warmup):
@@ -244,7 +244,7 @@ def run_b200(args):
     # pick the execution mode on a short probe unless forced
     if args.mode == "auto":
         probe = {}
-        for name in (("graph",) if len(rb) else ("graph", "persistent")):
+        for name in (("graph",) if len(rb) else ("graph", "persistent", "tiled")):
             try:
                 ms, _ = timed(modes[name], 3, 2)
                 probe[name] = ms
@@ -313,8 +313,8 @@ def run_b200(args):
                 _capi.FEMTRIANGLE: 128.0, _capi.STRAINTRIANGLE: 124.0, _capi.VOLUME: 148.0, _capi.VOLUME_XPBD: 156.0, _capi.FEMTET: 184.0,
                 _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0, _capi.SHAPEMATCHING: 240.0}  # DESIGN.md byte table (algorithmic bytes per projection)
     ms_step = ms_max / args.steps
-    if mode_name == "persistent":
-        roof = {"kernel": "k_step_persistent (whole step, one cooperative launch)", "bytes_per_launch": st.bytes_per_step, "ms_per_launch": ms_step}
+    if mode_name in ("persistent", "tiled"):
+        roof = {"kernel": "k_step_%s (whole step, one cooperative launch)" % mode_name, "bytes_per_launch": st.bytes_per_step, "ms_per_launch": ms_step}
     else:
         eng.set_mode(_capi.MODE_LAUNCH)
         eng.step(2); eng.sync()

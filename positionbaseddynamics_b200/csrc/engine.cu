@@ -16,6 +16,7 @@
 #include <vector>
 #include "kernels.cuh"
 #include "persistent.cuh"
+#include "tiled.cuh"
 #include "host/pbd_model.h"
 
 using namespace pbdk;
@@ -101,6 +102,10 @@ struct pbd_engine {
     bool timingPending = false;
     int persistentThreads = 0;
     bool mergeColours = true;             // one launch per colour when it holds several types (PBD_B200_MERGE=0 disables)
+    std::vector<unsigned> slot;           // host particle index -> device slot (formula layouts or the tile-major permutation)
+    DevBuf dSlot, dSlotOld, relayoutTmp, dTileOff, dTileStart, dTilePrivate;
+    bool slotIsTiled = false;
+    unsigned nTiles = 0;
     int layout = 1;                       // particle placement (device_image.h particle_slot); PBD_B200_LAYOUT=linear selects 0
     bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
     bool gatherCA = true;                 // particle gathers through L1 (tuning knob: PBD_B200_GATHER=cg selects L2-only loads)
@@ -192,11 +197,39 @@ static float4 *attr_buf(pbd_engine *e, int attr) {
     }
 }
 
+static int upload_slot_map(pbd_engine *e) {
+    if (e->n == 0) return 0;
+    CKE(e->dSlot.alloc((size_t)e->n * sizeof(unsigned)));
+    CK(cudaMemcpy(e->dSlot.p, e->slot.data(), (size_t)e->n * sizeof(unsigned), cudaMemcpyHostToDevice));
+    return 0;
+}
+static void formula_slot_map(pbd_engine *e, std::vector<unsigned> &m) {
+    m.resize(e->n);
+    for (unsigned i = 0; i < e->n; i++) m[i] = particle_slot(i, e->n, e->layout);
+}
+// move every particle array from the current slot map to `newSlot`
+static int relayout(pbd_engine *e, const std::vector<unsigned> &newSlot) {
+    if (e->n == 0 || newSlot == e->slot) { e->slot = newSlot; return 0; }
+    const size_t nb = (size_t)e->n * sizeof(unsigned);
+    CKE(e->dSlotOld.alloc(nb));
+    CK(cudaMemcpy(e->dSlotOld.p, e->slot.data(), nb, cudaMemcpyHostToDevice));
+    e->slot = newSlot;
+    CKE(upload_slot_map(e));
+    CKE(e->relayoutTmp.alloc((size_t)e->n * sizeof(float4)));
+    for (DevBuf *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0}) {
+        k_relayout<<<(e->n + 255) / 256, 256, 0, e->stream>>>((const float4 *)b->p, (float4 *)e->relayoutTmp.p, e->n, (const unsigned *)e->dSlotOld.p, (const unsigned *)e->dSlot.p);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        std::swap(b->p, e->relayoutTmp.p); std::swap(b->bytes, e->relayoutTmp.bytes);
+    }
+    return 0;
+}
+
 // host AoS-3 -> staging -> float4 (keeps .w)
 static int upload3(pbd_engine *e, const float *src, float4 *dst, int keepW) {
     const size_t bytes = (size_t)e->n * 3 * sizeof(float);
     CK(cudaMemcpyAsync(e->stage.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
-    k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, dst, e->n, keepW, e->layout);
+    k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, dst, e->n, keepW, (const unsigned *)e->dSlot.p);
     CK(cudaGetLastError());
     return 0;
 }
@@ -206,7 +239,7 @@ extern "C" int pbd_set_masses(pbd_engine *e, const float *mass) {
     CKE(use(e));
     if (e->n == 0) return 0;
     CK(cudaMemcpyAsync(e->massStage.p, mass, (size_t)e->n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    k_set_w<<<nblk(e->n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (const float *)e->massStage.p, e->n, e->layout);
+    k_set_w<<<nblk(e->n, 256), 256, 0, e->stream>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (const float *)e->massStage.p, e->n, (const unsigned *)e->dSlot.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));  // staging buffers are reused by the next call
     return 0;
@@ -223,7 +256,9 @@ extern "C" int pbd_set_particles(pbd_engine *e, unsigned n, const float *x, cons
     CKE(e->stage.alloc((size_t)n * 3 * sizeof(float)));
     CKE(e->massStage.alloc((size_t)n * sizeof(float)));
     drop_graph(e);  // buffers may have moved
+    formula_slot_map(e, e->slot); e->slotIsTiled = false; e->imageDirty = true;
     if (n == 0) return 0;
+    CKE(upload_slot_map(e));
     CK(cudaMemsetAsync(e->vel.p, 0, b4, e->stream));
     CKE(upload3(e, x, (float4 *)e->pos.p, 0)); CK(cudaStreamSynchronize(e->stream));
     if (v) { CKE(upload3(e, v, (float4 *)e->vel.p, 0)); CK(cudaStreamSynchronize(e->stream)); }
@@ -255,7 +290,7 @@ extern "C" int pbd_get_attr(pbd_engine *e, int attr, float *dst) {
     const float4 *src = attr_buf(e, attr);
     if (!src) return fail("pbd_get_attr: bad attribute %d", attr);
     if (e->n == 0) return 0;
-    k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>(src, (float *)e->stage.p, e->n, e->layout);
+    k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>(src, (float *)e->stage.p, e->n, (const unsigned *)e->dSlot.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, e->stage.p, (size_t)e->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -429,7 +464,8 @@ extern "C" int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsign
 }
 extern "C" int pbd_set_mode(pbd_engine *e, int mode) {
     if (!e) return fail("null engine");
-    if (mode < 0 || mode > 2) return fail("unknown solver mode %d", mode);
+    if (mode < 0 || mode > PBD_MODE_TILED) return fail("unknown solver mode %d", mode);
+    if ((mode == PBD_MODE_TILED) != (e->mode == PBD_MODE_TILED)) e->imageDirty = true;  // the tiled image encodes indices differently
     e->mode = mode; drop_graph(e);
     return 0;
 }
@@ -470,6 +506,77 @@ template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v
     return 0;
 }
 
+// Tiled mode (tiled.cuh): partition the particles into one tile per SM by recursive coordinate bisection of the rest
+// positions, classify them (private = every constraint touching it lies inside its tile), and move the device arrays to the
+// tile-major order [tile 0: private..., shared...][tile 1: ...].
+static void bisect(std::vector<unsigned> &idx, size_t lo, size_t hi, unsigned t0, unsigned nt, const std::vector<float4> &x, std::vector<unsigned> &tileOf) {
+    if (nt == 1) { for (size_t i = lo; i < hi; i++) tileOf[idx[i]] = t0; return; }
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (size_t i = lo; i < hi; i++) {
+        const float4 &p = x[idx[i]];
+        const float c[3] = {p.x, p.y, p.z};
+        for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], c[k]); mx[k] = std::max(mx[k], c[k]); }
+    }
+    int ax = 0;
+    for (int k = 1; k < 3; k++) if (mx[k] - mn[k] > mx[ax] - mn[ax]) ax = k;
+    const unsigned ntL = nt / 2;
+    const size_t mid = lo + (size_t)((double)(hi - lo) * ntL / nt);
+    auto key = [&](unsigned i) { const float4 &p = x[i]; return ax == 0 ? p.x : (ax == 1 ? p.y : p.z); };
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](unsigned a, unsigned b) { const float ka = key(a), kb = key(b); return ka < kb || (ka == kb && a < b); });
+    bisect(idx, lo, mid, t0, ntL, x, tileOf);
+    bisect(idx, mid, hi, t0 + ntL, nt - ntL, x, tileOf);
+}
+
+static int prepare_tiles(pbd_engine *e, std::vector<unsigned> &tileOf, std::vector<unsigned> &tileStart, std::vector<unsigned char> &inSmem) {
+    if (e->nRb || e->host[PBD_BALLJOINT].ids.size() || e->host[PBD_RB_PARTICLE_BALLJOINT].ids.size())
+        return fail("tiled mode handles particle constraints only (rigid-body joints: use the graph mode)");
+    const unsigned n = e->n, nTiles = (unsigned)e->smCount;
+    e->nTiles = nTiles;
+    tileOf.assign(n, 0); inSmem.assign(n, 0); tileStart.assign(nTiles + 1, 0);
+    std::vector<unsigned> priv(nTiles, 0);
+    if (n) {
+        // rest positions by host index
+        std::vector<float4> raw(n), x(n);
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMemcpy(raw.data(), e->pos0.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (unsigned i = 0; i < n; i++) x[i] = raw[e->slot[i]];
+        std::vector<unsigned> idx(n);
+        for (unsigned i = 0; i < n; i++) idx[i] = i;
+        bisect(idx, 0, n, 0, nTiles, x, tileOf);
+        // shared = touched by a constraint whose particles lie in more than one tile
+        std::vector<unsigned char> shared(n, 0);
+        for (int t = 0; t < PBD_NUM_TYPES; t++) {
+            const HostType &h = e->host[t];
+            const int nb = type_shape(t).nBodies;
+            for (size_t c = 0; c < h.ids.size(); c++) {
+                const unsigned *b = &h.bodies[c * nb];
+                bool spans = false;
+                for (int k = 1; k < nb; k++) spans |= (tileOf[b[k]] != tileOf[b[0]]);
+                if (spans) for (int k = 0; k < nb; k++) shared[b[k]] = 1;
+            }
+        }
+        // tile-major slots: private particles first (host order), shared behind them
+        std::vector<unsigned> cntP(nTiles, 0), cntS(nTiles, 0);
+        for (unsigned i = 0; i < n; i++) (shared[i] ? cntS : cntP)[tileOf[i]]++;
+        for (unsigned t = 0; t < nTiles; t++) tileStart[t + 1] = tileStart[t] + cntP[t] + cntS[t];
+        std::vector<unsigned> curP(nTiles), curS(nTiles), newSlot(n);
+        for (unsigned t = 0; t < nTiles; t++) { curP[t] = tileStart[t]; curS[t] = tileStart[t] + cntP[t]; priv[t] = std::min<unsigned>(cntP[t], (unsigned)kTileCapacity); }
+        for (unsigned i = 0; i < n; i++) {
+            const unsigned t = tileOf[i];
+            newSlot[i] = shared[i] ? curS[t]++ : curP[t]++;
+            inSmem[i] = !shared[i] && (newSlot[i] - tileStart[t] < priv[t]);
+        }
+        CKE(relayout(e, newSlot));
+        unsigned long long nShared = 0;
+        for (unsigned i = 0; i < n; i++) nShared += shared[i];
+        if (getenv("PBD_B200_VERBOSE")) fprintf(stderr, "[pbd_b200] tiled: %u tiles, %u particles, %.1f %% shared, max private/tile %u\n", nTiles, n, 100.0 * nShared / n, *std::max_element(cntP.begin(), cntP.end()));
+    }
+    e->slotIsTiled = true;
+    CKE(upload_vec(e->dTileStart, tileStart, e->stream));
+    CKE(upload_vec(e->dTilePrivate, priv, e->stream));
+    return 0;
+}
+
 static int flatten(pbd_engine *e) {
     if (!e->imageDirty) return 0;
     CKE(use(e));
@@ -481,6 +588,18 @@ static int flatten(pbd_engine *e) {
     std::vector<std::pair<int, unsigned>> map;
     CKE(build_id_map(e, map));
     const unsigned nGroups = (unsigned)e->groupOff.size() - 1;
+
+    // 0. particle placement: tile-major for the tiled mode, the formula layout otherwise
+    const bool tiled = (e->mode == PBD_MODE_TILED);
+    std::vector<unsigned> tileOf, tileStart, tileOff;
+    std::vector<unsigned char> inSmem;
+    if (tiled) CKE(prepare_tiles(e, tileOf, tileStart, inSmem));
+    else if (e->slotIsTiled) {
+        std::vector<unsigned> m;
+        formula_slot_map(e, m);
+        CKE(relayout(e, m));
+        e->slotIsTiled = false;
+    }
 
     // 1. order every type's constraints bucket by bucket
     std::vector<unsigned> order[PBD_NUM_TYPES];  // device position -> local host index
@@ -494,18 +613,25 @@ static int flatten(pbd_engine *e) {
         }
         for (int t = 0; t < PBD_NUM_TYPES; t++) {
             if (tmp[t].empty()) continue;
-            if (e->sortBuckets && t != PBD_BALLJOINT && t != PBD_RB_PARTICLE_BALLJOINT) {  // order inside a colour is free: sort by lowest particle index for gather locality
+            if ((e->sortBuckets || tiled) && t != PBD_BALLJOINT && t != PBD_RB_PARTICLE_BALLJOINT) {  // order inside a colour is free: sort by lowest particle slot for gather locality
                 const int nb = type_shape(t).nBodies;
                 const unsigned *bod = e->host[t].bodies.data();
-                std::vector<std::pair<unsigned, unsigned>> keyed(tmp[t].size());
+                std::vector<std::pair<unsigned long long, unsigned>> keyed(tmp[t].size());
                 for (size_t i = 0; i < tmp[t].size(); i++) {
                     const unsigned *b = bod + (size_t)tmp[t][i] * nb;
-                    unsigned mn = particle_slot(b[0], e->n, e->layout);
-                    for (int k = 1; k < nb; k++) mn = std::min(mn, particle_slot(b[k], e->n, e->layout));
-                    keyed[i] = std::make_pair(mn, tmp[t][i]);
+                    unsigned mn = e->slot[b[0]];
+                    for (int k = 1; k < nb; k++) mn = std::min(mn, e->slot[b[k]]);
+                    // tiled: the executing tile (tile of the first particle) is the major key
+                    keyed[i] = std::make_pair(((unsigned long long)(tiled ? tileOf[b[0]] : 0u) << 32) | mn, tmp[t][i]);
                 }
-                std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) { return a.first < b.first; });
+                std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; });
                 for (size_t i = 0; i < keyed.size(); i++) tmp[t][i] = keyed[i].second;
+                if (tiled) {  // range of every tile inside this bucket
+                    const size_t base = tileOff.size();
+                    tileOff.resize(base + e->nTiles + 1, 0u);
+                    for (size_t i = 0; i < keyed.size(); i++) tileOff[base + (keyed[i].first >> 32) + 1]++;
+                    for (unsigned k = 0; k < e->nTiles; k++) tileOff[base + k + 1] += tileOff[base + k];
+                }
             }
             Bucket b; b.type = t; b.first = (unsigned)order[t].size(); b.count = (unsigned)tmp[t].size(); b.colour = g;
             e->buckets.push_back(b);
@@ -553,7 +679,9 @@ static int flatten(pbd_engine *e) {
         auto B = [&](unsigned i, int k) {
             const unsigned raw = h.bodies[(size_t)order[t][i] * s.nBodies + k];
             const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && k == 0);
-            return isRb ? raw : particle_slot(raw, e->n, e->layout);
+            if (isRb) return raw;
+            if (tiled && inSmem[raw]) return kSmemFlag | (e->slot[raw] - tileStart[tileOf[raw]]);  // lives in the executing CTA's shared memory
+            return e->slot[raw];
         };
 
         // indices
@@ -678,6 +806,7 @@ static int flatten(pbd_engine *e) {
 
     // 3. bucket table + type arrays for the persistent kernel
     CKE(upload_vec(e->dBuckets, e->buckets, e->stream));
+    if (tiled) CKE(upload_vec(e->dTileOff, tileOff, e->stream));
     CKE(e->dBarrier.alloc(256));
     CK(cudaMemsetAsync(e->dBarrier.p, 0, 256, e->stream));
     e->barrierBase = 0;
@@ -866,6 +995,47 @@ static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long 
     return launch_persistent<kMaskAll, 512>(e, s, pa);
 }
 
+template <unsigned MASK, int THREADS>
+static int launch_tiled(pbd_engine *e, cudaStream_t s, TiledArgs &ta) {
+    auto kernel = k_step_tiled<MASK, THREADS>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmemBytes));
+        int perSM = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, THREADS, kTiledSmemBytes));
+        if (perSM < 1) return fail("tiled kernel does not fit on an SM");
+        configured = true;
+    }
+    void *args[] = {&ta};
+    CK(cudaLaunchCooperativeKernel((void *)kernel, dim3(e->nTiles), dim3(THREADS), args, kTiledSmemBytes, s));
+    return 0;
+}
+
+static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
+    const float h = e->dt / (float)e->subSteps;
+    TiledArgs ta;
+    ta.pos = (float4 *)e->pos.p; ta.vel = (float4 *)e->vel.p; ta.oldp = (float4 *)e->oldp.p; ta.lastp = (float4 *)e->lastp.p;
+    ta.buckets = (const Bucket *)e->dBuckets.p;
+    ta.tileOff = (const unsigned *)e->dTileOff.p; ta.tileStart = (const unsigned *)e->dTileStart.p; ta.tilePrivate = (const unsigned *)e->dTilePrivate.p;
+    ta.nBuckets = (unsigned)e->buckets.size(); ta.subSteps = e->subSteps; ta.maxIter = e->maxIter;
+    ta.h = h; ta.invH = (float)(1.0 / (double)h); ta.gx = e->g[0]; ta.gy = e->g[1]; ta.gz = e->g[2];
+    ta.secondOrder = e->velMethod; ta.trackLast = track_last(e);
+    ta.barrier = (unsigned long long *)e->dBarrier.p;
+    ta.barrierBase = e->barrierBase;
+    // barriers per substep: one after the prologue, one per colour and sweep
+    e->barrierBase += (unsigned long long)e->subSteps * (1ull + (unsigned long long)e->maxIter * e->coloursUsed) * e->nTiles;
+    unsigned present = 0;
+    for (int t = 0; t < PBD_NUM_TYPES; t++) { ta.types[t] = e->dev[t].arrays; if (e->dev[t].count) present |= 1u << t; }
+    *launches = 1;
+    const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
+    if ((present & ~kMaskClothXPBD) == 0) {
+        if (pt == 512) return launch_tiled<kMaskClothXPBD, 512>(e, s, ta);
+        return launch_tiled<kMaskClothXPBD, 1024>(e, s, ta);
+    }
+    if ((present & ~kMaskLight) == 0) return launch_tiled<kMaskLight, 512>(e, s, ta);
+    return launch_tiled<kMaskAll, 512>(e, s, ta);
+}
+
 static int ensure_graph(pbd_engine *e, unsigned long long *launchesPerStep) {
     if (e->graphValid) return 0;
     cudaGraph_t graph = nullptr;
@@ -895,6 +1065,8 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
             CKE(enqueue_step_launches(e, e->stream, &L));
         } else if (e->mode == PBD_MODE_PERSISTENT) {
             CKE(enqueue_step_persistent(e, e->stream, &L));
+        } else if (e->mode == PBD_MODE_TILED) {
+            CKE(enqueue_step_tiled(e, e->stream, &L));
         } else {
             unsigned long long LL = 0;
             if (!e->graphValid) { CKE(ensure_graph(e, &LL)); graphLaunches = LL; }
@@ -933,20 +1105,20 @@ extern "C" int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, 
     CKE(stage2.alloc(bytes));
     if (x_in) {
         CK(cudaMemcpyAsync(e->stage.p, x_in, bytes, cudaMemcpyHostToDevice, e->stream));
-        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, (float4 *)e->pos.p, e->n, 1, e->layout);
+        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)e->stage.p, (float4 *)e->pos.p, e->n, 1, (const unsigned *)e->dSlot.p);
     }
     if (v_in) {
         CK(cudaMemcpyAsync(stage2.p, v_in, bytes, cudaMemcpyHostToDevice, e->stream));
-        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)stage2.p, (float4 *)e->vel.p, e->n, 1, e->layout);
+        k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)stage2.p, (float4 *)e->vel.p, e->n, 1, (const unsigned *)e->dSlot.p);
     }
     CK(cudaGetLastError());
     CKE(pbd_step(e, nSteps));
     if (x_out) {
-        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float *)e->stage.p, e->n, e->layout);
+        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float *)e->stage.p, e->n, (const unsigned *)e->dSlot.p);
         CK(cudaMemcpyAsync(x_out, e->stage.p, bytes, cudaMemcpyDeviceToHost, e->stream));
     }
     if (v_out) {
-        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->vel.p, (float *)stage2.p, e->n, e->layout);
+        k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->vel.p, (float *)stage2.p, e->n, (const unsigned *)e->dSlot.p);
         CK(cudaMemcpyAsync(v_out, stage2.p, bytes, cudaMemcpyDeviceToHost, e->stream));
     }
     CK(cudaGetLastError());
@@ -980,6 +1152,7 @@ extern "C" int pbd_get_stats(pbd_engine *e, pbd_stats *out) {
 
 extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegrate, float *msVelocity, unsigned *launchesPerType) {
     if (!e) return fail("null engine");
+    if (e->mode == PBD_MODE_TILED) return fail("pbd_profile_step: per-bucket launches do not exist in the tiled mode (select another mode first)");
     CKE(use(e)); CKE(flatten(e));
     CK(cudaStreamSynchronize(e->stream));
     // One event between every pair of consecutive launches, all recorded in stream order without host synchronisation

@@ -99,15 +99,25 @@ __device__ __forceinline__ void project_joint(float4 *pos, const TypeArrays &a, 
     if (X0.w != 0.0f) { __stcg(a.rbX + s.b.x, X0); __stcg(a.rbQ + s.b.x, Q0); }
 }
 
-template <int T, bool CA>
-__device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &a, unsigned i, const Streamed &s, float dt,
-                                                 bool iterZero) {
-    if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) { project_joint<T>(pos, a, s); return; }
+// Particle accessors: where a constraint's particle index points to.
+//   GlobalAcc : the float4 array in global memory (L2-resident), index = device slot
+//   tiled kernel (tiled.cuh): bit 31 set -> slot of the CTA's shared-memory tile, else global
+template <bool CA> struct GlobalAcc {
+    float4 *pos;
+    __device__ __forceinline__ float4 ld(unsigned idx) const { return ldp<CA>(pos + idx); }
+    __device__ __forceinline__ void st(unsigned idx, const float4 &v) const { stp(pos + idx, v); }
+    __device__ __forceinline__ float4 *global() const { return pos; }
+};
+
+template <int T, class Acc>
+__device__ __forceinline__ void project_streamed_acc(const Acc &acc, const TypeArrays &a, unsigned i, const Streamed &s, float dt,
+                                                     bool iterZero) {
+    if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) { project_joint<T>(acc.global(), a, s); return; }
     constexpr bool XPBD = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
     constexpr int NB = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 2 : ((T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) ? 3 : 4);
-    float4 p0 = ldp<CA>(pos + s.b.x), p1 = ldp<CA>(pos + s.b.y), p2, p3;
-    if (NB >= 3) p2 = ldp<CA>(pos + s.b.z);
-    if (NB >= 4) p3 = ldp<CA>(pos + s.b.w);
+    float4 p0 = acc.ld(s.b.x), p1 = acc.ld(s.b.y), p2, p3;
+    if (NB >= 3) p2 = acc.ld(s.b.z);
+    if (NB >= 4) p3 = acc.ld(s.b.w);
     float lam = 0.0f;
     if (XPBD && !iterZero) lam = __ldcg(a.lambda + i);  // m_lambda; zero at the first sweep of a substep (Constraints.cpp:1241-1242)
 
@@ -146,9 +156,14 @@ __device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &
     }
 
     if (XPBD) __stcg(a.lambda + i, lam);
-    stp(pos + s.b.x, p0); stp(pos + s.b.y, p1);
-    if (NB >= 3) stp(pos + s.b.z, p2);
-    if (NB >= 4) stp(pos + s.b.w, p3);
+    acc.st(s.b.x, p0); acc.st(s.b.y, p1);
+    if (NB >= 3) acc.st(s.b.z, p2);
+    if (NB >= 4) acc.st(s.b.w, p3);
+}
+
+template <int T, bool CA>
+__device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &a, unsigned i, const Streamed &s, float dt, bool iterZero) {
+    project_streamed_acc<T>(GlobalAcc<CA>{pos}, a, i, s, dt, iterZero);
 }
 
 constexpr int kProjectThreads = 256;
@@ -294,26 +309,31 @@ __global__ void __launch_bounds__(256) k_velocity(const float4 *__restrict__ pos
 }
 
 // host AoS-3 <-> device float4 conversion (std::vector<Vector3r> layout on the host side); particle i of the host lives
-// in device slot particle_slot(i, n, layout) (device_image.h)
-__global__ void k_pack3(const float *__restrict__ src, float4 *__restrict__ dst, unsigned n, int keepW, int layout) {
+// in device slot slot[i] (de-interleaved formula of device_image.h, or the tile-major permutation of the tiled mode)
+__global__ void k_relayout(const float4 *__restrict__ src, float4 *__restrict__ dst, unsigned n, const unsigned *__restrict__ oldSlot,
+                           const unsigned *__restrict__ newSlot) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[newSlot[i]] = src[oldSlot[i]];
+}
+__global__ void k_pack3(const float *__restrict__ src, float4 *__restrict__ dst, unsigned n, int keepW, const unsigned *__restrict__ slot) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned s = particle_slot(i, n, layout);
+    const unsigned s = slot[i];
     float4 d = keepW ? dst[s] : make_float4(0.f, 0.f, 0.f, 0.f);
     d.x = src[3 * i]; d.y = src[3 * i + 1]; d.z = src[3 * i + 2];
     dst[s] = d;
 }
-__global__ void k_unpack3(const float4 *__restrict__ src, float *__restrict__ dst, unsigned n, int layout) {
+__global__ void k_unpack3(const float4 *__restrict__ src, float *__restrict__ dst, unsigned n, const unsigned *__restrict__ slot) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 s = src[particle_slot(i, n, layout)];
+    const float4 s = src[slot[i]];
     dst[3 * i] = s.x; dst[3 * i + 1] = s.y; dst[3 * i + 2] = s.z;
 }
-__global__ void k_set_w(float4 *__restrict__ pos, float4 *__restrict__ vel, const float *__restrict__ mass, unsigned n, int layout) {
+__global__ void k_set_w(float4 *__restrict__ pos, float4 *__restrict__ vel, const float *__restrict__ mass, unsigned n, const unsigned *__restrict__ slot) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float m = mass[i];
-    const unsigned s = particle_slot(i, n, layout);
+    const unsigned s = slot[i];
     pos[s].w = (m != 0.0f) ? 1.0f / m : 0.0f;  // ParticleData::setMass (ParticleData.h:239-246)
     vel[s].w = m;
 }

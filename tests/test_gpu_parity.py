@@ -86,9 +86,43 @@ def test_scene_vs_reference_f64(name, cpu_libs):
 def test_modes_agree_bitwise(name, cpu_libs):
     """Plain launches, the replayed CUDA graph and the persistent cooperative kernel execute the same projections in the
     same dependency order, so their results must be bit-identical."""
-    xs = [_run(name, mode, cpu_libs, "oracle") for mode in (2, 0, 1)]
+    xs = [_run(name, mode, cpu_libs, "oracle") for mode in (2, 0, 1, 3)]
     assert (xs[0] == xs[1]).all()
     assert (xs[0] == xs[2]).all()
+    assert (xs[0] == xs[3]).all()  # tiled: particle tiles in shared memory, tile-major particle order
+
+
+def test_mode_switch_keeps_state_bitwise():
+    """Switching to the tiled mode permutes every particle array on the device (tile-major order) and back; the simulation
+    state must survive both moves bit for bit and the uploads/downloads in between must address the right particles."""
+    from positionbaseddynamics_b200 import _capi
+    from positionbaseddynamics_b200.model import HostModel
+    nx = 40
+    hm = HostModel()
+    hm.add_regular_triangle_model(nx, nx, (0, 0, 0), np.eye(3), (4.0, 4.0))
+    for i in (0, nx - 1):
+        hm.set_mass(i, 0.0)
+    hm.add_cloth_constraints(0, 4, 1e5)   # Distance_XPBD on the edges
+    hm.add_bending_constraints(0, 3, 50.0)  # IsometricBending_XPBD
+    types, bodies, params, nb = hm.constraints()
+    x = hm.get("x"); mass, _ = hm.masses()
+
+    def run(schedule):
+        eng = _capi.Engine(0)
+        eng.set_particles(x, mass)
+        eng.add_flat(types, bodies, params)
+        eng.color_first_fit()
+        eng.set_params(dt=0.005, sub_steps=2, max_iter=5)
+        for mode, steps in schedule:
+            eng.set_mode(mode); eng.step(steps); eng.sync()
+            v = eng.get_attr(_capi.ATTR_V); eng.set_attr(_capi.ATTR_V, v)  # round trip through the host in the current layout
+        out = eng.get_attr(_capi.ATTR_X), eng.get_attr(_capi.ATTR_V), eng.get_attr(_capi.ATTR_OLDX)
+        eng.close()
+        return out
+    a = run([(_capi.MODE_GRAPH, 6)])
+    b = run([(_capi.MODE_GRAPH, 2), (_capi.MODE_TILED, 2), (_capi.MODE_LAUNCH, 1), (_capi.MODE_TILED, 1)])
+    for u, w in zip(a, b):
+        assert np.isfinite(u).all() and (u == w).all()
 
 
 def test_known_answers_against_reference_golden():
@@ -277,6 +311,9 @@ def test_engine_level_drop_in_with_rigid_bodies(cpu_libs):
     assert rel_position_error(eng.get_attr(_capi.ATTR_X), cpu.get("x")) <= TOL
     assert np.abs(eng.get_rigid_bodies()[:, :7] - cpu.rigid_bodies()[:, :7]).max() <= 1e-4
     eng.set_mode(_capi.MODE_PERSISTENT)
+    with pytest.raises(_capi.PbdError):
+        eng.step(1)
+    eng.set_mode(_capi.MODE_TILED)
     with pytest.raises(_capi.PbdError):
         eng.step(1)
     eng.close()
