@@ -498,7 +498,7 @@ static bool factor_rank1(const float *Q, float Kp[4]) {
 
 template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v, cudaStream_t s) {
     if (v.empty()) return 0;
-    if (buf.alloc(v.size() * sizeof(T))) return 1;
+    if (buf.alloc(v.size() * sizeof(T) + 16)) return 1;  // +16: bulk copies of the tiled kernel round their size up to 16 bytes
     cudaError_t e = cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return fail("upload -> %s", cudaGetErrorString(e));
     e = cudaStreamSynchronize(s);  // the host vector dies with the caller's scope
@@ -621,16 +621,22 @@ static int flatten(pbd_engine *e) {
                     const unsigned *b = bod + (size_t)tmp[t][i] * nb;
                     unsigned mn = e->slot[b[0]];
                     for (int k = 1; k < nb; k++) mn = std::min(mn, e->slot[b[k]]);
-                    // tiled: the executing tile (tile of the first particle) is the major key
-                    keyed[i] = std::make_pair(((unsigned long long)(tiled ? tileOf[b[0]] : 0u) << 32) | mn, tmp[t][i]);
+                    // tiled: major key = executing tile (tile of the first particle), then "all particles in shared memory?"
+                    unsigned long long major = 0;
+                    if (tiled) {
+                        bool pure = true;
+                        for (int k = 0; k < nb; k++) pure &= (inSmem[b[k]] != 0);
+                        major = 2ull * tileOf[b[0]] + (pure ? 1u : 0u);
+                    }
+                    keyed[i] = std::make_pair((major << 32) | mn, tmp[t][i]);
                 }
                 std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; });
                 for (size_t i = 0; i < keyed.size(); i++) tmp[t][i] = keyed[i].second;
-                if (tiled) {  // range of every tile inside this bucket
+                if (tiled) {  // runs of every tile inside this bucket: [2 tile] spanning, [2 tile + 1] private
                     const size_t base = tileOff.size();
-                    tileOff.resize(base + e->nTiles + 1, 0u);
+                    tileOff.resize(base + 2 * e->nTiles + 1, 0u);
                     for (size_t i = 0; i < keyed.size(); i++) tileOff[base + (keyed[i].first >> 32) + 1]++;
-                    for (unsigned k = 0; k < e->nTiles; k++) tileOff[base + k + 1] += tileOff[base + k];
+                    for (unsigned k = 0; k < 2 * e->nTiles; k++) tileOff[base + k + 1] += tileOff[base + k];
                 }
             }
             Bucket b; b.type = t; b.first = (unsigned)order[t].size(); b.count = (unsigned)tmp[t].size(); b.colour = g;
@@ -1027,6 +1033,30 @@ static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long 
     unsigned present = 0;
     for (int t = 0; t < PBD_NUM_TYPES; t++) { ta.types[t] = e->dev[t].arrays; if (e->dev[t].count) present |= 1u << t; }
     *launches = 1;
+    static const char *noStage = getenv("PBD_B200_NOSTAGE");  // A/B knob: constraint stream straight from global memory
+    ta.stage = noStage ? 0 : 1;
+    static const char *serialAB = getenv("PBD_B200_SERIAL_AB");
+    ta.serialAB = serialAB ? 1 : 0;
+    static const char *fenceMode = getenv("PBD_B200_FENCE");
+    ta.fenceMode = fenceMode ? atoi(fenceMode) : 0;
+    ta.trace = nullptr; ta.tracePhases = 0;
+    static const char *tracePath = getenv("PBD_B200_TRACE");  // development aid: dump per-phase timelines of one step
+    const unsigned kTracePhases = 128;
+    if (tracePath) {
+        CKE(e->dTrace.alloc((size_t)kTracePhases * e->nTiles * 4 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(e->dTrace.p, 0, e->dTrace.bytes, s));
+        ta.trace = (unsigned long long *)e->dTrace.p; ta.tracePhases = kTracePhases;
+    }
+    struct TraceDump {  // runs after the launch below has been enqueued (scope exit)
+        pbd_engine *e; cudaStream_t s; const char *path; unsigned phases;
+        ~TraceDump() {
+            if (!path) return;
+            cudaStreamSynchronize(s);
+            std::vector<unsigned long long> h((size_t)phases * e->nTiles * 4);
+            cudaMemcpy(h.data(), e->dTrace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+        }
+    } dump{e, s, tracePath, kTracePhases};
     const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
     if ((present & ~kMaskClothXPBD) == 0) {
         if (pt == 512) return launch_tiled<kMaskClothXPBD, 512>(e, s, ta);
