@@ -244,7 +244,7 @@ def run_b200(args):
     # pick the execution mode on a short probe unless forced
     if args.mode == "auto":
         probe = {}
-        for name in (("graph",) if len(rb) else ("graph", "persistent", "tiled")):
+        for name in (("graph",) if len(rb) else ("graph", "persistent")):  # the tiled mode is opt-in (--mode tiled): its flatten re-partitions the model
             try:
                 ms, _ = timed(modes[name], 3, 2)
                 probe[name] = ms

@@ -105,6 +105,7 @@ struct pbd_engine {
     std::vector<unsigned> slot;           // host particle index -> device slot (formula layouts or the tile-major permutation)
     DevBuf dSlot, dSlotOld, relayoutTmp, dTileOff, dTileStart, dTilePrivate;
     bool slotIsTiled = false;
+    bool tileSwizzle = true;              // PBD_B200_SWIZZLE=0 disables the bank swizzle of the shared-memory tiles
     unsigned nTiles = 0;
     int layout = 1;                       // particle placement (device_image.h particle_slot); PBD_B200_LAYOUT=linear selects 0
     bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
@@ -149,6 +150,7 @@ extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
     if (const char *g = getenv("PBD_B200_PDL")) e->usePDL = (strcmp(g, "0") != 0);
     if (const char *g = getenv("PBD_B200_PTHREADS")) e->persistentThreads = atoi(g);
     if (const char *g = getenv("PBD_B200_MERGE")) e->mergeColours = (strcmp(g, "0") != 0);
+    if (const char *g = getenv("PBD_B200_SWIZZLE")) e->tileSwizzle = (strcmp(g, "0") != 0);
     if (const char *g = getenv("PBD_B200_LAYOUT")) e->layout = (strcmp(g, "linear") == 0) ? 0 : 1;
     *out = e;
     return 0;
@@ -686,7 +688,10 @@ static int flatten(pbd_engine *e) {
             const unsigned raw = h.bodies[(size_t)order[t][i] * s.nBodies + k];
             const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && k == 0);
             if (isRb) return raw;
-            if (tiled && inSmem[raw]) return kSmemFlag | (e->slot[raw] - tileStart[tileOf[raw]]);  // lives in the executing CTA's shared memory
+            if (tiled && inSmem[raw]) {  // lives in the executing CTA's shared memory
+                const unsigned local = e->slot[raw] - tileStart[tileOf[raw]];
+                return kSmemFlag | (e->tileSwizzle ? tile_swizzle(local) : local);
+            }
             return e->slot[raw];
         };
 
@@ -1035,11 +1040,16 @@ static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long 
     *launches = 1;
     static const char *noStage = getenv("PBD_B200_NOSTAGE");  // A/B knob: constraint stream straight from global memory
     ta.stage = noStage ? 0 : 1;
+    ta.swizzle = e->tileSwizzle ? 1 : 0;
+    static const char *noLambda = getenv("PBD_B200_NOSTAGE_LAMBDA");
+    ta.stageLambda = (!noLambda && ta.stage && e->coloursUsed >= 2) ? 1 : 0;
     static const char *serialAB = getenv("PBD_B200_SERIAL_AB");
     ta.serialAB = serialAB ? 1 : 0;
     static const char *fenceMode = getenv("PBD_B200_FENCE");
     ta.fenceMode = fenceMode ? atoi(fenceMode) : 0;
     ta.trace = nullptr; ta.tracePhases = 0;
+    static const char *traceWorker = getenv("PBD_B200_TRACE_WORKER");
+    ta.traceWorker = traceWorker ? atoi(traceWorker) : -1;
     static const char *tracePath = getenv("PBD_B200_TRACE");  // development aid: dump per-phase timelines of one step
     const unsigned kTracePhases = 128;
     if (tracePath) {
@@ -1059,8 +1069,10 @@ static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long 
     } dump{e, s, tracePath, kTracePhases};
     const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
     if ((present & ~kMaskClothXPBD) == 0) {
+        if (pt == 1024) return launch_tiled<kMaskClothXPBD, 1024>(e, s, ta);
+        if (pt == 768) return launch_tiled<kMaskClothXPBD, 768>(e, s, ta);
         if (pt == 512) return launch_tiled<kMaskClothXPBD, 512>(e, s, ta);
-        return launch_tiled<kMaskClothXPBD, 1024>(e, s, ta);
+        return launch_tiled<kMaskClothXPBD, 640>(e, s, ta);  // measured best on cfg2 (profiles/README.md section 6)
     }
     if ((present & ~kMaskLight) == 0) return launch_tiled<kMaskLight, 512>(e, s, ta);
     return launch_tiled<kMaskAll, 512>(e, s, ta);

@@ -111,7 +111,7 @@ template <bool CA> struct GlobalAcc {
 
 template <int T, class Acc>
 __device__ __forceinline__ void project_streamed_acc(const Acc &acc, const TypeArrays &a, unsigned i, const Streamed &s, float dt,
-                                                     bool iterZero) {
+                                                     bool iterZero, const float *stagedLambda = nullptr) {
     if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) { project_joint<T>(acc.global(), a, s); return; }
     constexpr bool XPBD = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
     constexpr int NB = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 2 : ((T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) ? 3 : 4);
@@ -119,7 +119,7 @@ __device__ __forceinline__ void project_streamed_acc(const Acc &acc, const TypeA
     if (NB >= 3) p2 = acc.ld(s.b.z);
     if (NB >= 4) p3 = acc.ld(s.b.w);
     float lam = 0.0f;
-    if (XPBD && !iterZero) lam = __ldcg(a.lambda + i);  // m_lambda; zero at the first sweep of a substep (Constraints.cpp:1241-1242)
+    if (XPBD && !iterZero) lam = stagedLambda ? *stagedLambda : __ldcg(a.lambda + i);  // m_lambda; zero at the first sweep of a substep (Constraints.cpp:1241-1242)
 
     if (T == PBD_DISTANCE) {
         project_distance(p0, p1, s.s0, matv(a, 0, i));
@@ -166,7 +166,10 @@ __device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &
     project_streamed_acc<T>(GlobalAcc<CA>{pos}, a, i, s, dt, iterZero);
 }
 
-constexpr int kProjectThreads = 256;
+#ifndef PBD_PROJECT_THREADS
+#define PBD_PROJECT_THREADS 256
+#endif
+constexpr int kProjectThreads = PBD_PROJECT_THREADS;
 
 template <int T, bool CA>
 __global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeArrays a, unsigned first,

@@ -35,7 +35,10 @@ constexpr unsigned kSmemFlag = 0x80000000u;
 constexpr int kTileCapacity = 8192;                 // private particles per tile kept in shared memory (128 KB)
 constexpr unsigned kStageBytes = 48u * 1024u;       // one stage buffer (two of them)
 constexpr size_t kTiledSmemBytes = (size_t)kTileCapacity * sizeof(float4) + 2u * kStageBytes + 64u;
-constexpr int kStreamArrays = 7;                    // idx a/b/c, gv0, gv1, gs0, gs1
+// bank swizzle of the tile: slot s lives at sp[s ^ ((s >> 3) & 7)] (a permutation inside every aligned 64-slot block), so that
+// the stride-2 / stride-4 slot patterns of one colour's constraints spread over all eight 16-byte bank groups
+__host__ __device__ __forceinline__ unsigned tile_swizzle(unsigned s) { return s ^ ((s >> 3) & 7u); }
+constexpr int kStreamArrays = 8;                    // idx a/b/c, gv0, gv1, gs0, gs1, lambda (XPBD multipliers)
 
 struct TiledArgs {
     float4 *pos, *vel, *oldp, *lastp;
@@ -50,6 +53,9 @@ struct TiledArgs {
     unsigned long long barrierBase;
     unsigned long long *trace;   // development aid (PBD_B200_TRACE): 4 timestamps per (colour phase, CTA)
     unsigned tracePhases;
+    int traceWorker;             // -1: the manager records (collect, arrive, release, colour end); w >= 0: worker warp w records (start, operands there, spanning done, private done)
+    int swizzle;                 // tile slots are bank-swizzled (tile_swizzle); must match the index encoding done at flatten time
+    int stageLambda;             // XPBD multipliers travel with the staged operands (needs >= 2 colours: the copy for phase p + 1 starts during phase p)
     int stage;                   // 0: workers read the constraint stream straight from global memory (A/B knob)
     int fenceMode;               // development knob: 0 manager fence (default), 1 fence by the worker threads that ran spanning constraints, 2 none (timing only)
     int serialAB;                // 1: the private constraints start only when the CTA's spanning constraints are done (A/B knob)
@@ -85,8 +91,9 @@ template <int T> __host__ __device__ constexpr unsigned stream_es(int r) {
     constexpr bool g1 = (T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET);
     constexpr bool s0 = two || T == PBD_FEMTRIANGLE || T == PBD_DIHEDRAL || T == PBD_VOLUME || T == PBD_VOLUME_XPBD || g1;
     constexpr bool s1 = (T == PBD_FEMTET || T == PBD_FEMTET_XPBD);
+    constexpr bool xpbd = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
     return r == 0 ? (two ? 8u : (tri ? 4u : 16u)) : (r == 1 || r == 2) ? (tri ? 4u : 0u) : r == 3 ? (g0 ? 16u : 0u) : r == 4 ? (g1 ? 16u : 0u)
-         : r == 5 ? (s0 ? 4u : 0u) : (s1 ? 4u : 0u);
+         : r == 5 ? (s0 ? 4u : 0u) : r == 6 ? (s1 ? 4u : 0u) : (xpbd ? 4u : 0u);
 }
 template <int T, int R> __device__ __forceinline__ const unsigned char *stream_ptr(const TypeArrays &ta) {
     constexpr bool two = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD), tri = (T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE);
@@ -97,20 +104,21 @@ template <int T, int R> __device__ __forceinline__ const unsigned char *stream_p
     else if (R == 3) p = ta.gv[0];
     else if (R == 4) p = ta.gv[1];
     else if (R == 5) p = ta.gs[0];
-    else p = ta.gs[1];
+    else if (R == 6) p = ta.gs[1];
+    else p = ta.lambda;
     return static_cast<const unsigned char *>(p);
 }
 
 // Where the run [g0, g0 + n) of a type lands in the stage buffer.  Every array of the run is copied from its 16-byte
 // aligned start (head = misalignment of element g0) with a size rounded up to 16; `staged` items fit, the rest of the run is
 // read from global memory.  Deterministic in its arguments: the manager (who copies) and the workers (who read) agree.
-struct RunPlan { unsigned o0, o1, o2, o3, o4, o5, o6; unsigned staged; };
+struct RunPlan { unsigned o0, o1, o2, o3, o4, o5, o6, o7; unsigned staged; };
 template <int R> __device__ __forceinline__ unsigned &plan_off(RunPlan &pl) {
     if (R == 0) return pl.o0; if (R == 1) return pl.o1; if (R == 2) return pl.o2; if (R == 3) return pl.o3;
-    if (R == 4) return pl.o4; if (R == 5) return pl.o5; return pl.o6;
+    if (R == 4) return pl.o4; if (R == 5) return pl.o5; if (R == 6) return pl.o6; return pl.o7;
 }
 template <int T> __host__ __device__ constexpr unsigned stream_item_bytes() {
-    return stream_es<T>(0) + stream_es<T>(1) + stream_es<T>(2) + stream_es<T>(3) + stream_es<T>(4) + stream_es<T>(5) + stream_es<T>(6);
+    return stream_es<T>(0) + stream_es<T>(1) + stream_es<T>(2) + stream_es<T>(3) + stream_es<T>(4) + stream_es<T>(5) + stream_es<T>(6) + stream_es<T>(7);
 }
 template <int T> __host__ __device__ constexpr unsigned stream_slack() {
     unsigned s = 0;
@@ -133,7 +141,7 @@ __device__ __forceinline__ void plan_run(unsigned g0, unsigned n, unsigned &runn
     if ((unsigned long long)n * perItem + slack > avail) m = (avail > slack) ? (avail - slack) / perItem : 0u;
     pl.staged = m;
     plan_one<T, 0>(g0, m, running, pl); plan_one<T, 1>(g0, m, running, pl); plan_one<T, 2>(g0, m, running, pl); plan_one<T, 3>(g0, m, running, pl);
-    plan_one<T, 4>(g0, m, running, pl); plan_one<T, 5>(g0, m, running, pl); plan_one<T, 6>(g0, m, running, pl);
+    plan_one<T, 4>(g0, m, running, pl); plan_one<T, 5>(g0, m, running, pl); plan_one<T, 6>(g0, m, running, pl); plan_one<T, 7>(g0, m, running, pl);
 }
 // manager lane R copies stream slot R of the run
 template <int T, int R>
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                 plan_run<T>(g0, c2 - c0, running, pl);
                 issue_one<T, 0>(ta, g0, pl, lane, dst0, bar); issue_one<T, 1>(ta, g0, pl, lane, dst0, bar); issue_one<T, 2>(ta, g0, pl, lane, dst0, bar);
                 issue_one<T, 3>(ta, g0, pl, lane, dst0, bar); issue_one<T, 4>(ta, g0, pl, lane, dst0, bar); issue_one<T, 5>(ta, g0, pl, lane, dst0, bar);
-                issue_one<T, 6>(ta, g0, pl, lane, dst0, bar);)
+                issue_one<T, 6>(ta, g0, pl, lane, dst0, bar); issue_one<T, 7>(ta, g0, pl, lane, dst0, bar);)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                 x.x = fmaf(v.x, a.h, x.x); x.y = fmaf(v.y, a.h, x.y); x.z = fmaf(v.z, a.h, x.z);
                 __stcs(a.vel + i, v);
             }
-            if (i - p0 < nPriv) sp[i - p0] = x;       // private: lives in shared memory for the whole substep
+            if (i - p0 < nPriv) sp[a.swizzle ? tile_swizzle(i - p0) : i - p0] = x;  // private: lives in shared memory for the whole substep
             else if (v.w != 0.0f) __stcg(a.pos + i, x);  // shared: other CTAs read it through L2
         }
         grid_barrier(a.barrier, target);  // shared particles integrated everywhere (also orders the smem tile inside the CTA)
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                 const bool lastPhase = (be == a.nBuckets) && (it + 1 == a.maxIter) && (sub + 1 == a.subSteps);
                 target += nTiles;
                 if (manager) {
-                    const bool tr = a.trace && phase < a.tracePhases && lane == 0;
+                    const bool tr = a.trace && a.traceWorker < 0 && phase < a.tracePhases && lane == 0;
                     unsigned long long *rec = a.trace + ((size_t)phase * nTiles + tile) * 4;
                     cta_collect<THREADS>();                      // every worker's spanning constraints are done
                     if (tr) rec[0] = globaltimer_ns();
@@ -258,7 +266,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                     __syncwarp();
                     // while the arrival travels: start streaming the next colour (its buffer was released by the sync that ended
                     // phase - 1).  Issued after the fence on purpose: the fence would wait for the copies.
-                    if (a.stage && !lastPhase) issue_phase(be < a.nBuckets ? be : 0u, phase + 1u);
+                    if (a.stage && !lastPhase) {
+                        // the multipliers of the next colour were written with generic stores (by the sync that ended phase - 1 at the
+                        // latest); the bulk copy reads them through the async proxy
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        issue_phase(be < a.nBuckets ? be : 0u, phase + 1u);
+                    }
                     if (lane == 0) {
                         while (ld_acquire_u64(a.barrier) < target) { }
                         if (tr) rec[2] = globaltimer_ns();
@@ -268,7 +281,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                     if (tr) rec[3] = globaltimer_ns();
                 } else {
                     const unsigned char *stage = stageBuf + (size_t)(phase & 1u) * kStageBytes;
+                    const bool tr = a.trace && a.traceWorker >= 0 && phase < a.tracePhases && t == 32u * (unsigned)a.traceWorker;
+                    unsigned long long *rec = a.trace + ((size_t)phase * nTiles + tile) * 4;
+                    if (tr) rec[0] = globaltimer_ns();
                     if (a.stage) mbar_wait(barAddr + 8u * (phase & 1u), (phase >> 1) & 1u);
+                    if (tr) rec[1] = globaltimer_ns();
                     unsigned rot = 0;  // items of this colour handed out so far (mod W): the next run starts at that thread
                     bool ranSpanning = false;
 #pragma unroll 1
@@ -287,12 +304,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                                 RunPlan pl;
                                 if (a.stage) plan_run<T>(g0, c2 - c0, running, pl); else pl.staged = 0;
                                 for (unsigned j = j0 + ((t + W - rot) % W); j < j1; j += W) {
-                                    const Streamed s = (j < pl.staged) ? load_streamed_stage<T>(stage, pl, j) : load_streamed<T>(ta, g0 + j);
-                                    project_streamed_acc<T>(acc, ta, g0 + j, s, a.h, iterZero);
+                                    const bool st = (j < pl.staged);
+                                    const Streamed s = st ? load_streamed_stage<T>(stage, pl, j) : load_streamed<T>(ta, g0 + j);
+                                    const float *lam = (st && a.stageLambda && stream_es<T>(7)) ? reinterpret_cast<const float *>(stage + pl.o7 + 4u * j) : nullptr;
+                                    project_streamed_acc<T>(acc, ta, g0 + j, s, a.h, iterZero, lam);
                                     if (part == 0) ranSpanning = true;
                                 })
                             rot = (rot + (j1 - j0)) % W;
                         }
+                        if (tr) rec[2 + part] = globaltimer_ns();
                         if (part == 0) { if (a.fenceMode == 1 && ranSpanning) asm volatile("fence.acq_rel.gpu;" ::: "memory"); cta_arrive<THREADS>(); if (a.serialAB) asm volatile("bar.sync 2, %0;" :: "n"(THREADS - 32) : "memory"); }
                     }
                     __syncthreads();                             // end of the colour: released by the manager after the grid barrier
@@ -306,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
         // ---- epilogue on the tile's own particles: write the private ones back, velocity update ----------------------------------
         for (unsigned i = p0 + t; i < p1; i += THREADS) {
             float4 x;
-            if (i - p0 < nPriv) { x = sp[i - p0]; if (x.w != 0.0f) __stcg(a.pos + i, x); }
+            if (i - p0 < nPriv) { x = sp[a.swizzle ? tile_swizzle(i - p0) : i - p0]; if (x.w != 0.0f) __stcg(a.pos + i, x); }
             else x = __ldcg(a.pos + i);
             if (x.w == 0.0f) continue;
             const float4 o = __ldcg(a.oldp + i);

@@ -86,13 +86,26 @@ def test_translation_invariance_large_cloth():
 
 
 def test_modes_and_layouts_agree_at_scale():
-    """Graph, persistent and plain-launch execution of a 300x300 XPBD cloth (540k constraints): bit-identical."""
+    """Graph, persistent, plain-launch and tiled execution of a 300x300 XPBD cloth (540k constraints): bit-identical."""
     out = []
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         gpu = _gpu(lambda m: scenes.cfg2(m, 300, 8), mode)
         gpu.step(3)
         out.append(gpu.get("x").copy()); gpu.close()
-    assert (out[0] == out[1]).all() and (out[0] == out[2]).all()
+    assert (out[0] == out[1]).all() and (out[0] == out[2]).all() and (out[0] == out[3]).all()
+
+
+def test_tiled_mode_full_size_cfg2_bitwise():
+    """cfg2 at full size in the tiled mode: 6,757 particles per tile, the largest colours exceed the 48 KB operand stage (the
+    overflow constraints are read from global memory) and every tile has spanning and private runs.  Must reproduce the graph
+    mode bit for bit, positions and velocities."""
+    res = []
+    for mode in (0, 3):
+        gpu = _gpu(lambda m: scenes.cfg2(m, 1000, 20), mode)
+        gpu.step(2)
+        res.append((gpu.get("x").copy(), gpu.get("v").copy())); gpu.close()
+    assert np.isfinite(res[0][0]).all()
+    assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
 
 
 def test_free_fall_of_an_unpinned_sheet_is_rigid():

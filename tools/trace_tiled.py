@@ -18,3 +18,14 @@ for name, x in (("A collected", A), ("fence+atomic", at), ("spin", W), ("B tail"
     print("%-16s per CTA: median %.2f us, mean %.2f, p95 %.2f, max-over-CTAs median %.2f" % (name, np.median(x) / 1e3, x.mean() / 1e3, np.percentile(x, 95) / 1e3, np.median(x.max(axis=1)) / 1e3))
 for p in range(1, min(len(d), 8)):
     print("phase %3d: len %.2f  A(max) %.2f  spin(min) %.2f  Btail(max) %.2f" % (p, (d[p, :, 3].max() - d[p - 1, :, 3].max()) / 1e3, A[p - 1].max() / 1e3, W[p - 1].min() / 1e3, B[p - 1].max() / 1e3))
+
+if len(sys.argv) > 3:  # worker trace: [0] phase start, [1] operands there, [2] spanning done, [3] private done
+    w0 = d[:, :, 1] - d[:, :, 0]; w1 = d[:, :, 2] - d[:, :, 1]; w2 = d[:, :, 3] - d[:, :, 2]
+    gap = d[1:, :, 0] - d[:-1, :, 3]
+    for name, x in (("wait operands", w0), ("spanning part", w1), ("private part", w2), ("colour end -> next start", gap)):
+        print("worker %-24s median %.2f us, mean %.2f, p95 %.2f" % (name, np.median(x) / 1e3, x.mean() / 1e3, np.percentile(x, 95) / 1e3))
+if len(sys.argv) > 3:
+    start = d[:, :, 0]
+    for p in (5, 12, 25, 26):
+        if p + 1 < len(d):
+            print("phase %d: start skew %.2f us, phase len %.2f us" % (p, (start[p].max() - start[p].min()) / 1e3, (np.median(start[p + 1]) - np.median(start[p])) / 1e3))
