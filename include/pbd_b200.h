@@ -104,6 +104,9 @@ int pbd_num_params(int type);
  * insertion index) or recompute them with the reference's greedy first-fit (SimulationModel.cpp:1033-1094). */
 int pbd_set_groups(pbd_engine *e, unsigned nGroups, const unsigned *offsets, const unsigned *ids);
 int pbd_color_first_fit(pbd_engine *e);
+/* The same colouring computed on the GPU (exact: wavefronts over the insertion-order dependency DAG, csrc/colouring.cuh);
+ * identical groups.  ms / wavefronts (may be NULL): device time of the colouring and number of wavefronts. */
+int pbd_color_first_fit_device(pbd_engine *e, float *ms, unsigned *wavefronts);
 int pbd_get_num_groups(pbd_engine *e, unsigned *nGroups);
 int pbd_get_groups(pbd_engine *e, unsigned *offsets, unsigned *ids);
 

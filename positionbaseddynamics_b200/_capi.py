@@ -22,7 +22,7 @@ MODE_GRAPH, MODE_PERSISTENT, MODE_LAUNCH, MODE_TILED = 0, 1, 2, 3
 # every symbol include/pbd_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "pbd_set_particles", "pbd_set_attr",
            "pbd_get_attr", "pbd_set_masses", "pbd_set_rigid_bodies", "pbd_get_rigid_bodies", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
-           "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_get_num_groups", "pbd_get_groups",
+           "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_color_first_fit_device", "pbd_get_num_groups", "pbd_get_groups",
            "pbd_set_params", "pbd_set_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host",
            "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step"]
 
@@ -57,6 +57,7 @@ def lib():
                 fn.restype = C.c_int
         for name in ("pbd_destroy", "pbd_clear_constraints", "pbd_color_first_fit", "pbd_sync"):
             getattr(_lib, name).argtypes = [C.c_void_p]
+        _lib.pbd_color_first_fit_device.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint)]
         _lib.pbd_set_particles.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.pbd_set_attr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.pbd_get_attr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -112,6 +113,7 @@ class Engine:
         self._h = C.c_void_p()
         _ck(lib().pbd_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.n = 0
+        self._nc = 0  # constraints added so far (sizes the buffer of groups())
 
     def close(self):
         if self._h:
@@ -166,6 +168,7 @@ class Engine:
     # constraints -----------------------------------------------------------------------------------
     def clear_constraints(self):
         _ck(lib().pbd_clear_constraints(self._h))
+        self._nc = 0
 
     def add_constraints(self, ctype, bodies, params, ids=None):
         nb, npar = num_bodies(ctype), num_params(ctype)
@@ -174,6 +177,7 @@ class Engine:
         assert len(bodies) == len(params)
         ids = np.ascontiguousarray(ids, dtype=np.uint32) if ids is not None else None
         _ck(lib().pbd_add_constraints(self._h, ctype, len(bodies), _ptr(bodies), _ptr(params), _ptr(ids)))
+        self._nc += len(bodies)
 
     def add_flat(self, types, bodies, params):
         """Insert a whole flat constraint list (types[n], bodies[n,4], params[n,24]) keeping insertion ids."""
@@ -191,18 +195,19 @@ class Engine:
     def color_first_fit(self):
         _ck(lib().pbd_color_first_fit(self._h))
 
+    def color_first_fit_device(self):
+        """Exact first-fit colouring on the GPU; returns (device ms, wavefronts)."""
+        ms = C.c_float(0.0); wf = C.c_uint(0)
+        _ck(lib().pbd_color_first_fit_device(self._h, C.byref(ms), C.byref(wf)))
+        return ms.value, wf.value
+
     def groups(self):
         ng = C.c_uint(0)
         _ck(lib().pbd_get_num_groups(self._h, C.byref(ng)))
-        st = self.stats(flatten=False) if False else None
         off = np.zeros(ng.value + 1, dtype=np.uint32)
-        # number of constraints = last offset; fetch in two passes
-        ids = np.zeros(max(self._num_constraints_hint(), 1), dtype=np.uint32)
+        ids = np.zeros(max(self._nc, 1), dtype=np.uint32)  # the groups partition all constraints added so far
         _ck(lib().pbd_get_groups(self._h, _ptr(off), _ptr(ids)))
         return off, ids[:off[-1]]
-
-    def _num_constraints_hint(self):
-        return getattr(self, "_nc", 0)
 
     # parameters / stepping -------------------------------------------------------------------------
     def set_params(self, dt=0.005, sub_steps=5, max_iter=1, vel_method=0, gravity=(0.0, -9.81, 0.0)):

@@ -17,6 +17,8 @@
 #include "kernels.cuh"
 #include "persistent.cuh"
 #include "tiled.cuh"
+#include "colouring.cuh"
+#include <cub/cub.cuh>
 #include "host/pbd_model.h"
 
 using namespace pbdk;
@@ -344,6 +346,16 @@ extern "C" int pbd_get_rigid_bodies(pbd_engine *e, float *x, float *q, float *v,
     return 0;
 }
 
+template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v, cudaStream_t s) {
+    if (v.empty()) return 0;
+    if (buf.alloc(v.size() * sizeof(T) + 16)) return 1;  // +16: bulk copies of the tiled kernel round their size up to 16 bytes
+    cudaError_t e = cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return fail("upload -> %s", cudaGetErrorString(e));
+    e = cudaStreamSynchronize(s);  // the host vector dies with the caller's scope
+    if (e != cudaSuccess) return fail("upload sync -> %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // constraints and groups
 // ------------------------------------------------------------------------------------------------------------
@@ -410,15 +422,13 @@ extern "C" int pbd_set_groups(pbd_engine *e, unsigned nGroups, const unsigned *o
     return 0;
 }
 
-// Greedy first fit in insertion order == SimulationModel::initConstraintGroups (Simulation/SimulationModel.cpp:1033-1094);
-// the colouring itself is host/pbd_model.cpp:firstFitColouring (shared with the host model mirror).
-extern "C" int pbd_color_first_fit(pbd_engine *e) {
-    if (!e) return fail("null engine");
+// insertion-ordered CSR of the constraint bodies (the colouring's input)
+static int build_id_csr(pbd_engine *e, std::vector<unsigned> &off, std::vector<unsigned> &bodies) {
     std::vector<std::pair<int, unsigned>> map;
     CKE(build_id_map(e, map));
     const unsigned N = e->numConstraints;
-    std::vector<unsigned> off(N + 1, 0), bodies;
-    bodies.reserve((size_t)N * 4);
+    off.assign(N + 1, 0u);
+    bodies.clear(); bodies.reserve((size_t)N * 4);
     for (unsigned id = 0; id < N; id++) {
         const int t = map[id].first;
         const int nb = type_shape(t).nBodies;
@@ -426,9 +436,11 @@ extern "C" int pbd_color_first_fit(pbd_engine *e) {
         bodies.insert(bodies.end(), b, b + nb);
         off[id + 1] = (unsigned)bodies.size();
     }
-    std::vector<unsigned> colour;
-    // rigid-body and particle indices share one index space without offset (SimulationModel.cpp:1041,1058,1070)
-    const unsigned nColours = pbd_b200::firstFitColouring(e->n + e->nRb, N, off.data(), bodies.data(), colour);
+    return 0;
+}
+// colour per constraint -> groups in insertion order (what SimulationModel::getConstraintGroups holds)
+static void groups_from_colours(pbd_engine *e, const std::vector<unsigned> &colour, unsigned nColours) {
+    const unsigned N = e->numConstraints;
     std::vector<unsigned> goff(nColours + 1, 0);
     for (unsigned id = 0; id < N; id++) goff[colour[id] + 1]++;
     for (unsigned c = 0; c < nColours; c++) goff[c + 1] += goff[c];
@@ -436,6 +448,79 @@ extern "C" int pbd_color_first_fit(pbd_engine *e) {
     for (unsigned id = 0; id < N; id++) ids[cur[colour[id]]++] = id;
     e->groupOff = goff; e->groupIds = ids;
     e->groupsSet = true; e->imageDirty = true;
+}
+
+// Greedy first fit in insertion order == SimulationModel::initConstraintGroups (Simulation/SimulationModel.cpp:1033-1094);
+// the colouring itself is host/pbd_model.cpp:firstFitColouring (shared with the host model mirror).
+extern "C" int pbd_color_first_fit(pbd_engine *e) {
+    if (!e) return fail("null engine");
+    std::vector<unsigned> off, bodies, colour;
+    CKE(build_id_csr(e, off, bodies));
+    // rigid-body and particle indices share one index space without offset (SimulationModel.cpp:1041,1058,1070)
+    const unsigned nColours = pbd_b200::firstFitColouring(e->n + e->nRb, e->numConstraints, off.data(), bodies.data(), colour);
+    groups_from_colours(e, colour, nColours);
+    return 0;
+}
+
+// The same colouring computed on the device (colouring.cuh): identical groups, SURVEY.md section 8 f-3.
+extern "C" int pbd_color_first_fit_device(pbd_engine *e, float *ms, unsigned *wavefronts) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    const unsigned N = e->numConstraints, V = e->n + e->nRb;
+    if (ms) *ms = 0.0f;
+    if (wavefronts) *wavefronts = 0;
+    if (N == 0) { e->groupOff.assign(1, 0u); e->groupIds.clear(); e->groupsSet = true; e->imageDirty = true; return 0; }
+    std::vector<unsigned> off, bodies;
+    CKE(build_id_csr(e, off, bodies));
+    const unsigned M = (unsigned)bodies.size();
+    cudaStream_t s = e->stream;
+    DevBuf dOff, dBody, dBody4, dNext4, dKeys, dVals, dKeysS, dValsS, dIndeg, dUsed, dColour, dA, dB, dCnt, dTmp;
+    struct Release { std::vector<DevBuf *> b; ~Release() { for (auto *x : b) x->release(); } } rel{{&dOff, &dBody, &dBody4, &dNext4, &dKeys, &dVals, &dKeysS, &dValsS, &dIndeg, &dUsed, &dColour, &dA, &dB, &dCnt, &dTmp}};
+    CKE(upload_vec(dOff, off, s)); CKE(upload_vec(dBody, bodies, s));
+    for (DevBuf *b : {&dKeys, &dVals, &dKeysS, &dValsS}) CKE(b->alloc((size_t)M * sizeof(unsigned)));
+    for (DevBuf *b : {&dBody4, &dNext4}) CKE(b->alloc((size_t)N * sizeof(uint4)));
+    for (DevBuf *b : {&dIndeg, &dColour, &dA, &dB}) CKE(b->alloc((size_t)N * sizeof(unsigned)));
+    CKE(dCnt.alloc(4 * sizeof(unsigned)));
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, s));
+    // incidence lists: stable sort of (body, incidence) by body, then successor / in-degree of every constraint
+    k_colour_expand<<<nblk(N, 256), 256, 0, s>>>((const unsigned *)dOff.p, (const unsigned *)dBody.p, (uint4 *)dBody4.p, (unsigned *)dKeys.p, (unsigned *)dVals.p, N);
+    int endBit = 1; while (endBit < 32 && (1ull << endBit) < (unsigned long long)V) endBit++;
+    size_t tmpBytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const unsigned *)dKeys.p, (unsigned *)dKeysS.p, (const unsigned *)dVals.p, (unsigned *)dValsS.p, (int)M, 0, endBit, s));
+    CKE(dTmp.alloc(tmpBytes));
+    CK(cub::DeviceRadixSort::SortPairs(dTmp.p, tmpBytes, (const unsigned *)dKeys.p, (unsigned *)dKeysS.p, (const unsigned *)dVals.p, (unsigned *)dValsS.p, (int)M, 0, endBit, s));
+    CK(cudaMemsetAsync(dNext4.p, 0xff, (size_t)N * sizeof(uint4), s));
+    std::vector<unsigned> colour(N);
+    unsigned cnt[4] = {0, 0, 0, 0};
+    for (unsigned words = 2;; words *= 2) {  // 128 colours to begin with; doubled when a constraint finds none free
+        CKE(dUsed.alloc((size_t)V * words * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(dUsed.p, 0, (size_t)V * words * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(dIndeg.p, 0, (size_t)N * sizeof(unsigned), s));
+        CK(cudaMemsetAsync(dCnt.p, 0, 4 * sizeof(unsigned), s));
+        k_colour_links<<<nblk(M, 256), 256, 0, s>>>((const unsigned *)dKeysS.p, (const unsigned *)dValsS.p, M, (unsigned *)dNext4.p, (unsigned *)dIndeg.p);
+        ColourArgs a{N, V, words, (const uint4 *)dBody4.p, (const uint4 *)dNext4.p, (unsigned *)dIndeg.p, (unsigned long long *)dUsed.p,
+                     (unsigned *)dColour.p, (unsigned *)dA.p, (unsigned *)dB.p, (unsigned *)dCnt.p};
+        k_colour_seed<<<nblk(N, 256), 256, 0, s>>>(a);
+        k_colour_wavefronts<<<1, kColourThreads, 0, s>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cnt, dCnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (!cnt[1]) break;
+        if (words >= 1024) return fail("device colouring: more than %u colours needed", words * 64);
+    }
+    CK(cudaEventRecord(ev1, s));
+    CK(cudaMemcpyAsync(colour.data(), dColour.p, (size_t)N * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    float t = 0.0f; cudaEventElapsedTime(&t, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (cnt[2] != N) return fail("device colouring: coloured %u of %u constraints (dependency cycle?)", cnt[2], N);
+    unsigned nColours = 0;
+    for (unsigned id = 0; id < N; id++) nColours = std::max(nColours, colour[id] + 1);
+    groups_from_colours(e, colour, nColours);
+    if (ms) *ms = t;
+    if (wavefronts) *wavefronts = cnt[3];
     return 0;
 }
 
@@ -498,15 +583,6 @@ static bool factor_rank1(const float *Q, float Kp[4]) {
     return true;
 }
 
-template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v, cudaStream_t s) {
-    if (v.empty()) return 0;
-    if (buf.alloc(v.size() * sizeof(T) + 16)) return 1;  // +16: bulk copies of the tiled kernel round their size up to 16 bytes
-    cudaError_t e = cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return fail("upload -> %s", cudaGetErrorString(e));
-    e = cudaStreamSynchronize(s);  // the host vector dies with the caller's scope
-    if (e != cudaSuccess) return fail("upload sync -> %s", cudaGetErrorString(e));
-    return 0;
-}
 
 // Tiled mode (tiled.cuh): partition the particles into one tile per SM by recursive coordinate bisection of the rest
 // positions, classify them (private = every constraint touching it lies inside its tile), and move the device arrays to the

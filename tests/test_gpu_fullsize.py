@@ -140,3 +140,25 @@ def test_cfg4_full_size_vs_fp64(cpu_libs):
     print("cfg4 full size: %d constraints, %d colours, particles rel %.2e, rigid bodies abs %.2e" % (gpu.num_constraints(), len(og) - 1, e, erb))
     assert e <= 1e-4 and erb <= 1e-4
     gpu.close()
+
+
+def test_device_colouring_cfg2_full_size():
+    """Exact first-fit colouring of cfg2 (5,988,006 constraints, 27 colours) on the GPU equals the host colouring; prints both times."""
+    import time
+    from positionbaseddynamics_b200 import _capi
+    from positionbaseddynamics_b200.model import HostModel
+    hm = HostModel(); scenes.cfg2(hm, 1000, 20)
+    types, bodies, params, _ = hm.constraints()
+    mass, _ = hm.masses()
+    eng = _capi.Engine(0)
+    eng.set_particles(hm.get("x"), mass)
+    eng.add_flat(types, bodies, params)
+    t0 = time.perf_counter(); eng.color_first_fit(); t_host = time.perf_counter() - t0
+    off_h, ids_h = eng.groups()
+    t0 = time.perf_counter(); ms, fronts = eng.color_first_fit_device(); t_dev = time.perf_counter() - t0
+    off_d, ids_d = eng.groups()
+    print("cfg2 colouring: host %.1f ms, device %.1f ms on the GPU (%.1f ms incl. host CSR build, upload and readback), %d wavefronts, %d colours"
+          % (t_host * 1e3, ms, t_dev * 1e3, fronts, len(off_d) - 1))
+    assert len(off_d) - 1 == 27
+    assert (off_d == off_h).all() and (ids_d == ids_h).all()
+    eng.close(); hm.close()
