@@ -76,11 +76,10 @@ struct pbd_engine {
     int smCount = 148;
     // particles
     unsigned n = 0;
-    DevBuf pos, vel, oldp, lastp, pos0, stage, massStage;
+    DevBuf pos, vel, oldp, lastp, pos0, stage, stage2, massStage;
     // rigid bodies coupled through joints: float4 arrays X(xyz,invMass) Q(x,y,z,w) V(xyz,mass) W(omega) + history + inertia
     unsigned nRb = 0;
     DevBuf rbX, rbQ, rbV, rbW, rbOldX, rbLastX, rbOldQ, rbLastQ, rbI, rbIinv;
-    float *pinned = nullptr; size_t pinnedBytes = 0;
     // constraints (host copy, insertion order) and groups
     HostType host[PBD_NUM_TYPES];
     unsigned numConstraints = 0;
@@ -89,7 +88,7 @@ struct pbd_engine {
     // device image
     DevType dev[PBD_NUM_TYPES];
     std::vector<Bucket> buckets;
-    DevBuf dBuckets, dTypeArrays, dBarrier, dTrace;
+    DevBuf dBuckets, dBarrier, dTrace;
     bool imageDirty = true;
     bool sortBuckets = true;
     // parameters
@@ -98,6 +97,7 @@ struct pbd_engine {
     // graph cache
     cudaGraphExec_t graphExec = nullptr;
     bool graphValid = false;
+    unsigned long long graphLaunches = 0;  // kernel nodes of the captured step
     // stats
     pbd_stats stats{};
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -168,7 +168,8 @@ extern "C" int pbd_destroy(pbd_engine *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
-    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->massStage, &e->dBuckets, &e->dTypeArrays, &e->dBarrier, &e->dTrace,
+    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->stage2, &e->massStage, &e->dSlot, &e->dSlotOld, &e->relayoutTmp,
+                    &e->dTileOff, &e->dTileStart, &e->dTilePrivate, &e->dBuckets, &e->dBarrier, &e->dTrace,
                     &e->rbX, &e->rbQ, &e->rbV, &e->rbW, &e->rbOldX, &e->rbLastX, &e->rbOldQ, &e->rbLastQ, &e->rbI, &e->rbIinv}) b->release();
     for (auto &d : e->dev) {
         for (auto &b : d.idx) b.release();
@@ -177,7 +178,6 @@ extern "C" int pbd_destroy(pbd_engine *e) {
         for (auto &b : d.mat) b.release();
         d.lambda.release();
     }
-    if (e->pinned) cudaFreeHost(e->pinned);
     if (e->evStart) cudaEventDestroy(e->evStart);
     if (e->evStop) cudaEventDestroy(e->evStop);
     if (e->ownsStream) cudaStreamDestroy(e->stream);
@@ -1085,14 +1085,11 @@ static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long 
 template <unsigned MASK, int THREADS>
 static int launch_tiled(pbd_engine *e, cudaStream_t s, TiledArgs &ta) {
     auto kernel = k_step_tiled<MASK, THREADS>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmemBytes));
-        int perSM = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, THREADS, kTiledSmemBytes));
-        if (perSM < 1) return fail("tiled kernel does not fit on an SM");
-        configured = true;
-    }
+    // per device and function; cheap, so not cached (engines on several devices may live in one thread)
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmemBytes));
+    int perSM = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, THREADS, kTiledSmemBytes));
+    if (perSM < 1) return fail("tiled kernel does not fit on an SM");
     void *args[] = {&ta};
     CK(cudaLaunchCooperativeKernel((void *)kernel, dim3(e->nTiles), dim3(THREADS), args, kTiledSmemBytes, s));
     return 0;
@@ -1117,12 +1114,7 @@ static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long 
     static const char *noStage = getenv("PBD_B200_NOSTAGE");  // A/B knob: constraint stream straight from global memory
     ta.stage = noStage ? 0 : 1;
     ta.swizzle = e->tileSwizzle ? 1 : 0;
-    static const char *noLambda = getenv("PBD_B200_NOSTAGE_LAMBDA");
-    ta.stageLambda = (!noLambda && ta.stage && e->coloursUsed >= 2) ? 1 : 0;
-    static const char *serialAB = getenv("PBD_B200_SERIAL_AB");
-    ta.serialAB = serialAB ? 1 : 0;
-    static const char *fenceMode = getenv("PBD_B200_FENCE");
-    ta.fenceMode = fenceMode ? atoi(fenceMode) : 0;
+    ta.stageLambda = (ta.stage && e->coloursUsed >= 2) ? 1 : 0;  // the copy for phase p + 1 starts during phase p: needs another colour in between
     ta.trace = nullptr; ta.tracePhases = 0;
     static const char *traceWorker = getenv("PBD_B200_TRACE_WORKER");
     ta.traceWorker = traceWorker ? atoi(traceWorker) : -1;
@@ -1175,7 +1167,6 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
     if (!e) return fail("null engine");
     CKE(use(e));
     CKE(flatten(e));
-    static thread_local unsigned long long graphLaunches = 0;
     CK(cudaEventRecord(e->evStart, e->stream));
     for (unsigned s = 0; s < nSteps; s++) {
         unsigned long long L = 0;
@@ -1187,9 +1178,9 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
             CKE(enqueue_step_tiled(e, e->stream, &L));
         } else {
             unsigned long long LL = 0;
-            if (!e->graphValid) { CKE(ensure_graph(e, &LL)); graphLaunches = LL; }
+            if (!e->graphValid) { CKE(ensure_graph(e, &LL)); e->graphLaunches = LL; }
             CK(cudaGraphLaunch(e->graphExec, e->stream));
-            L = graphLaunches;
+            L = e->graphLaunches;
         }
         e->stats.kernel_launches += L;
         e->stats.steps++;
@@ -1219,7 +1210,7 @@ extern "C" int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, 
     const size_t bytes = (size_t)e->n * 3 * sizeof(float);
     // two staging areas so that x and v uploads do not serialise on a host sync
     CKE(e->stage.alloc(bytes));
-    static thread_local DevBuf stage2;
+    DevBuf &stage2 = e->stage2;
     CKE(stage2.alloc(bytes));
     if (x_in) {
         CK(cudaMemcpyAsync(e->stage.p, x_in, bytes, cudaMemcpyHostToDevice, e->stream));

@@ -57,8 +57,6 @@ struct TiledArgs {
     int swizzle;                 // tile slots are bank-swizzled (tile_swizzle); must match the index encoding done at flatten time
     int stageLambda;             // XPBD multipliers travel with the staged operands (needs >= 2 colours: the copy for phase p + 1 starts during phase p)
     int stage;                   // 0: workers read the constraint stream straight from global memory (A/B knob)
-    int fenceMode;               // development knob: 0 manager fence (default), 1 fence by the worker threads that ran spanning constraints, 2 none (timing only)
-    int serialAB;                // 1: the private constraints start only when the CTA's spanning constraints are done (A/B knob)
     TypeArrays types[PBD_NUM_TYPES];
 };
 
@@ -259,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                     if (lane == 0) {
                         // release: the workers' stores were ordered before this thread by the named barrier; every particle /
                         // multiplier access of this kernel is an L2 access (ld.cg / st.cg), so no L1 invalidation is needed
-                        if (a.fenceMode == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
                         asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(a.barrier), "l"(1ull) : "memory");
                         if (tr) rec[1] = globaltimer_ns();
                     }
@@ -287,7 +285,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                     if (a.stage) mbar_wait(barAddr + 8u * (phase & 1u), (phase >> 1) & 1u);
                     if (tr) rec[1] = globaltimer_ns();
                     unsigned rot = 0;  // items of this colour handed out so far (mod W): the next run starts at that thread
-                    bool ranSpanning = false;
 #pragma unroll 1
                     for (int part = 0; part < 2; part++) {
                         unsigned running = 0;
@@ -308,12 +305,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                                     const Streamed s = st ? load_streamed_stage<T>(stage, pl, j) : load_streamed<T>(ta, g0 + j);
                                     const float *lam = (st && a.stageLambda && stream_es<T>(7)) ? reinterpret_cast<const float *>(stage + pl.o7 + 4u * j) : nullptr;
                                     project_streamed_acc<T>(acc, ta, g0 + j, s, a.h, iterZero, lam);
-                                    if (part == 0) ranSpanning = true;
                                 })
                             rot = (rot + (j1 - j0)) % W;
                         }
                         if (tr) rec[2 + part] = globaltimer_ns();
-                        if (part == 0) { if (a.fenceMode == 1 && ranSpanning) asm volatile("fence.acq_rel.gpu;" ::: "memory"); cta_arrive<THREADS>(); if (a.serialAB) asm volatile("bar.sync 2, %0;" :: "n"(THREADS - 32) : "memory"); }
+                        if (part == 0) cta_arrive<THREADS>();
                     }
                     __syncthreads();                             // end of the colour: released by the manager after the grid barrier
                 }

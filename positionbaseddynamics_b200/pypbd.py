@@ -80,6 +80,7 @@ class TetModel:
     def __init__(self, host, idx): self._h, self._i = host, idx
     def getIndexOffset(self): return self._h.tet_index_offset(self._i)
     def getParticleMesh(self): return _Mesh(self._h, self._i, False)
+    def updateMeshNormals(self, pd): pass  # rendering helper of the reference
 
 
 class SimulationModel:
@@ -93,17 +94,33 @@ class SimulationModel:
     def getTriangleModels(self): return [TriangleModel(self._host, i) for i in range(_m._l().pbdm_num_triangle_models(self._host._h))]
     def getTetModels(self): return [TetModel(self._host, i) for i in range(_m._l().pbdm_num_tet_models(self._host._h))]
 
-    def addRegularTriangleModel(self, width, height, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1)):
+    # The builders return the new model like pyPBD does (SimulationModelModule.cpp:98-229).  uvIndices / uvs (rendering) and
+    # testMesh (collision detection against signed distance fields) belong to parts of the reference outside this path: accepted
+    # for source compatibility, testMesh=True is refused because no collision detection runs here.
+    @staticmethod
+    def _no_collision(testMesh):
+        if testMesh:
+            raise _capi.PbdError("testMesh=True needs the reference's collision detection, which is outside this engine's path")
+
+    def addRegularTriangleModel(self, width, height, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1), testMesh=False):
+        self._no_collision(testMesh)
         self._host.add_regular_triangle_model(width, height, translation, rotation, scale)
+        return self.getTriangleModels()[-1]
 
-    def addRegularTetModel(self, width, height, depth, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1, 1)):
+    def addRegularTetModel(self, width, height, depth, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1, 1), testMesh=False):
+        self._no_collision(testMesh)
         self._host.add_regular_tet_model(width, height, depth, translation, rotation, scale)
+        return self.getTetModels()[-1]
 
-    def addTriangleModel(self, points, indices):
+    def addTriangleModel(self, points, indices, uvIndices=None, uvs=None, testMesh=False):
+        self._no_collision(testMesh)
         self._host.add_triangle_model(np.asarray(points).reshape(-1, 3), np.asarray(indices).reshape(-1, 3))
+        return self.getTriangleModels()[-1]
 
-    def addTetModel(self, points, indices):
+    def addTetModel(self, points, indices, testMesh=False, **unused):
+        self._no_collision(testMesh)
         self._host.add_tet_model(np.asarray(points).reshape(-1, 3), np.asarray(indices).reshape(-1, 4))
+        return self.getTetModels()[-1]
 
     def addClothConstraints(self, tm, clothMethod, distanceStiffness, xxStiffness, yyStiffness, xyStiffness, xyPoissonRatio, yxPoissonRatio,
                             normalizeStretch, normalizeShear):
@@ -157,6 +174,49 @@ class SimulationModel:
     def setSolidVolumeStiffness(self, v): self._host.set_model_param(11, v)
 
 
+class LogLevel:
+    """Utils/Logger.h levels (pyPBD exposes them as an enum)."""
+    DEBUG, INFO, WARN, ERR = 0, 1, 2, 3
+
+
+class Logger:
+    """pyPBD's Logger.addConsoleSink / addFileSink (UtilitiesModule.cpp): this path has nothing of its own to log, the calls are
+    kept so that the reference's example scripts run unchanged; errors surface as PbdError."""
+    level = LogLevel.INFO
+
+    @staticmethod
+    def addConsoleSink(level=LogLevel.INFO): Logger.level = level
+
+    @staticmethod
+    def addFileSink(level=LogLevel.INFO, path=None): Logger.level = level
+
+
+class Timing:
+    """pyPBD's Timing.printAverageTimes / reset: the reference prints its START_TIMING sections (Utils/Timing.h); here the one
+    section that exists is the step itself, timed on the device with CUDA events."""
+    _steps = 0; _ms = 0.0
+    enabled = False  # recording synchronises after every step; switch on with Timing.enabled = True
+
+    @staticmethod
+    def _record(ms): Timing._steps += 1; Timing._ms += ms
+
+    @staticmethod
+    def reset(): Timing._steps = 0; Timing._ms = 0.0
+
+    @staticmethod
+    def averageStepMs(): return Timing._ms / Timing._steps if Timing._steps else 0.0
+
+    @staticmethod
+    def printAverageTimes():
+        print("---------------------------------------------------------------------------")
+        print("Average times:")
+        print("SimStep (device): %.4f ms over %d steps" % (Timing.averageStepMs(), Timing._steps))
+        print("---------------------------------------------------------------------------")
+
+    @staticmethod
+    def printTimeSums(): print("SimStep (device): %.4f ms in %d steps" % (Timing._ms, Timing._steps))
+
+
 class TimeManager:
     _current = None
 
@@ -183,7 +243,10 @@ class TimeStepController:
     def getValueUInt(self, pid): return self._ts.get_uint(pid)
     def setValueInt(self, pid, v): self._ts.set_int(pid, v)
     def getValueInt(self, pid): return self._ts.get_int(pid)
-    def step(self, model): self._ts.step(model._host)
+    def step(self, model):
+        self._ts.step(model._host)
+        if Timing.enabled:
+            self._ts.sync(); Timing._record(self._ts.stats().last_step_ms)
 
 
 class Simulation:
