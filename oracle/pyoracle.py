@@ -43,9 +43,11 @@ def build(ref=True):
 
 
 def lib_path(kind, precision):
-    """kind: 'oracle' | 'ref'; precision: 'f32' | 'f64'."""
+    """kind: 'oracle' | 'ref' | 'refgpu' (reference build + integration/GpuTimeStepController.h); precision: 'f32' | 'f64'."""
     if kind == "oracle":
         return os.path.join(HERE, "liboracle_%s.so" % precision)
+    if kind == "refgpu":
+        return os.path.join(HERE, "_ref", "libpbdref_gpu_%s.so" % precision)
     return os.path.join(HERE, "_ref", "libpbdref_%s.so" % precision)
 
 
@@ -130,6 +132,17 @@ class CpuPbd:
         n = self.f("num_rigid_bodies")()
         out = np.zeros((max(n, 1), 13)); self.f("get_rigid_bodies")(_dp(out)); return out[:n]
 
+    def use_gpu_timestep(self, device=0, mode=0):
+        """refgpu only: install PBD::GpuTimeStepController (integration/GpuTimeStepController.h) as the reference's TimeStep."""
+        assert self.kind == "refgpu"
+        self.lib.ref_gpu_error.restype = C.c_char_p
+        if self.lib.ref_use_gpu_timestep(int(device), int(mode)):
+            raise RuntimeError(self.lib.ref_gpu_error().decode())
+
+    def gpu_error(self):
+        self.lib.ref_gpu_error.restype = C.c_char_p
+        return self.lib.ref_gpu_error().decode()
+
     def set_params(self, dt=0.005, sub_steps=5, max_iter=1, vel_method=0, gravity=(0, -9.81, 0)):
         self.f("set_params")(_D(dt), sub_steps, max_iter, vel_method, _dp(_f64(gravity)))
 
@@ -193,6 +206,10 @@ class CpuPbd:
         return self.f("step")(int(n))
 
     # -- known-answer entry points --------------------------------------------------------------
+    def time(self):
+        """TimeManager::getTime of the checker."""
+        return self.f("time")()
+
     def kat_solve(self, ctype, x, w, params, dt=0.005, handle_inversion=False, lam=0.0):
         x = _f64(x).reshape(4, 3).copy(); w = _f64(w); p = np.zeros(MAX_PARAMS); p[:len(params)] = params
         lam_c = _D(lam); corr = np.zeros((4, 3))

@@ -28,6 +28,13 @@
 #include <omp.h>
 #endif
 
+#ifdef PBD_WITH_GPU_ADAPTER
+// the reference-side binding of libpbd_b200.so, compiled inside this reference build so that the parity tests can step a model
+// the reference built and coloured through the GPU engine (integration/GpuTimeStepController.h)
+#define PBD_GPU_TIMESTEP_IMPLEMENTATION
+#include "GpuTimeStepController.h"
+#endif
+
 INIT_LOGGING
 INIT_TIMING
 
@@ -39,6 +46,10 @@ enum { T_DISTANCE = 0, T_DISTANCE_XPBD, T_DIHEDRAL, T_ISOBENDING, T_ISOBENDING_X
        T_BALLJOINT, T_RB_PARTICLE_BALLJOINT, T_UNKNOWN = -1 };
 
 static SimulationModel *g_model = nullptr;
+#ifdef PBD_WITH_GPU_ADAPTER
+static GpuTimeStepController *g_gpuTs = nullptr;  // owned by Simulation once installed
+static std::string g_gpuErr;
+#endif
 
 static Vector3r v3(const double *p) { return Vector3r((Real)p[0], (Real)p[1], (Real)p[2]); }
 static Matrix3r m3(const double *p) {  // row-major in
@@ -71,6 +82,9 @@ void ref_reset() {
         if (g_model) { g_model->cleanup(); delete g_model; g_model = nullptr; }
         delete s;  // deletes TimeStep and TimeManager (Simulation.cpp:22-28)
         TimeManager::setCurrent(nullptr);
+#ifdef PBD_WITH_GPU_ADAPTER
+        g_gpuTs = nullptr;
+#endif
     }
     g_model = new SimulationModel();
     g_model->init();
@@ -164,10 +178,19 @@ int ref_add_constraint(int type, const unsigned *b, const double *p) {
 
 void ref_set_params(double dt, unsigned subSteps, unsigned maxIter, int velMethod, const double *g) {
     TimeManager::getCurrent()->setTimeStepSize((Real)dt);
+#ifdef PBD_WITH_GPU_ADAPTER
+    if (g_gpuTs) {
+        g_gpuTs->setValue<unsigned int>(GpuTimeStepController::NUM_SUB_STEPS, subSteps);
+        g_gpuTs->setValue<unsigned int>(GpuTimeStepController::MAX_ITERATIONS, maxIter);
+        g_gpuTs->setValue<int>(GpuTimeStepController::VELOCITY_UPDATE_METHOD, velMethod);
+    } else
+#endif
+    {
     TimeStepController *ts = static_cast<TimeStepController *>(Simulation::getCurrent()->getTimeStep());
     ts->setValue<unsigned int>(TimeStepController::NUM_SUB_STEPS, subSteps);
     ts->setValue<unsigned int>(TimeStepController::MAX_ITERATIONS, maxIter);
     ts->setValue<int>(TimeStepController::VELOCITY_UPDATE_METHOD, velMethod);
+    }
     Real gg[3] = {(Real)g[0], (Real)g[1], (Real)g[2]};
     Simulation::getCurrent()->setVecValue<Real>(Simulation::GRAVITATION, gg);
 }
@@ -314,6 +337,30 @@ double ref_step(int n) {
     return std::chrono::duration<double>(t1 - t0).count();
 }
 double ref_time() { return TimeManager::getCurrent()->getTime(); }
+
+#ifdef PBD_WITH_GPU_ADAPTER
+// Install the GPU time step the way a user of the reference would (Simulation.h:48-49), carrying over the solver parameters.
+// mode: PBD_MODE_* of include/pbd_b200.h.  Returns 0 on success.
+int ref_use_gpu_timestep(int device, int mode) {
+    Simulation *sim = Simulation::getCurrent();
+    TimeStepController *old = static_cast<TimeStepController *>(sim->getTimeStep());
+    const unsigned subSteps = old->getValue<unsigned int>(TimeStepController::NUM_SUB_STEPS);
+    const unsigned maxIter = old->getValue<unsigned int>(TimeStepController::MAX_ITERATIONS);
+    const int velMethod = old->getValue<int>(TimeStepController::VELOCITY_UPDATE_METHOD);
+    GpuTimeStepController *ts = new GpuTimeStepController(device);
+    ts->init();
+    if (!ts->ok()) { g_gpuErr = ts->lastError(); delete ts; return 1; }
+    ts->setMode(mode);
+    ts->setValue<unsigned int>(GpuTimeStepController::NUM_SUB_STEPS, subSteps);
+    ts->setValue<unsigned int>(GpuTimeStepController::MAX_ITERATIONS, maxIter);
+    ts->setValue<int>(GpuTimeStepController::VELOCITY_UPDATE_METHOD, velMethod);
+    delete old;
+    sim->setTimeStep(ts);
+    g_gpuTs = ts;
+    return 0;
+}
+const char *ref_gpu_error() { if (g_gpuTs && !g_gpuTs->lastError().empty()) g_gpuErr = g_gpuTs->lastError(); return g_gpuErr.c_str(); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Known-answer entry points: call the stateless static solver functions directly.

@@ -608,7 +608,9 @@ static void bisect(std::vector<unsigned> &idx, size_t lo, size_t hi, unsigned t0
 static int prepare_tiles(pbd_engine *e, std::vector<unsigned> &tileOf, std::vector<unsigned> &tileStart, std::vector<unsigned char> &inSmem) {
     if (e->nRb || e->host[PBD_BALLJOINT].ids.size() || e->host[PBD_RB_PARTICLE_BALLJOINT].ids.size())
         return fail("tiled mode handles particle constraints only (rigid-body joints: use the graph mode)");
-    const unsigned n = e->n, nTiles = (unsigned)e->smCount;
+    unsigned nTiles = (unsigned)e->smCount;  // one tile per SM; PBD_B200_TILES=<k> (development knob) uses fewer, larger tiles
+    if (const char *g = getenv("PBD_B200_TILES")) { const int k = atoi(g); if (k >= 1 && k <= e->smCount) nTiles = (unsigned)k; }
+    const unsigned n = e->n;
     e->nTiles = nTiles;
     tileOf.assign(n, 0); inSmem.assign(n, 0); tileStart.assign(nTiles + 1, 0);
     std::vector<unsigned> priv(nTiles, 0);

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
             if (i - p0 < nPriv) sp[a.swizzle ? tile_swizzle(i - p0) : i - p0] = x;  // private: lives in shared memory for the whole substep
             else if (v.w != 0.0f) __stcg(a.pos + i, x);  // shared: other CTAs read it through L2
         }
-        grid_barrier(a.barrier, target);  // shared particles integrated everywhere (also orders the smem tile inside the CTA)
+        if (nTiles > 1) grid_barrier(a.barrier, target);  // shared particles integrated everywhere (also orders the smem tile inside the CTA)
+        else __syncthreads();
 
         // ---- coloured Gauss-Seidel sweeps: one split grid-barrier phase per colour -------------------------------------------------
         for (unsigned it = 0; it < a.maxIter; it++) {
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                     unsigned long long *rec = a.trace + ((size_t)phase * nTiles + tile) * 4;
                     cta_collect<THREADS>();                      // every worker's spanning constraints are done
                     if (tr) rec[0] = globaltimer_ns();
-                    if (lane == 0) {
+                    if (lane == 0 && nTiles > 1) {
                         // release: the workers' stores were ordered before this thread by the named barrier; every particle /
                         // multiplier access of this kernel is an L2 access (ld.cg / st.cg), so no L1 invalidation is needed
                         asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_tiled(const __grid_constant
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                         issue_phase(be < a.nBuckets ? be : 0u, phase + 1u);
                     }
-                    if (lane == 0) {
+                    if (lane == 0 && nTiles > 1) {
                         while (ld_acquire_u64(a.barrier) < target) { }
                         if (tr) rec[2] = globaltimer_ns();
                     }

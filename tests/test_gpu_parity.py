@@ -125,6 +125,42 @@ def test_mode_switch_keeps_state_bitwise():
         assert np.isfinite(u).all() and (u == w).all()
 
 
+ADAPTER_SCENES = ["cloth_isobending_xpbd", "cloth_femtriangle", "cloth_dihedral", "bar_fem_plus_volume", "bar_straintet", "bar_shapematching",
+                  "mixed_cloth_solid", "cfg4_small_with_rig"]
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("name", ADAPTER_SCENES)
+def test_reference_side_adapter(name, precision, cpu_libs):
+    """The drop-in proper.  integration/GpuTimeStepController.h -- the PBD::TimeStep subclass a maintainer adds to the reference --
+    is compiled inside a build of the unmodified reference (oracle/_ref/libpbdref_gpu_*.so, both Real = float and Real = double) and
+    installed with Simulation::setTimeStep.  The REFERENCE builds the scene, initialises the constraints and colours them; the
+    adapter flattens the model through its public members and steps it with libpbd_b200.so.  A twin scene stepped by the
+    reference's own TimeStepController (fp64) is the yardstick."""
+    from oracle import pyoracle
+    if not (pyoracle.available("refgpu", precision) and have_ref("f64")):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_gpu_%s.so not present on this box" % precision)
+    if name == "cfg4_small_with_rig":
+        build, amp, steps = (lambda m: scenes.cfg4(m, n_cloth=32, bar_dims=(7, 4, 4))), 0.0, 6
+    else:
+        build, amp, steps = SCENES[name]
+    gpu = cpu_libs.CpuPbd("refgpu", precision); cpu = cpu_libs.CpuPbd("ref", "f64")
+    build(gpu); build(cpu)
+    gpu.use_gpu_timestep(0, 0)
+    x_start = perturb([gpu, cpu], amp) if amp else cpu.get("x")
+    gpu.step(steps); cpu.step(steps)
+    assert gpu.gpu_error() == ""
+    xg, xc = gpu.get("x"), cpu.get("x")
+    assert np.isfinite(xg).all()
+    e_pos = rel_position_error(xg, xc)
+    print("adapter %s Real=%s: rel pos %.2e" % (name, precision, e_pos))
+    assert e_pos <= TOL, (name, e_pos)
+    assert abs(gpu.time() - cpu.time()) < 1e-6       # TimeManager advanced like TimeStepController.cpp:239
+    if name == "cfg4_small_with_rig":
+        assert np.abs(gpu.rigid_bodies()[:, :7] - cpu.rigid_bodies()[:, :7]).max() <= 1e-4
+    assert np.abs(xg - x_start).max() > 1e-4         # the step did something
+
+
 def _engine_from(hm, with_rb=False):
     from positionbaseddynamics_b200 import _capi
     types, bodies, params, _ = hm.constraints()

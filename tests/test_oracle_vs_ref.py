@@ -56,3 +56,26 @@ def test_thread_count_does_not_change_results(cpu_libs):
         r.step(5)
         out.append(r.get("x"))
     assert (out[0] == out[1]).all()
+
+
+def test_reference_side_adapter_is_built_and_fails_loudly_without_a_gpu():
+    """oracle/_ref/libpbdref_gpu_*.so = the unmodified reference + integration/GpuTimeStepController.h (the PBD::TimeStep subclass
+    that binds libpbd_b200.so).  Here (no GPU) installing it must fail with the engine's "no CUDA device" message, never fall
+    back to a CPU path; the GPU parity of the adapter is tests/test_gpu_parity.py::test_reference_side_adapter."""
+    import torch
+    from oracle import pyoracle
+    for precision in ("f32", "f64"):
+        if not pyoracle.available("refgpu", precision):
+            pytest.skip("oracle/_ref/libpbdref_gpu_%s.so not built (no /root/reference here)" % precision)
+        m = pyoracle.CpuPbd("refgpu", precision)
+        scenes.cloth(m, 6, 6, 4, 3, dist_k=1e5, bend_k=100.0)
+        if torch.cuda.is_available():
+            m.use_gpu_timestep(0, 0)
+            m.step(1)
+            assert m.gpu_error() == ""
+        else:
+            with pytest.raises(RuntimeError, match="no CUDA device"):
+                m.use_gpu_timestep(0, 0)
+            x0 = m.get("x").copy()
+            m.step(1)  # the reference's own TimeStepController is still installed and still works
+            assert np.abs(m.get("x") - x0).max() > 0
