@@ -13,6 +13,7 @@
  */
 #ifndef PBD_B200_H
 #define PBD_B200_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -123,6 +124,11 @@ int pbd_step(pbd_engine *e, unsigned nSteps);
 int pbd_sync(pbd_engine *e);
 /* End-to-end convenience used by host-buffer callers: upload x and v (3 floats/particle each, pinned or pageable),
  * run nSteps, download x (and v if v_out != NULL), synchronise. */
+/* Page-lock caller-owned host arrays (e.g. the reference's std::vector<Vector3r> storage) so that pbd_step_host copies at full
+ * PCIe speed straight from / into them; unpin before the memory is freed or reallocated.  Thin wrappers over cudaHostRegister,
+ * exported so that a reference-side adapter needs no CUDA headers. */
+int pbd_pin_host(void *ptr, size_t bytes);
+int pbd_unpin_host(void *ptr);
 int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out);
 
 int pbd_get_lambdas(pbd_engine *e, int type, float *dst, unsigned *ids); /* debug: per-type XPBD multipliers + insertion ids */

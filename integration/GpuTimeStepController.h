@@ -37,7 +37,7 @@ public:
         m_collisionDetection = NULL;
         if (pbd_create(device, nullptr, &m_engine)) { m_error = pbd_last_error(); m_engine = nullptr; }
     }
-    ~GpuTimeStepController() override { pbd_destroy(m_engine); }
+    ~GpuTimeStepController() override { unpin(); pbd_destroy(m_engine); }
 
     const std::string &lastError() const { return m_error; }
     bool ok() const { return m_engine != nullptr && m_error.empty(); }
@@ -63,11 +63,20 @@ public:
         if (pbd_set_params(m_engine, (float)tm->getTimeStepSize(), m_subSteps, m_maxIterations, m_velocityUpdateMethod, grav)) return fail();
         // rigid bodies: uploaded at bind time, device state is authoritative afterwards (their history feeds the second-order
         // velocity update); particles: x and v come from the host every step, so user edits between steps are honoured
-        packParticles(pd, n);
-        if (pbd_step_host(m_engine, 1, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr)) return fail();
-        for (unsigned i = 0; i < n; i++) {
-            pd.getPosition(i) = Vector3r((Real)m_x[3 * i], (Real)m_x[3 * i + 1], (Real)m_x[3 * i + 2]);
-            pd.getVelocity(i) = Vector3r((Real)m_v[3 * i], (Real)m_v[3 * i + 1], (Real)m_v[3 * i + 2]);
+        if (sizeof(Real) == sizeof(float) && n) {
+            // Real == float: std::vector<Vector3r> is already n x 3 packed floats (Common/Common.h:31); the engine copies straight
+            // from and into the model's own arrays (page-locked at bind time), no host-side conversion at all
+            float *x = reinterpret_cast<float *>(&pd.getPosition(0)[0]), *v = reinterpret_cast<float *>(&pd.getVelocity(0)[0]);
+            if (x != m_pinnedX || v != m_pinnedV) pin(x, v, n);  // the vectors were reallocated
+            if (pbd_step_host(m_engine, 1, x, v, x, v)) return fail();
+        } else {
+            packParticles(pd, n);
+            if (pbd_step_host(m_engine, 1, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr)) return fail();
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < (int)n; i++) {
+                pd.getPosition(i) = Vector3r((Real)m_x[3 * i], (Real)m_x[3 * i + 1], (Real)m_x[3 * i + 2]);
+                pd.getVelocity(i) = Vector3r((Real)m_v[3 * i], (Real)m_v[3 * i + 1], (Real)m_v[3 * i + 2]);
+            }
         }
         if (!rbs.empty() && !downloadBodies(rbs)) return;
         tm->setTime(tm->getTime() + tm->getTimeStepSize());  // TimeStepController.cpp:239
@@ -81,9 +90,20 @@ protected:
     unsigned m_boundParticles = ~0u;
     size_t m_boundBodies = ~size_t(0);
     std::string m_error;
-    std::vector<float> m_x, m_v, m_tmp;
+    std::vector<float> m_x, m_v;
+    float *m_pinnedX = nullptr, *m_pinnedV = nullptr;
 
     void fail() { m_error = pbd_last_error(); }
+    void unpin() {
+        if (m_pinnedX) pbd_unpin_host(m_pinnedX);
+        if (m_pinnedV) pbd_unpin_host(m_pinnedV);
+        m_pinnedX = m_pinnedV = nullptr;
+    }
+    void pin(float *x, float *v, unsigned n) {  // best effort: an unpinned array still works, only slower
+        unpin();
+        if (pbd_pin_host(x, (size_t)n * 3 * sizeof(float)) == 0) m_pinnedX = x;
+        if (pbd_pin_host(v, (size_t)n * 3 * sizeof(float)) == 0) m_pinnedV = v;
+    }
 
     void initParameters() override {
         TimeStep::initParameters();
@@ -108,7 +128,8 @@ protected:
 
     void packParticles(ParticleData &pd, unsigned n) {
         m_x.resize(3 * (size_t)n); m_v.resize(3 * (size_t)n);
-        for (unsigned i = 0; i < n; i++)
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < (int)n; i++)
             for (int k = 0; k < 3; k++) { m_x[3 * i + k] = (float)pd.getPosition(i)[k]; m_v[3 * i + k] = (float)pd.getVelocity(i)[k]; }
     }
 

@@ -22,7 +22,7 @@ MODE_GRAPH, MODE_PERSISTENT, MODE_LAUNCH, MODE_TILED = 0, 1, 2, 3
 # every symbol include/pbd_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "pbd_set_particles", "pbd_set_attr",
            "pbd_get_attr", "pbd_set_masses", "pbd_set_rigid_bodies", "pbd_get_rigid_bodies", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
-           "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_color_first_fit_device", "pbd_get_num_groups", "pbd_get_groups",
+           "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_color_first_fit_device", "pbd_pin_host", "pbd_unpin_host", "pbd_get_num_groups", "pbd_get_groups",
            "pbd_set_params", "pbd_set_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host",
            "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step"]
 

@@ -544,6 +544,9 @@ extern "C" int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsign
     if (maxIter < 1) return fail("maxIterations must be >= 1 (TimeStepController.cpp:55)");
     if (velMethod != 0 && velMethod != 1) return fail("velocityUpdateMethod must be 0 or 1");
     if (!(dt > 0.0f)) return fail("time step size must be positive");
+    const bool same = e->dt == dt && e->subSteps == subSteps && e->maxIter == maxIter && e->velMethod == velMethod &&
+                      (!gravity || (e->g[0] == gravity[0] && e->g[1] == gravity[1] && e->g[2] == gravity[2]));
+    if (same) return 0;  // callers such as a TimeStep adapter set the parameters before every step: keep the captured graph
     e->dt = dt; e->subSteps = subSteps; e->maxIter = maxIter; e->velMethod = velMethod;
     if (gravity) { e->g[0] = gravity[0]; e->g[1] = gravity[1]; e->g[2] = gravity[2]; }
     drop_graph(e);
@@ -1202,6 +1205,17 @@ extern "C" int pbd_sync(pbd_engine *e) {
         if (cudaEventElapsedTime(&ms, e->evStart, e->evStop) == cudaSuccess) e->stats.last_step_ms = ms;
         e->timingPending = false;
     }
+    return 0;
+}
+
+extern "C" int pbd_pin_host(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail("pbd_pin_host: null argument");
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int pbd_unpin_host(void *ptr) {
+    if (!ptr) return 0;
+    CK(cudaHostUnregister(ptr));
     return 0;
 }
 
