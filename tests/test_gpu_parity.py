@@ -342,6 +342,47 @@ def test_second_order_velocity_update_and_pinned_particles(cpu_libs):
     gpu.close()
 
 
+def test_degenerate_inputs_take_the_reference_branches(cpu_libs):
+    """The early-outs of the reference's solvers ("branches the kernel must keep"): both particles static (wSum == 0),
+    coincident particles (d <= eps / zero gradient), stiffness 0 (XPBD alpha = 0; PBD volume k == 0 skip), a constraint between a
+    static and a dynamic particle, a flat (zero-volume) tetrahedron.  Every constraint sits on its own particles; GPU and fp64
+    checker must agree and stay finite."""
+    from positionbaseddynamics_b200 import _capi
+    from positionbaseddynamics_b200.model import HostModel
+    pts = np.array([[0, 0, 0], [1, 0, 0],            # 0-1   both static, stretched distance
+                    [0, 1, 0], [0, 1, 0],            # 2-3   coincident
+                    [0, 2, 0], [1.5, 2, 0],          # 4-5   XPBD distance with stiffness 0
+                    [0, 3, 0], [1.2, 3, 0],          # 6-7   static + dynamic
+                    [0, 4, 0], [1, 4, 0], [0, 5, 0], [1, 5, 0],        # 8-11  flat tetrahedron (volume constraints)
+                    [0, 6, 0], [1, 6, 0], [0, 7, 0], [0.3, 6.4, 0.8],  # 12-15 volume constraint with stiffness 0
+                    ], dtype=np.float64)
+    tris = np.array([[0, 1, 2]], dtype=np.uint32)  # a triangle model only provides the particles' container
+    gpu = HostModel(); cpu = cpu_libs.CpuPbd("oracle", "f64")
+    for m in (gpu, cpu):
+        m.add_triangle_model(pts, np.array([[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11], [12, 13, 14], [13, 14, 15]], dtype=np.uint32))
+        for i in (0, 1, 6):
+            m.set_mass(i, 0.0)
+        assert m.add_constraint(_capi.DISTANCE, [0, 1], [1.0])
+        assert m.add_constraint(_capi.DISTANCE_XPBD, [2, 3], [1.0e5])
+        assert m.add_constraint(_capi.DISTANCE_XPBD, [4, 5], [0.0])
+        assert m.add_constraint(_capi.DISTANCE, [6, 7], [1.0])
+        m.add_constraint(_capi.VOLUME, [8, 9, 10, 11], [1.0])
+        m.add_constraint(_capi.VOLUME_XPBD, [8, 9, 10, 11], [1.0e5])
+        assert m.add_constraint(_capi.VOLUME, [12, 13, 14, 15], [0.0])
+        m.set_params(dt=0.005, sub_steps=2, max_iter=3)
+    # stretch / compress away from the rest state so that the non-degenerate parts of the solvers are active
+    x = gpu.get("x").astype(np.float64)
+    x[1] += [0.5, 0, 0]; x[5] += [0.3, 0, 0]; x[7] += [0.4, 0, 0]; x[15] += [0.1, 0.1, 0.1]
+    gpu.set("x", x); cpu.set("x", x)
+    assert gpu.num_constraints() == cpu.num_constraints()
+    gpu.step(3); cpu.step(3)
+    xg, xc = gpu.get("x"), cpu.get("x")
+    assert np.isfinite(xg).all() and np.isfinite(xc).all()
+    assert rel_position_error(xg, xc) <= TOL
+    assert (xg[0] == x[0].astype(np.float32)).all() and (xg[1] == x[1].astype(np.float32)).all() and (xg[6] == x[6].astype(np.float32)).all()
+    gpu.close()
+
+
 def test_empty_and_constraint_free_models():
     from positionbaseddynamics_b200.model import HostModel
     m = HostModel()
