@@ -19,6 +19,7 @@
 #include "tiled.cuh"
 #include "colouring.cuh"
 #include <cub/cub.cuh>
+#include <parallel/algorithm>  // libstdc++ parallel mode (OpenMP): the per-bucket sorts of flatten
 #include "host/pbd_model.h"
 
 using namespace pbdk;
@@ -700,7 +701,8 @@ static int flatten(pbd_engine *e) {
                 const int nb = type_shape(t).nBodies;
                 const unsigned *bod = e->host[t].bodies.data();
                 std::vector<std::pair<unsigned long long, unsigned>> keyed(tmp[t].size());
-                for (size_t i = 0; i < tmp[t].size(); i++) {
+                #pragma omp parallel for schedule(static)
+                for (long long i = 0; i < (long long)tmp[t].size(); i++) {
                     const unsigned *b = bod + (size_t)tmp[t][i] * nb;
                     unsigned mn = e->slot[b[0]];
                     for (int k = 1; k < nb; k++) mn = std::min(mn, e->slot[b[k]]);
@@ -713,8 +715,9 @@ static int flatten(pbd_engine *e) {
                     }
                     keyed[i] = std::make_pair((major << 32) | mn, tmp[t][i]);
                 }
-                std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; });
-                for (size_t i = 0; i < keyed.size(); i++) tmp[t][i] = keyed[i].second;
+                __gnu_parallel::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; });
+                #pragma omp parallel for schedule(static)
+                for (long long i = 0; i < (long long)keyed.size(); i++) tmp[t][i] = keyed[i].second;
                 if (tiled) {  // runs of every tile inside this bucket: [2 tile] spanning, [2 tile + 1] private
                     const size_t base = tileOff.size();
                     tileOff.resize(base + 2 * e->nTiles + 1, 0u);
@@ -763,7 +766,8 @@ static int flatten(pbd_engine *e) {
         d.arrays = TypeArrays{};
         d.order.resize(cnt);
         if (cnt == 0) continue;
-        for (unsigned i = 0; i < cnt; i++) d.order[i] = h.ids[order[t][i]];
+        #pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)cnt; i++) d.order[i] = h.ids[order[t][i]];
         auto P = [&](unsigned i, int k) { return h.params[(size_t)order[t][i] * s.nParams + k]; };
         auto B = [&](unsigned i, int k) {
             const unsigned raw = h.bodies[(size_t)order[t][i] * s.nBodies + k];
@@ -779,16 +783,19 @@ static int flatten(pbd_engine *e) {
         // indices
         if (s.nBodies == 2) {
             std::vector<uint2> v(cnt);
-            for (unsigned i = 0; i < cnt; i++) v[i] = make_uint2(B(i, 0), B(i, 1));
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)cnt; i++) v[i] = make_uint2(B(i, 0), B(i, 1));
             CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx2 = (const uint2 *)d.idx[0].p;
         } else if (s.nBodies == 4) {
             std::vector<uint4> v(cnt);
-            for (unsigned i = 0; i < cnt; i++) v[i] = make_uint4(B(i, 0), B(i, 1), B(i, 2), B(i, 3));
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)cnt; i++) v[i] = make_uint4(B(i, 0), B(i, 1), B(i, 2), B(i, 3));
             CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx4 = (const uint4 *)d.idx[0].p;
         } else {
             for (int k = 0; k < 3; k++) {
                 std::vector<unsigned> v(cnt);
-                for (unsigned i = 0; i < cnt; i++) v[i] = B(i, k);
+                #pragma omp parallel for schedule(static)
+                for (long long i = 0; i < (long long)cnt; i++) v[i] = B(i, k);
                 CKE(upload_vec(d.idx[k], v, e->stream)); d.arrays.idx3[k] = (const unsigned *)d.idx[k].p;
             }
         }
@@ -800,35 +807,41 @@ static int flatten(pbd_engine *e) {
         switch (t) {
         case PBD_DISTANCE: case PBD_DISTANCE_XPBD: case PBD_DIHEDRAL: case PBD_VOLUME: case PBD_VOLUME_XPBD:
             gs[0].resize(cnt);
-            for (unsigned i = 0; i < cnt; i++) gs[0][i] = P(i, 0);
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)cnt; i++) gs[0][i] = P(i, 0);
             matSlot[0] = 1;
             break;
         case PBD_ISOBENDING: case PBD_ISOBENDING_XPBD: {
             matSlot[0] = 0;
             gv[0].resize(cnt);
-            bool rank1 = true;
-            for (unsigned i = 0; i < cnt && rank1; i++) {
-                float Q[16], Kp[4];
-                for (int k = 0; k < 16; k++) Q[k] = P(i, 1 + k);
-                rank1 = factor_rank1(Q, Kp);
+            int notRank1 = 0;
+            #pragma omp parallel for schedule(static) reduction(| : notRank1)
+            for (long long i = 0; i < (long long)cnt; i++) {
+                float Q[16], Kp[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < 16; k++) Q[k] = P((unsigned)i, 1 + k);
+                if (!factor_rank1(Q, Kp)) notRank1 |= 1;
                 gv[0][i] = make_float4(Kp[0], Kp[1], Kp[2], Kp[3]);
             }
+            const bool rank1 = !notRank1;
             if (!rank1) {  // user-modified Q somewhere in this type: literal 4x4 evaluation for the whole type
                 variant = 1;
                 for (int r = 0; r < 4; r++) {
                     gv[r].resize(cnt);
-                    for (unsigned i = 0; i < cnt; i++) gv[r][i] = make_float4(P(i, 1 + 4 * r), P(i, 2 + 4 * r), P(i, 3 + 4 * r), P(i, 4 + 4 * r));
+                    #pragma omp parallel for schedule(static)
+                    for (long long i = 0; i < (long long)cnt; i++) gv[r][i] = make_float4(P(i, 1 + 4 * r), P(i, 2 + 4 * r), P(i, 3 + 4 * r), P(i, 4 + 4 * r));
                 }
             }
             break; }
         case PBD_FEMTRIANGLE:
             gv[0].resize(cnt); gs[0].resize(cnt);
-            for (unsigned i = 0; i < cnt; i++) { gs[0][i] = P(i, 0); gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), P(i, 4)); }
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)cnt; i++) { gs[0][i] = P(i, 0); gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), P(i, 4)); }
             for (int k = 0; k < 5; k++) matSlot[k] = 5 + k;
             break;
         case PBD_STRAINTRIANGLE:
             gv[0].resize(cnt);
-            for (unsigned i = 0; i < cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), P(i, 3));
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), P(i, 3));
             for (int k = 0; k < 5; k++) matSlot[k] = 4 + k;
             break;
         case PBD_FEMTET: case PBD_FEMTET_XPBD:
@@ -851,7 +864,8 @@ static int flatten(pbd_engine *e) {
             break;
         case PBD_BALLJOINT: case PBD_RB_PARTICLE_BALLJOINT:  // local connectors (jointInfo columns 0 [and 1]); global columns are recomputed per solve
             gv[0].resize(cnt);
-            for (unsigned i = 0; i < cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), 0.0f);
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), 0.0f);
             if (t == PBD_BALLJOINT) { gv[1].resize(cnt); for (unsigned i = 0; i < cnt; i++) gv[1][i] = make_float4(P(i, 3), P(i, 4), P(i, 5), 0.0f); }
             break;
         case PBD_SHAPEMATCHING:  // restCm | x0[0..3] packed in 3 float4 | w | numClusters ; stiffness is the material slot
@@ -884,7 +898,8 @@ static int flatten(pbd_engine *e) {
             d.arrays.matU[k] = first;
             if (!uniform) {
                 std::vector<float> v(cnt);
-                for (unsigned i = 0; i < cnt; i++) v[i] = P(i, matSlot[k]);
+                #pragma omp parallel for schedule(static)
+                for (long long i = 0; i < (long long)cnt; i++) v[i] = P(i, matSlot[k]);
                 CKE(upload_vec(d.mat[k], v, e->stream)); d.arrays.mat[k] = (const float *)d.mat[k].p;
             }
         }
