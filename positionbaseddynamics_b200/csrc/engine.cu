@@ -19,6 +19,7 @@
 #include "tiled.cuh"
 #include "colouring.cuh"
 #include <cub/cub.cuh>
+#include <omp.h>
 #include <parallel/algorithm>  // libstdc++ parallel mode (OpenMP): the per-bucket sorts of flatten
 #include "host/pbd_model.h"
 
@@ -27,6 +28,13 @@ using namespace pbdk;
 // ------------------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------------------
+// OpenMP team of the host-side flatten.  GPU hosts expose far more hardware threads (128 here) than a process may actually use
+// (measured: a 128-thread team made flatten 9x slower than the serial code, 8-16 threads 3x faster), so the team is capped.
+static int host_threads() {
+    static const int n = [] { const char *g = getenv("PBD_B200_HOST_THREADS"); const int want = g ? atoi(g) : 8; return std::max(1, std::min(want, omp_get_max_threads())); }();
+    return n;
+}
+
 static thread_local std::string g_err;
 static int fail(const char *fmt, ...) {
     char buf[1024];
@@ -701,7 +709,7 @@ static int flatten(pbd_engine *e) {
                 const int nb = type_shape(t).nBodies;
                 const unsigned *bod = e->host[t].bodies.data();
                 std::vector<std::pair<unsigned long long, unsigned>> keyed(tmp[t].size());
-                #pragma omp parallel for schedule(static)
+                #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)tmp[t].size(); i++) {
                     const unsigned *b = bod + (size_t)tmp[t][i] * nb;
                     unsigned mn = e->slot[b[0]];
@@ -715,8 +723,9 @@ static int flatten(pbd_engine *e) {
                     }
                     keyed[i] = std::make_pair((major << 32) | mn, tmp[t][i]);
                 }
-                __gnu_parallel::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; });
-                #pragma omp parallel for schedule(static)
+                __gnu_parallel::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; },
+                                            __gnu_parallel::default_parallel_tag(host_threads()));
+                #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)keyed.size(); i++) tmp[t][i] = keyed[i].second;
                 if (tiled) {  // runs of every tile inside this bucket: [2 tile] spanning, [2 tile + 1] private
                     const size_t base = tileOff.size();
@@ -766,7 +775,7 @@ static int flatten(pbd_engine *e) {
         d.arrays = TypeArrays{};
         d.order.resize(cnt);
         if (cnt == 0) continue;
-        #pragma omp parallel for schedule(static)
+        #pragma omp parallel for schedule(static) num_threads(host_threads())
         for (long long i = 0; i < (long long)cnt; i++) d.order[i] = h.ids[order[t][i]];
         auto P = [&](unsigned i, int k) { return h.params[(size_t)order[t][i] * s.nParams + k]; };
         auto B = [&](unsigned i, int k) {
@@ -783,18 +792,18 @@ static int flatten(pbd_engine *e) {
         // indices
         if (s.nBodies == 2) {
             std::vector<uint2> v(cnt);
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) v[i] = make_uint2(B(i, 0), B(i, 1));
             CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx2 = (const uint2 *)d.idx[0].p;
         } else if (s.nBodies == 4) {
             std::vector<uint4> v(cnt);
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) v[i] = make_uint4(B(i, 0), B(i, 1), B(i, 2), B(i, 3));
             CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx4 = (const uint4 *)d.idx[0].p;
         } else {
             for (int k = 0; k < 3; k++) {
                 std::vector<unsigned> v(cnt);
-                #pragma omp parallel for schedule(static)
+                #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)cnt; i++) v[i] = B(i, k);
                 CKE(upload_vec(d.idx[k], v, e->stream)); d.arrays.idx3[k] = (const unsigned *)d.idx[k].p;
             }
@@ -807,7 +816,7 @@ static int flatten(pbd_engine *e) {
         switch (t) {
         case PBD_DISTANCE: case PBD_DISTANCE_XPBD: case PBD_DIHEDRAL: case PBD_VOLUME: case PBD_VOLUME_XPBD:
             gs[0].resize(cnt);
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) gs[0][i] = P(i, 0);
             matSlot[0] = 1;
             break;
@@ -815,7 +824,7 @@ static int flatten(pbd_engine *e) {
             matSlot[0] = 0;
             gv[0].resize(cnt);
             int notRank1 = 0;
-            #pragma omp parallel for schedule(static) reduction(| : notRank1)
+            #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(| : notRank1)
             for (long long i = 0; i < (long long)cnt; i++) {
                 float Q[16], Kp[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int k = 0; k < 16; k++) Q[k] = P((unsigned)i, 1 + k);
@@ -827,20 +836,20 @@ static int flatten(pbd_engine *e) {
                 variant = 1;
                 for (int r = 0; r < 4; r++) {
                     gv[r].resize(cnt);
-                    #pragma omp parallel for schedule(static)
+                    #pragma omp parallel for schedule(static) num_threads(host_threads())
                     for (long long i = 0; i < (long long)cnt; i++) gv[r][i] = make_float4(P(i, 1 + 4 * r), P(i, 2 + 4 * r), P(i, 3 + 4 * r), P(i, 4 + 4 * r));
                 }
             }
             break; }
         case PBD_FEMTRIANGLE:
             gv[0].resize(cnt); gs[0].resize(cnt);
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) { gs[0][i] = P(i, 0); gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), P(i, 4)); }
             for (int k = 0; k < 5; k++) matSlot[k] = 5 + k;
             break;
         case PBD_STRAINTRIANGLE:
             gv[0].resize(cnt);
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), P(i, 3));
             for (int k = 0; k < 5; k++) matSlot[k] = 4 + k;
             break;
@@ -864,7 +873,7 @@ static int flatten(pbd_engine *e) {
             break;
         case PBD_BALLJOINT: case PBD_RB_PARTICLE_BALLJOINT:  // local connectors (jointInfo columns 0 [and 1]); global columns are recomputed per solve
             gv[0].resize(cnt);
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), 0.0f);
             if (t == PBD_BALLJOINT) { gv[1].resize(cnt); for (unsigned i = 0; i < cnt; i++) gv[1][i] = make_float4(P(i, 3), P(i, 4), P(i, 5), 0.0f); }
             break;
@@ -898,7 +907,7 @@ static int flatten(pbd_engine *e) {
             d.arrays.matU[k] = first;
             if (!uniform) {
                 std::vector<float> v(cnt);
-                #pragma omp parallel for schedule(static)
+                #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)cnt; i++) v[i] = P(i, matSlot[k]);
                 CKE(upload_vec(d.mat[k], v, e->stream)); d.arrays.mat[k] = (const float *)d.mat[k].p;
             }
