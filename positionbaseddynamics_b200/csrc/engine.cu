@@ -944,12 +944,24 @@ static int flatten(pbd_engine *e) {
 // ------------------------------------------------------------------------------------------------------------
 // step drivers
 // ------------------------------------------------------------------------------------------------------------
+// Block size of a projection launch (kProjectThreads is only the compiled upper bound).  Measured on B200 (profiles/README.md
+// section 3): 128 threads beat 256 on every config (more, smaller CTAs: faster ramp-up and drain of each dependent launch); a
+// launch that would not even give every SM one CTA is spread further, down to one warp per CTA, because such phases are pure
+// latency chains (cfg1, cfg3).  PBD_B200_BLOCK=<n> pins the size (development knob).
+static unsigned project_block(const pbd_engine *e, unsigned count) {
+    static const int pinned = [] { const char *g = getenv("PBD_B200_BLOCK"); return g ? atoi(g) : 0; }();
+    if (pinned >= 32 && pinned <= kProjectThreads) return (unsigned)pinned & ~31u;
+    const unsigned perSM = (count + (unsigned)e->smCount - 1) / (unsigned)e->smCount;
+    return std::max(32u, std::min(128u, (perSM + 31u) & ~31u));
+}
+
 static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, cudaStream_t s) {
     float4 *pos = (float4 *)e->pos.p;
     const TypeArrays &a = e->dev[b.type].arrays;
-    const unsigned grid = nblk(b.count, kProjectThreads);
+    const unsigned block = project_block(e, b.count);
+    const unsigned grid = nblk(b.count, block);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kProjectThreads); cfg.stream = s;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -978,17 +990,19 @@ static int launch_colour(pbd_engine *e, size_t b0, size_t b1, float h, int iterZ
         const size_t c1 = std::min(b1, c0 + (size_t)kMultiSegments);
         MultiArgs m{};
         m.nSeg = (int)(c1 - c0);
-        unsigned blocks = 0;
+        unsigned blocks = 0, total = 0;
+        for (size_t i = c0; i < c1; i++) total += e->buckets[i].count;
+        const unsigned block = project_block(e, total);
         for (size_t i = c0; i < c1; i++) {
             const Bucket &b = e->buckets[i];
             const int k = (int)(i - c0);
             m.type[k] = b.type; m.first[k] = b.first; m.count[k] = b.count; m.blockStart[k] = blocks;
             m.arrays[k] = e->dev[b.type].arrays;
-            blocks += nblk(b.count, kProjectThreads);
+            blocks += nblk(b.count, block);
         }
         for (int k = m.nSeg; k <= kMultiSegments; k++) m.blockStart[k] = blocks;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kProjectThreads); cfg.stream = s;
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(block); cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
