@@ -143,6 +143,27 @@ class ClockSampler:
         self.idx = gpu_index; self.p = None
 
     def start(self):
+        # NVML in a thread (a sample every ~2 ms: the timed region of the default run is only tens of milliseconds long);
+        # nvidia-smi -lms as the fallback when NVML cannot be used
+        self.samples = []; self.thread = None; self.stop_flag = False
+        try:
+            import pynvml, threading
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True); self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -150,6 +171,15 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if getattr(self, "thread", None) is not None:
+            self.stop_flag = True; self.thread.join(timeout=2)
+            sm = sorted(c for c, _, _ in self.samples)
+            bits = 0
+            for _, _, r in self.samples:
+                bits |= r
+            names = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))  # nvml.h nvmlClocksEventReason*
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples else None,
+                    "samples": len(sm), "reasons": sorted(n for n, b in names if bits & b), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -171,7 +201,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def measured_peak():
