@@ -46,6 +46,9 @@ const float *pbdm_vertices(pbdm_model *m);  /* zero-copy view of m_x (pyPBD getV
  * pbdm_add_constraint(PBD_RB_PARTICLE_BALLJOINT, {rb, particle}, NULL). */
 unsigned pbdm_add_rigid_body(pbdm_model *m, float mass, const float *x3, const float *inertia3, const float *q4);
 unsigned pbdm_num_rigid_bodies(pbdm_model *m);
+/* RigidBody::setMass (RigidBody.h:277-284): invMass = mass != 0 ? 1 / mass : 0; a body with mass 0 is static */
+int pbdm_set_rigid_body_mass(pbdm_model *m, unsigned i, float mass);
+float pbdm_get_rigid_body_mass(pbdm_model *m, unsigned i);
 void pbdm_get_rigid_bodies(pbdm_model *m, float *out13);  /* per body: x(3) q(w,x,y,z) v(3) omega(3) */
 
 /* constraints */

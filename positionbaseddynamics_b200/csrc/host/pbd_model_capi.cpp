@@ -92,6 +92,17 @@ unsigned pbdm_add_rigid_body(pbdm_model *m, float mass, const float *x3, const f
     return (unsigned)m->model.getRigidBodies().size() - 1;
 }
 unsigned pbdm_num_rigid_bodies(pbdm_model *m) { return (unsigned)m->model.getRigidBodies().size(); }
+int pbdm_set_rigid_body_mass(pbdm_model *m, unsigned i, float mass) {
+    auto &rbs = m->model.getRigidBodies();
+    if (i >= rbs.size()) return 1;
+    rbs[i]->m_mass = mass; rbs[i]->m_invMass = (mass != 0.0f) ? 1.0f / mass : 0.0f;
+    m->model.rigidBodiesDirty = true;
+    return 0;
+}
+float pbdm_get_rigid_body_mass(pbdm_model *m, unsigned i) {
+    auto &rbs = m->model.getRigidBodies();
+    return i < rbs.size() ? rbs[i]->m_mass : 0.0f;
+}
 void pbdm_get_rigid_bodies(pbdm_model *m, float *out) {
     const auto &rbs = m->model.getRigidBodies();
     for (size_t i = 0; i < rbs.size(); i++) {

@@ -12,7 +12,7 @@ MODEL_SYMBOLS = [
     "pbdm_model_create", "pbdm_model_destroy", "pbdm_model_reset", "pbdm_model_cleanup", "pbdm_add_regular_triangle_model",
     "pbdm_add_regular_tet_model", "pbdm_add_triangle_model", "pbdm_add_tet_model", "pbdm_num_particles", "pbdm_set_mass",
     "pbdm_get_mass", "pbdm_get_inv_mass", "pbdm_get_masses", "pbdm_get_particle", "pbdm_set_particle", "pbdm_get_particles", "pbdm_set_particles",
-    "pbdm_vertices", "pbdm_add_rigid_body", "pbdm_num_rigid_bodies", "pbdm_get_rigid_bodies", "pbdm_add_constraint", "pbdm_add_cloth_constraints", "pbdm_add_bending_constraints",
+    "pbdm_vertices", "pbdm_add_rigid_body", "pbdm_num_rigid_bodies", "pbdm_set_rigid_body_mass", "pbdm_get_rigid_body_mass", "pbdm_get_rigid_bodies", "pbdm_add_constraint", "pbdm_add_cloth_constraints", "pbdm_add_bending_constraints",
     "pbdm_add_solid_constraints", "pbdm_num_constraints", "pbdm_get_constraint", "pbdm_get_constraints",
     "pbdm_init_constraint_groups", "pbdm_num_groups", "pbdm_get_groups", "pbdm_set_model_param", "pbdm_num_triangle_models",
     "pbdm_tri_num_edges", "pbdm_tri_num_faces", "pbdm_tri_index_offset", "pbdm_tri_get_edges", "pbdm_tri_get_faces",
@@ -61,6 +61,8 @@ def _l():
         L.pbdm_add_rigid_body.argtypes = [_vp, _F, _vp, _vp, _vp]; L.pbdm_add_rigid_body.restype = C.c_uint
         L.pbdm_num_rigid_bodies.argtypes = one; L.pbdm_num_rigid_bodies.restype = C.c_uint
         L.pbdm_get_rigid_bodies.argtypes = [_vp, _vp]
+        L.pbdm_set_rigid_body_mass.argtypes = [_vp, C.c_uint, _F]
+        L.pbdm_get_rigid_body_mass.argtypes = [_vp, C.c_uint]; L.pbdm_get_rigid_body_mass.restype = C.c_float
         L.pbdm_add_cloth_constraints.argtypes = [_vp, C.c_uint, C.c_uint, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int]
         L.pbdm_add_bending_constraints.argtypes = [_vp, C.c_uint, C.c_uint, _F]
         L.pbdm_add_solid_constraints.argtypes = [_vp, C.c_uint, C.c_uint, _F, _F, _F, C.c_int, C.c_int]
@@ -160,6 +162,13 @@ class HostModel:
 
     def add_rigid_body(self, mass, x, inertia, q=(1, 0, 0, 0)):
         return _l().pbdm_add_rigid_body(self._h, float(mass), _p(_f32(x)), _p(_f32(inertia)), _p(_f32(q)))
+
+    def set_rigid_body_mass(self, i, mass):
+        if _l().pbdm_set_rigid_body_mass(self._h, int(i), float(mass)):
+            raise PbdError("rigid body index %d out of range" % i)
+
+    def rigid_body_mass(self, i):
+        return float(_l().pbdm_get_rigid_body_mass(self._h, int(i)))
 
     def add_ball_joint(self, rb0, rb1, pos):
         return self.add_constraint(_capi.BALLJOINT, [rb0, rb1], list(pos))

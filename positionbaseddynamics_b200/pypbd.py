@@ -9,6 +9,7 @@ Covers the calls the reference's own example scripts make for the accelerated pa
   TimeStepController.NUM_SUB_STEPS/MAX_ITERATIONS/..., ts.setValueUInt/getValueUInt/setValueInt, ts.step(model).
 GUI, scene files, rigid bodies and collision detection are not part of this path.
 """
+import math
 import numpy as np
 from . import _capi, model as _m
 from ._capi import PbdError  # noqa: F401
@@ -83,6 +84,35 @@ class TetModel:
     def updateMeshNormals(self, pd): pass  # rendering helper of the reference
 
 
+def mass_properties(vertices, faces, density):
+    """Mass, centre of mass and inertia tensor (about the centre of mass) of the closed triangle mesh, as
+    Utilities::VolumeIntegration (Utils/VolumeIntegration.cpp) provides them to RigidBody::determineMassProperties
+    (Simulation/RigidBody.h:209-262): exact polyhedral integrals, here summed over signed tetrahedra from the origin."""
+    v = np.asarray(vertices, dtype=np.float64).reshape(-1, 3); f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    vol6 = np.einsum("ij,ij->i", a, np.cross(b, c))              # 6 x signed tetra volume
+    vol = vol6.sum() / 6.0
+    com = (vol6[:, None] * (a + b + c)).sum(axis=0) / (24.0 * vol)
+    s = a + b + c
+    cov = (vol6[:, None, None] * (s[:, :, None] * s[:, None, :] + a[:, :, None] * a[:, None, :] + b[:, :, None] * b[:, None, :]
+                                  + c[:, :, None] * c[:, None, :])).sum(axis=0) / 120.0   # integral of x x^T
+    cov -= vol * np.outer(com, com)
+    inertia = density * (np.trace(cov) * np.eye(3) - cov)
+    return density * vol, com, inertia
+
+
+class RigidBody:
+    """View of one rigid body of the model (pyPBD RigidBodyModule.cpp subset: what the coupling example touches)."""
+    def __init__(self, host, idx): self._h, self._i = host, idx
+    def _row(self): return self._h.rigid_bodies()[self._i]
+    def setMass(self, mass): self._h.set_rigid_body_mass(self._i, mass)
+    def getMass(self): return self._h.rigid_body_mass(self._i)
+    def getPosition(self): return self._row()[0:3].copy()
+    def getRotation(self): return self._row()[3:7].copy()        # (w, x, y, z)
+    def getVelocity(self): return self._row()[7:10].copy()
+    def getAngularVelocity(self): return self._row()[10:13].copy()
+
+
 class SimulationModel:
     def __init__(self):
         self._host = _m.HostModel()
@@ -132,6 +162,42 @@ class SimulationModel:
 
     def addSolidConstraints(self, tm, solidMethod, stiffness, poissonRatio, volumeStiffness, normalizeStretch, normalizeShear):
         self._host.add_solid_constraints(tm._i, solidMethod, stiffness, poissonRatio, volumeStiffness, normalizeStretch, normalizeShear)
+
+    # ---- rigid bodies coupled through ball joints (pyPBD SimulationModelModule.cpp:306-376, 396-420) -------------------
+    def addRigidBody(self, density, vertices, mesh, translation=(0, 0, 0), rotation=np.eye(3), scale=(1, 1, 1), testMesh=False,
+                     generateCollisionObject=False, resolution=None, sdf=None):
+        """RigidBody::initBody(density, x, rotation, vertices, mesh, scale): mass and principal inertia from the scaled mesh, the body
+        frame moved to the centre of mass and rotated into the principal axes (RigidBody.h:122-262).  `vertices` is an (n, 3) array,
+        `mesh` an (m, 3) face array (or an object with getFaces()).  Collision objects / signed distance fields are outside this
+        engine's path: requesting them is refused.  For repeated eigenvalues (cube, sphere) the principal frame is not unique; it may
+        differ from Eigen's choice without changing the dynamics."""
+        self._no_collision(testMesh)
+        if generateCollisionObject or sdf is not None:
+            raise _capi.PbdError("collision objects need the reference's collision detection, which is outside this engine's path")
+        faces = np.asarray(mesh.getFaces() if hasattr(mesh, "getFaces") else mesh).reshape(-1, 3)
+        v = np.asarray(vertices, dtype=np.float64).reshape(-1, 3) * np.asarray(scale, dtype=np.float64)
+        mass, com, J = mass_properties(v, faces, float(density))
+        w, R = np.linalg.eigh(J)
+        if np.linalg.det(R) < 0.0:
+            R = -R
+        R0 = np.asarray(rotation, dtype=np.float64).reshape(3, 3)
+        x = R0 @ com + np.asarray(translation, dtype=np.float64)
+        Rw = R0 @ R
+        # rotation matrix -> unit quaternion (w, x, y, z)
+        q = np.empty(4); t = np.trace(Rw)
+        if t > 0.0:
+            r = math.sqrt(1.0 + t); q[0] = 0.5 * r; r = 0.5 / r
+            q[1] = (Rw[2, 1] - Rw[1, 2]) * r; q[2] = (Rw[0, 2] - Rw[2, 0]) * r; q[3] = (Rw[1, 0] - Rw[0, 1]) * r
+        else:
+            i = int(np.argmax(np.diag(Rw))); j = (i + 1) % 3; k = (i + 2) % 3
+            r = math.sqrt(1.0 + Rw[i, i] - Rw[j, j] - Rw[k, k]); q[1 + i] = 0.5 * r; r = 0.5 / r
+            q[0] = (Rw[k, j] - Rw[j, k]) * r; q[1 + j] = (Rw[j, i] + Rw[i, j]) * r; q[1 + k] = (Rw[k, i] + Rw[i, k]) * r
+        idx = self._host.add_rigid_body(mass, x, w, q / np.linalg.norm(q))
+        return RigidBody(self._host, idx)
+
+    def getRigidBodies(self): return [RigidBody(self._host, i) for i in range(len(self._host.rigid_bodies()))]
+    def addBallJoint(self, rbIndex1, rbIndex2, pos): return bool(self._host.add_ball_joint(rbIndex1, rbIndex2, pos))
+    def addRigidBodyParticleBallJoint(self, rbIndex, particleIndex): return bool(self._host.add_rb_particle_ball_joint(rbIndex, particleIndex))
 
     def addDistanceConstraint(self, p1, p2, k): return bool(self._host.add_constraint(_capi.DISTANCE, [p1, p2], [k]))
     def addDistanceConstraint_XPBD(self, p1, p2, k): return bool(self._host.add_constraint(_capi.DISTANCE_XPBD, [p1, p2], [k]))

@@ -96,3 +96,79 @@ def test_example_scripts_run():
             assert (out[name][i] == np.asarray(pd.getPosition0(i), dtype=np.float32)).all()
         assert out[name][:, 1].min() < -1e-3               # the rest sags under gravity
     assert pbd.Timing.averageStepMs() > 0.0
+
+
+CUBE_V = np.array([[-0.5, -0.5, -0.5], [0.5, -0.5, -0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, -0.5],
+                   [-0.5, -0.5, 0.5], [0.5, -0.5, 0.5], [0.5, 0.5, 0.5], [-0.5, 0.5, 0.5]])
+CUBE_F = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5], [0, 4, 7], [0, 7, 3]])
+
+
+def test_mass_properties_and_rigid_body_facade():
+    """pyPBD's addRigidBody(density, vertices, mesh, ...) derives mass, centre of mass and principal inertia from the mesh
+    (RigidBody::determineMassProperties); checked against the closed forms of a box and of a tetrahedron."""
+    import positionbaseddynamics_b200.pypbd as pbd
+    w, h, d = 0.4, 2.0, 0.6
+    m, c, J = pbd.mass_properties(CUBE_V * [w, h, d] + [1.0, -2.0, 3.0], CUBE_F, 2.5)
+    assert np.isclose(m, 2.5 * w * h * d) and np.allclose(c, [1.0, -2.0, 3.0])
+    assert np.allclose(J, np.diag([m / 12 * (h * h + d * d), m / 12 * (w * w + d * d), m / 12 * (w * w + h * h)]), atol=1e-12)
+    tet_v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]]); tet_f = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]])
+    m, c, J = pbd.mass_properties(tet_v, tet_f, 6.0)
+    assert np.isclose(m, 1.0) and np.allclose(c, [0.25, 0.25, 0.25])
+    assert np.isclose(J[0, 0], 6.0 * (1 / 60 + 1 / 60) - 2 * 0.25 ** 2)          # int(y^2 + z^2) about the origin, shifted to the centre of mass
+    pbd.Simulation._current = None
+    sim = pbd.Simulation.getCurrent(); sim.initDefault(); model = sim.getModel()
+    a = model.addRigidBody(1.0, CUBE_V, CUBE_F, translation=[-5.0, 0.0, -5.0], scale=[0.5, 0.5, 0.5], testMesh=False, generateCollisionObject=False)
+    a.setMass(0.0)
+    b = model.addRigidBody(1.0, CUBE_V, CUBE_F, [-5.0, 1.0, -5.0], scale=[w, h, d])
+    assert a.getMass() == 0.0 and np.isclose(b.getMass(), w * h * d) and np.allclose(b.getPosition(), [-5.0, 1.0, -5.0])
+    assert np.isclose(np.linalg.norm(b.getRotation()), 1.0) and len(model.getRigidBodies()) == 2
+    tri = model.addRegularTriangleModel(4, 4, [0, 0, 0], np.eye(3), [1, 1])
+    assert model.addBallJoint(0, 1, [-5.0, 0.0, -5.0]) and model.addRigidBodyParticleBallJoint(1, 0)
+    assert model.numConstraints() == 2
+    with pytest.raises(pbd.PbdError):
+        model.addRigidBody(1.0, CUBE_V, CUBE_F, generateCollisionObject=True)
+
+
+@pytest.mark.gpu
+def test_coupling_example_against_the_reference(cpu_libs):
+    """examples/rigid_body_cloth_coupling.py (pyPBD-style construction incl. mesh-derived mass properties) stepped on the GPU, against
+    the unmodified reference given the same bodies (mass, position, principal inertia, rotation)."""
+    import importlib.util, os
+    import positionbaseddynamics_b200.pypbd as pbd
+    from conftest import have_ref
+    if not have_ref("f64"):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_f64.so not present on this box")
+    pbd.Simulation._current = None
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+    spec = importlib.util.spec_from_file_location("rigid_body_cloth_coupling", os.path.join(root, "rigid_body_cloth_coupling.py"))
+    ex = importlib.util.module_from_spec(spec); spec.loader.exec_module(ex)
+    model = ex.buildModel()
+    host = model._host
+    ref = cpu_libs.CpuPbd("ref", "f64")
+    ref.add_regular_triangle_model(ex.nCols, ex.nRows, [-5, 4, -5], ex.rotation_x(np.pi * 0.5), [ex.clothWidth, ex.clothHeight])
+    ref.add_cloth_constraints(0, 2, 1.0, 1.0, 1.0, 1.0, 0.3, 0.3)
+    ref.add_bending_constraints(0, 2, 0.01)
+    rb = host.rigid_bodies()
+    dims = {0: (0.5, 0.5, 0.5)}
+    for i in range(len(rb)):
+        mass = host.rigid_body_mass(i)
+        w, h, d = (0.5, 0.5, 0.5) if i % 3 == 0 else (ex.width, ex.height, ex.depth)
+        m = w * h * d
+        inertia = np.sort([m / 12 * (h * h + d * d), m / 12 * (w * w + d * d), m / 12 * (w * w + h * h)])  # principal moments, ascending like eigh
+        ref.add_rigid_body(mass, rb[i, 0:3], inertia, rb[i, 3:7])
+    for chain in range(4):
+        base = 3 * chain; x, z = rb[base, 0], rb[base, 2]
+        ref.add_ball_joint(base, base + 1, [x, 0.0, z]); ref.add_ball_joint(base + 1, base + 2, [x, 2.0, z])
+    for body, particle in ((2, 0), (5, ex.nCols - 1), (8, ex.nRows * ex.nCols - 1), (11, (ex.nRows - 1) * ex.nCols)):
+        ref.add_rb_particle_ball_joint(body, particle)
+    ref.set_params(dt=0.005, sub_steps=3, max_iter=1)
+    assert ref.num_constraints() == model.numConstraints()
+    sim = pbd.Simulation.getCurrent()
+    for _ in range(6):
+        sim.getTimeStep().step(model)
+    ref.step(6)
+    xg = model.getParticles().getVertices(); xc = ref.get("x")
+    err = np.abs(xg - xc).max() / np.abs(xc).max()
+    print("coupling example vs reference: rel pos %.2e" % err)
+    assert err <= 1e-4
+    assert np.abs(host.rigid_bodies()[:, :3] - ref.rigid_bodies()[:, :3]).max() <= 1e-4
