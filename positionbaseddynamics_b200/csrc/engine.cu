@@ -1183,7 +1183,7 @@ static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long 
         if (pt == 1024) return launch_tiled<kMaskClothXPBD, 1024>(e, s, ta);
         if (pt == 768) return launch_tiled<kMaskClothXPBD, 768>(e, s, ta);
         if (pt == 512) return launch_tiled<kMaskClothXPBD, 512>(e, s, ta);
-        return launch_tiled<kMaskClothXPBD, 640>(e, s, ta);  // measured best on cfg2 (profiles/README.md section 6)
+        return launch_tiled<kMaskClothXPBD, 640>(e, s, ta);  // measured best on cfg2 (profiles/README.md section 4)
     }
     if ((present & ~kMaskLight) == 0) return launch_tiled<kMaskLight, 512>(e, s, ta);
     return launch_tiled<kMaskAll, 512>(e, s, ta);
