@@ -171,6 +171,12 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        try:
+            return self._stop()
+        except Exception as ex:  # never let the clock report break the measurement
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling failed: %s" % ex]}
+
+    def _stop(self):
         if getattr(self, "thread", None) is not None:
             self.stop_flag = True; self.thread.join(timeout=2)
             sm = sorted(c for c, _, _ in self.samples)
