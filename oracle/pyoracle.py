@@ -120,6 +120,14 @@ class CpuPbd:
         self.f("add_rigid_body").restype = C.c_uint
         return self.f("add_rigid_body")(_D(mass), _dp(_f64(x)), _dp(_f64(inertia)), _dp(_f64(q)))
 
+    def add_rigid_body_mesh(self, density, verts, faces, x=(0, 0, 0), R=np.eye(3), scale=(1, 1, 1)):
+        """ref only: RigidBody::initBody(density, x, rotation, vertices, mesh, scale); returns (index, [mass, inertia(3), x(3), q(w,x,y,z)])."""
+        assert self.kind != "oracle"
+        v = _f64(verts).reshape(-1, 3); f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        i = self.lib.ref_add_rigid_body_mesh(_D(density), len(v), _dp(v), len(f), f.ctypes.data_as(C.c_void_p), _dp(_f64(x)), _dp(_f64(R)), _dp(_f64(scale)))
+        out = np.zeros(11); self.lib.ref_get_rigid_body_props(i, _dp(out))
+        return i, out
+
     def add_ball_joint(self, rb0, rb1, pos):
         return self.add_constraint(BALLJOINT, [rb0, rb1], list(pos))
 

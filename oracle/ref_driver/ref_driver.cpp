@@ -129,6 +129,30 @@ unsigned ref_add_rigid_body(double mass, const double *x, const double *inertia,
     g_model->m_groupsInitialized = false;
     return (unsigned)g_model->getRigidBodies().size() - 1;
 }
+// RigidBody::initBody(density, x, rotation, vertices, mesh, scale) (Simulation/RigidBody.h:122-150): mass properties from the
+// mesh (Utils/VolumeIntegration.cpp), body frame moved to the centre of mass and the principal axes.  R row-major.
+unsigned ref_add_rigid_body_mesh(double density, unsigned nV, const double *verts, unsigned nF, const unsigned *faces,
+                                 const double *x, const double *R, const double *scale) {
+    VertexData vd;
+    for (unsigned i = 0; i < nV; i++) vd.addVertex(v3(verts + 3 * i));
+    Utilities::IndexedFaceMesh mesh;
+    mesh.initMesh(nV, nF * 2, nF);
+    for (unsigned i = 0; i < nF; i++) mesh.addFace(faces + 3 * i);
+    mesh.buildNeighbors();
+    RigidBody *rb = new RigidBody();
+    rb->initBody((Real)density, v3(x), Quaternionr(m3(R)), vd, mesh, v3(scale));
+    g_model->getRigidBodies().push_back(rb);
+    g_model->m_groupsInitialized = false;
+    return (unsigned)g_model->getRigidBodies().size() - 1;
+}
+// mass, principal inertia (3), position (3), rotation (w, x, y, z)
+void ref_get_rigid_body_props(unsigned i, double *out) {
+    RigidBody *rb = g_model->getRigidBodies()[i];
+    out[0] = rb->getMass();
+    for (int k = 0; k < 3; k++) { out[1 + k] = rb->getInertiaTensor()[k]; out[4 + k] = rb->getPosition()[k]; }
+    const Quaternionr &q = rb->getRotation();
+    out[7] = q.w(); out[8] = q.x(); out[9] = q.y(); out[10] = q.z();
+}
 unsigned ref_num_rigid_bodies() { return (unsigned)g_model->getRigidBodies().size(); }
 void ref_get_rigid_bodies(double *out) {
     auto &rbs = g_model->getRigidBodies();
