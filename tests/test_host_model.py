@@ -138,3 +138,38 @@ def test_rigid_coupling_structure_equals_oracle(cpu_libs):
     assert (gh[0] == go[0]).all() and (gh[1] == go[1]).all()
     assert np.allclose(h.rigid_bodies(), o.rigid_bodies(), atol=1e-7)
     h.close()
+
+
+def _build_cpp_demo(tmp_path):
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cloth_demo")
+    pkg = os.path.join(root, "positionbaseddynamics_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I" + root, os.path.join(root, "examples", "cloth_demo.cpp"), "-L" + pkg, "-lpbd_b200",
+                           "-Wl,-rpath," + pkg, "-o", exe])
+    return exe
+
+
+def test_cpp_cloth_demo_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/cloth_demo.cpp = Demos/ClothDemo/main.cpp against the C++ host mirror (csrc/host/pbd_model.h, the reference's class and
+    method names).  It must compile and link against libpbd_b200.so, build the demo's scene, and -- here, without a CUDA device --
+    stop with the engine's "no CPU fallback" message instead of computing anything on the host."""
+    import subprocess, torch
+    exe = _build_cpp_demo(tmp_path)
+    r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=120)
+    assert "Number of triangles: 4802" in r.stdout and "Number of constraints: 11907" in r.stdout
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "centroid" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_cloth_demo_runs_on_the_gpu(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_cpp_demo(tmp_path), "40"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("Time:")][0].split()
+    assert abs(float(line[1]) - 0.2) < 1e-5                     # 40 steps of 0.005
+    cx, cy, cz = (float(v) for v in line[3:6])
+    assert abs(cx - 5.0) < 0.1 and -5.0 < cy < 1.0 - 0.01 and abs(cz - 5.0) < 1.0   # the sheet (hung at y = 1 by one edge) starts to fall
