@@ -3,7 +3,8 @@
  * Drop-in seam: this is what a `PBD::TimeStep` subclass on the reference side binds to replace
  * `TimeStepController::step` (Simulation/TimeStepController.cpp:75-241; seam: Simulation/TimeStep.h:13-48,
  * installed via Simulation::setTimeStep, Simulation/Simulation.h:48-49).  The reference-side adapter that
- * flattens a `PBD::SimulationModel` into these calls is shown in INTEGRATION.md.
+ * flattens a `PBD::SimulationModel` into these calls is integration/GpuTimeStepController.h (compiled inside the
+ * unmodified reference by oracle/Makefile and parity-tested).
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success, non-zero on error
  * (the reference's own convention is bool/void with no exceptions, Simulation/SimulationModel.cpp:565-575);
@@ -122,13 +123,14 @@ int pbd_set_bucket_sort(pbd_engine *e, int enable);
 /* nSteps x TimeStepController::step, asynchronous on the engine's stream. */
 int pbd_step(pbd_engine *e, unsigned nSteps);
 int pbd_sync(pbd_engine *e);
-/* End-to-end convenience used by host-buffer callers: upload x and v (3 floats/particle each, pinned or pageable),
- * run nSteps, download x (and v if v_out != NULL), synchronise. */
 /* Page-lock caller-owned host arrays (e.g. the reference's std::vector<Vector3r> storage) so that pbd_step_host copies at full
  * PCIe speed straight from / into them; unpin before the memory is freed or reallocated.  Thin wrappers over cudaHostRegister,
  * exported so that a reference-side adapter needs no CUDA headers. */
 int pbd_pin_host(void *ptr, size_t bytes);
 int pbd_unpin_host(void *ptr);
+/* End-to-end convenience used by host-buffer callers (what the TimeStep adapter calls once per step): upload x and v
+ * (3 floats/particle each, pinned or pageable; NULL = keep the device state), run nSteps, download x (and v if
+ * v_out != NULL), synchronise.  Input and output buffers may be the same arrays. */
 int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out);
 
 int pbd_get_lambdas(pbd_engine *e, int type, float *dst, unsigned *ids); /* debug: per-type XPBD multipliers + insertion ids */
