@@ -372,10 +372,17 @@ def run_b200(args):
         eng.set_mode(mode)
     achieved = (roof["bytes_per_launch"] / (roof["ms_per_launch"] * 1e-3)) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram__bytes_read+write per launch from the committed ncu --set full capture
+    # dram__bytes_read + dram__bytes_write of ONE captured launch of the dominant kernel (committed ncu --set full capture) together
+    # with the number of constraints that launch processed; scaled to the average launch `achieved` is quoted for
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(WORKLOAD, {}).get(roof["kernel"])
+            t = json.load(open(tpath)).get(WORKLOAD, {}).get(roof["kernel"])
+            if isinstance(t, dict):
+                per_launch = st.constraints_per_type[dom] * args.iters * sub_steps / max(roof.get("launches_per_step", 1), 1)
+                traffic = t["dram_bytes"] / t["constraints_in_launch"] * per_launch
+            elif t is not None:
+                traffic = float(t)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
