@@ -266,6 +266,7 @@ public:
 
 private:
     bool pushConstraint(int type, const unsigned int *bodies, const Real *params, bool ok);
+    void reserveConstraints(int type, size_t count);
     void setParam(int type, int slot, Real val);
     ParticleData m_particles;
     RigidBodyVector m_rigidBodies;
