@@ -982,7 +982,12 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
 
 // all buckets [b0, b1) belong to one colour: one launch for up to kMultiSegments of them
 static int launch_colour(pbd_engine *e, size_t b0, size_t b1, float h, int iterZero, cudaStream_t s, unsigned long long *launches) {
-    if (b1 - b0 == 1 || !e->mergeColours) {
+    // One launch per colour pays off when the colour is small (latency-bound phases: cfg3 14.3 -> 10.65 ms); a large colour is
+    // better served by the specialised single-type kernels (cfg2, 250k-constraint colours: 2.92 -> 2.85 ms without merging).
+    constexpr unsigned kMergeMaxConstraints = 65536;
+    unsigned colourTotal = 0;
+    for (size_t i = b0; i < b1; i++) colourTotal += e->buckets[i].count;
+    if (b1 - b0 == 1 || !e->mergeColours || colourTotal > kMergeMaxConstraints) {
         for (size_t i = b0; i < b1; i++) { CKE(launch_bucket(e, e->buckets[i], h, iterZero, s)); (*launches)++; }
         return 0;
     }
