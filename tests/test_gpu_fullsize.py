@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import scenes
-from parity_util import rel_position_error
+from parity_util import perturb, rel_position_error, assert_parity, assert_gate_rejects
 from conftest import have_ref
 
 pytestmark = pytest.mark.gpu
@@ -17,41 +17,82 @@ def _gpu(build, mode=0):
     return m
 
 
-def test_cfg2_full_size_two_steps_vs_fp64(cpu_libs):
-    """cfg2 at the benchmark size (1,000,000 particles, 5,988,006 constraints, 20 iterations): structure equal to the
-    checker's bit for bit, positions within 1e-4 relative after 2 steps.  fp64 checker = the unmodified reference when the
-    prebuilt oracle/_ref is on this box, else the C restatement."""
-    kind = "ref" if have_ref("f64") else "oracle"
-    cpu = cpu_libs.CpuPbd(kind, "f64"); cpu.set_threads(16)
-    gpu = _gpu(lambda m: scenes.cfg2(m, 1000, 20))
-    scenes.cfg2(cpu, 1000, 20)
-    assert gpu.num_constraints() == cpu.num_constraints() == 5988006
+def _particles_only(kind):
+    """The scene's particles, pins and time-step parameters WITHOUT any constraint: stepping it integrates and updates velocities
+    only -- what an engine whose projection kernels did nothing would produce (negative control of the parity gate)."""
+    from positionbaseddynamics_b200.model import HostModel
+    m = HostModel()
+    if kind in ("cfg2", "cfg5"):
+        n = 1000 if kind == "cfg2" else 500
+        m.add_regular_triangle_model(n, n, t=(0, 1, 0), R=scenes.RX90, scale=(10.0, 10.0))
+        m.set_mass(0, 0.0); m.set_mass(n - 1, 0.0)
+        m.set_params(dt=0.005, sub_steps=1, max_iter=20)
+    elif kind == "cfg3":
+        w, h, d = 101, 21, 21
+        m.add_regular_tet_model(w, h, d, t=(5, 0, 0), R=np.eye(3), scale=(10.0, 1.5, 1.5))
+        for j in range(h):
+            for k in range(d):
+                m.set_mass(j * d + k, 0.0)
+        m.set_params(dt=0.005, sub_steps=10, max_iter=5)
+    return m
+
+
+def _full_size_case(name, build, amp, steps, cpu, control=None):
+    """Perturbed start state (seeded, identical fp32 values on both sides), `steps` steps, then the discriminating gate:
+    <= 1e-4 of the scene size AND <= 5e-3 of the largest displacement; the untouched start state and a projection-free step must
+    both FAIL the same gate."""
+    gpu = _gpu(build)
+    build(cpu)
+    assert gpu.num_constraints() == cpu.num_constraints()
     og, ig = gpu.groups(); oc, ic = cpu.groups()
     assert (og == oc).all() and (ig == ic).all()
-    assert list(np.diff(og))[:4] == [500000, 499999, 499499, 498004]
-    gpu.step(2); cpu.step(2)
+    x_start = perturb([gpu, cpu], amp)
+    gpu.step(steps); cpu.step(steps)
     xg, xc = gpu.get("x"), cpu.get("x")
-    e = rel_position_error(xg, xc)
-    moved = np.abs(xc - cpu.get("x0")).max()
-    print("cfg2 full size: rel pos %.2e (max displacement %.3e, abs err %.2e)" % (e, moved, np.abs(xg - xc).max()))
-    assert e <= 1e-4
+    e_pos, e_disp = assert_parity(xg, xc, x_start, what=name)
+    moved = np.abs(np.asarray(xc, dtype=np.float64) - x_start).max()
+    print("%s full size, perturbed by %.1e: rel pos %.2e, rel to displacement %.2e (max displacement %.3e, abs err %.2e)"
+          % (name, amp, e_pos, e_disp, moved, np.abs(xg - xc).max()))
+    assert_gate_rejects(x_start, xc, x_start, what=name + " / untouched start state")
+    if control is not None:
+        twin = _particles_only(control)
+        twin.set("x", x_start)
+        twin.step(steps)
+        assert_gate_rejects(twin.get("x"), xc, x_start, what=name + " / step without projections")
+        twin.close()
+    return gpu, og
+
+
+def test_cfg2_full_size_two_steps_vs_fp64(cpu_libs):
+    """cfg2 at the benchmark size (1,000,000 particles, 5,988,006 constraints, 20 iterations): structure equal to the
+    checker's bit for bit; from a perturbed state (20 % of the edge length) positions within 1e-4 relative and within 5e-3 of the
+    displacement after 2 steps.  fp64 checker = the unmodified reference when the prebuilt oracle/_ref is on this box, else the
+    C restatement."""
+    kind = "ref" if have_ref("f64") else "oracle"
+    cpu = cpu_libs.CpuPbd(kind, "f64"); cpu.set_threads(16)
+    gpu, og = _full_size_case("cfg2", lambda m: scenes.cfg2(m, 1000, 20), 2.0e-3, 2, cpu, control="cfg2")
+    assert gpu.num_constraints() == 5988006
+    assert list(np.diff(og))[:4] == [500000, 499999, 499499, 498004]
+    xg = gpu.get("x")
     # pinned corners (particles 0 and 999) never move
     assert (xg[0] == gpu.get("x0")[0]).all() and (xg[999] == gpu.get("x0")[999]).all()
     gpu.close()
 
 
+def test_cfg5_size_two_steps_vs_fp64(cpu_libs):
+    """cfg5's per-GPU scene (500x500 cloth, 1,494,006 constraints, XPBD 1 x 20) against the fp64 checker, perturbed."""
+    kind = "ref" if have_ref("f64") else "oracle"
+    cpu = cpu_libs.CpuPbd(kind, "f64"); cpu.set_threads(16)
+    gpu, og = _full_size_case("cfg5", lambda m: scenes.cfg2(m, 500, 20), 4.0e-3, 2, cpu, control="cfg5")
+    assert gpu.num_constraints() == 748001 + 746005
+    gpu.close()
+
+
 def test_cfg3_full_size_one_step_vs_fp64(cpu_libs):
-    """cfg3 at the benchmark size (200,000 tets, FEMTet E=1e6 + Volume, 10 substeps x 5 iterations): one step."""
+    """cfg3 at the benchmark size (200,000 tets, FEMTet E=1e6 + Volume, 10 substeps x 5 iterations): one step from a perturbed state."""
     cpu = cpu_libs.CpuPbd("oracle", "f64"); cpu.set_threads(16)
-    gpu = _gpu(scenes.cfg3)
-    scenes.cfg3(cpu)
-    assert gpu.num_constraints() == cpu.num_constraints() == 400000
-    og, ig = gpu.groups(); oc, ic = cpu.groups()
-    assert (og == oc).all() and (ig == ic).all() and len(og) - 1 == 74
-    gpu.step(1); cpu.step(1)
-    e = rel_position_error(gpu.get("x"), cpu.get("x"))
-    print("cfg3 full size: rel pos %.2e" % e)
-    assert e <= 1e-4
+    gpu, og = _full_size_case("cfg3", scenes.cfg3, 4.0e-3, 1, cpu, control="cfg3")
+    assert gpu.num_constraints() == 400000 and len(og) - 1 == 74
     gpu.close()
 
 
@@ -127,18 +168,14 @@ def test_free_fall_of_an_unpinned_sheet_is_rigid():
 
 def test_cfg4_full_size_vs_fp64(cpu_libs):
     """cfg4 at the benchmark size: 224x224 cloth (FEMTriangle + IsometricBending) + 51x21x11 tet block (FEMTet) + the rigid
-    coupling rig, 5 substeps x 1 iteration; two steps against the fp64 checker."""
+    coupling rig, 5 substeps x 1 iteration; two steps from a perturbed state against the fp64 checker (particles and rigid bodies)."""
     cpu = cpu_libs.CpuPbd("oracle", "f64"); cpu.set_threads(16)
-    gpu = _gpu(scenes.cfg4)
-    scenes.cfg4(cpu)
-    assert gpu.num_constraints() == cpu.num_constraints()
-    og, ig = gpu.groups(); oc, ic = cpu.groups()
-    assert (og == oc).all() and (ig == ic).all()
-    gpu.step(2); cpu.step(2)
-    e = rel_position_error(gpu.get("x"), cpu.get("x"))
-    erb = np.abs(gpu.rigid_bodies().astype(np.float64)[:, :7] - cpu.rigid_bodies()[:, :7]).max()
-    print("cfg4 full size: %d constraints, %d colours, particles rel %.2e, rigid bodies abs %.2e" % (gpu.num_constraints(), len(og) - 1, e, erb))
-    assert e <= 1e-4 and erb <= 1e-4
+    rb_start = None
+    gpu, og = _full_size_case("cfg4", scenes.cfg4, 2.0e-3, 2, cpu)
+    rg, rc = gpu.rigid_bodies().astype(np.float64)[:, :7], cpu.rigid_bodies()[:, :7]
+    erb = np.abs(rg - rc).max()
+    print("cfg4 full size: %d constraints, %d colours, rigid bodies abs %.2e" % (gpu.num_constraints(), len(og) - 1, erb))
+    assert erb <= 1e-4
     gpu.close()
 
 

@@ -15,7 +15,7 @@ from conftest import have_ref
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4       # relative on positions (north_star)
-TOL_DISP = 2e-2  # relative to the distance the particles moved in the test (reported, loosely gated)
+TOL_DISP = 5e-3  # relative to the distance the particles moved in the test (measured 1e-4 ... 1.4e-3)
 
 SCENES = {
     # name: (builder, perturbation amplitude, steps)
@@ -255,7 +255,7 @@ def test_known_answers_against_reference_golden():
             err = np.abs(got[j] - ref).max() / sc
             worst[int(T[i])] = max(worst.get(int(T[i]), 0.0), err)
             # fp32 kernels vs fp64 reference answers on O(1) stencils a few units from the origin
-            assert err <= 2e-3, (int(T[i]), int(i), err, got[j], ref)
+            assert err <= 5e-4, (int(T[i]), int(i), err, got[j], ref)
         eng.close()
     print("GPU known answers, worst relative error per type:", {_capi.TYPE_NAMES[k]: "%.1e" % v for k, v in sorted(worst.items())})
     assert len(worst) == 13
