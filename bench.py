@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1000, help="cloth is size x size particles (cfg2 = 1000)")
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "launch", "tiled"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "resident", "launch"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 is the BASELINE.json metric configuration (default); cfg1/cfg3 are side measurements for DESIGN.md")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -262,7 +262,7 @@ def run_b200(args):
     del types, bodies, params
     hm.close()
 
-    modes = {"graph": _capi.MODE_GRAPH, "persistent": _capi.MODE_PERSISTENT, "launch": _capi.MODE_LAUNCH, "tiled": _capi.MODE_TILED}
+    modes = {"graph": _capi.MODE_GRAPH, "resident": _capi.MODE_RESIDENT, "launch": _capi.MODE_LAUNCH}
     proj_per_step = ncons * sub_steps * args.iters
 
     def timed(mode, steps, warmup):
@@ -280,7 +280,7 @@ def run_b200(args):
     # pick the execution mode on a short probe unless forced
     if args.mode == "auto":
         probe = {}
-        for name in (("graph",) if len(rb) else ("graph", "persistent")):  # the tiled mode is opt-in (--mode tiled): its flatten re-partitions the model
+        for name in ("graph", "resident"):
             try:
                 ms, _ = timed(modes[name], 3, 2)
                 probe[name] = ms
@@ -349,8 +349,9 @@ def run_b200(args):
                 _capi.FEMTRIANGLE: 128.0, _capi.STRAINTRIANGLE: 124.0, _capi.VOLUME: 148.0, _capi.VOLUME_XPBD: 156.0, _capi.FEMTET: 184.0,
                 _capi.FEMTET_XPBD: 192.0, _capi.STRAINTET: 180.0, _capi.SHAPEMATCHING: 240.0}  # DESIGN.md byte table (algorithmic bytes per projection)
     ms_step = ms_max / args.steps
-    if mode_name in ("persistent", "tiled"):
-        roof = {"kernel": "k_step_%s (whole step, one cooperative launch)" % mode_name, "bytes_per_launch": st.bytes_per_step, "ms_per_launch": ms_step}
+    if mode_name == "resident":
+        roof = {"kernel": "k_step_resident (whole step, one cluster launch; event-timed directly)", "bytes_per_launch": st.bytes_per_step, "ms_per_launch": ms_step}
+        dom = -1
     else:
         eng.set_mode(_capi.MODE_LAUNCH)
         eng.step(2); eng.sync()
@@ -375,7 +376,7 @@ def run_b200(args):
     # dram__bytes_read + dram__bytes_write of ONE captured launch of the dominant kernel (committed ncu --set full capture) together
     # with the number of constraints that launch processed; scaled to the average launch `achieved` is quoted for
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and dom >= 0:
         try:
             t = json.load(open(tpath)).get(WORKLOAD, {}).get(roof["kernel"])
             if isinstance(t, dict):

@@ -55,9 +55,9 @@ enum pbd_attr { PBD_ATTR_X = 0, PBD_ATTR_V = 1, PBD_ATTR_X0 = 2, PBD_ATTR_OLDX =
 
 enum pbd_solver_mode {
     PBD_MODE_GRAPH = 0,      /* one kernel per (colour,type) bucket, whole step replayed as a CUDA graph */
-    PBD_MODE_PERSISTENT = 1, /* one cooperative kernel per step; grid-wide barrier between colours */
-    PBD_MODE_LAUNCH = 2,     /* plain stream launches (debug / per-kernel profiling) */
-    PBD_MODE_TILED = 3       /* one cooperative kernel, particle tiles resident in shared memory (particle constraints only) */
+    PBD_MODE_RESIDENT = 1,   /* one launch per step: positions resident in the distributed shared memory of thread-block clusters,
+                                hardware cluster barrier between colours (csrc/resident.cuh); scenes up to ~1.5 M particles */
+    PBD_MODE_LAUNCH = 2      /* plain stream launches (debug / per-kernel profiling) */
 };
 
 typedef struct pbd_stats {

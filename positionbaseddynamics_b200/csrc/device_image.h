@@ -53,6 +53,9 @@ struct Bucket {
 // static per-type shape of the image
 struct TypeShape { int nBodies, nParams, nGeoV, nGeoS, nMat; bool xpbd; };
 
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 inline TypeShape type_shape(int t) {
     switch (t) {
     case PBD_DISTANCE:        return {2, 2, 0, 1, 1, false};
@@ -73,6 +76,8 @@ inline TypeShape type_shape(int t) {
     default:                  return {0, 0, 0, 0, 0, false};
     }
 }
+
+#define type_shape_dev type_shape
 
 // Algorithmic bytes per projection: indices + particle float4 read + per-constraint constants
 // + particle float4 write (+ lambda read/write for XPBD).  Isometric bending uses the rank-1 figure (4 floats Kp).

@@ -4,7 +4,8 @@
 //   * flattening of a constraint list + the reference's colour groups into (colour,type) buckets of SoA arrays,
 //   * the step driver that replaces TimeStepController::step (Simulation/TimeStepController.cpp:75-241) for
 //     particle constraints: per substep  integrate -> maxIterations x (colour by colour, bucket by bucket) -> velocity update,
-//     executed as plain launches, as a replayed CUDA graph, or as one persistent cooperative kernel.
+//     executed as plain launches, as a replayed CUDA graph, or as one cluster launch with the positions resident in
+//     distributed shared memory (resident.cuh).
 // There is no CPU fallback: every path that computes needs the CUDA device.
 #include <algorithm>
 #include <cstdarg>
@@ -15,8 +16,7 @@
 #include <string>
 #include <vector>
 #include "kernels.cuh"
-#include "persistent.cuh"
-#include "tiled.cuh"
+#include "resident.cuh"
 #include "colouring.cuh"
 #include <cub/cub.cuh>
 #include <omp.h>
@@ -97,7 +97,7 @@ struct pbd_engine {
     // device image
     DevType dev[PBD_NUM_TYPES];
     std::vector<Bucket> buckets;
-    DevBuf dBuckets, dBarrier, dTrace;
+    DevBuf dBuckets, dTrace;
     bool imageDirty = true;
     bool sortBuckets = true;
     // parameters
@@ -111,18 +111,19 @@ struct pbd_engine {
     pbd_stats stats{};
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool timingPending = false;
-    int persistentThreads = 0;
     bool mergeColours = true;             // one launch per colour when it holds several types (PBD_B200_MERGE=0 disables)
     std::vector<unsigned> slot;           // host particle index -> device slot (formula layouts or the tile-major permutation)
-    DevBuf dSlot, dSlotOld, relayoutTmp, dTileOff, dTileStart, dTilePrivate;
+    DevBuf dSlot, dSlotOld, relayoutTmp;
     bool slotIsTiled = false;
-    bool tileSwizzle = true;              // PBD_B200_SWIZZLE=0 disables the bank swizzle of the shared-memory tiles
-    unsigned nTiles = 0;
+    // resident mode (resident.cuh): G clusters x C CTAs = nTiles tiles, block size and type mask of the instantiation
+    unsigned resG = 0, resC = 0, nTiles = 0, resThreads = 0, resMask = 0, resColours = 0, resTileCap = 0, resXThreads = 0;
+    bool resChecked = false;              // co-residency of the clusters verified for the current image
+    DevBuf dColourStart, dTileOff, dTileStart, dTileSmem, dXArrive, dXCounter;
+    unsigned long long xBase = 0, xPerStep = 0;  // arrival counter of the X items: value at the next launch, arrivals per substep-sweep unit
     int layout = 1;                       // particle placement (device_image.h particle_slot); PBD_B200_LAYOUT=linear selects 0
     bool usePDL = true;                   // programmatic dependent launch between the kernels of a step (PBD_B200_PDL=0 disables)
     bool gatherCA = true;                 // particle gathers through L1 (tuning knob: PBD_B200_GATHER=cg selects L2-only loads)
-    unsigned coloursUsed = 0;             // colours that own at least one bucket
-    unsigned long long barrierBase = 0;   // value of the grid-barrier counter when the next persistent launch starts
+    std::vector<unsigned long long> xArriveInt, xArriveCol;  // per-launch bookkeeping of the X counter (host copy of dXArrive)
 };
 
 static int use(pbd_engine *e) { CK(cudaSetDevice(e->device)); return 0; }
@@ -159,9 +160,7 @@ extern "C" int pbd_create(int device, void *stream, pbd_engine **out) {
     cudaEventCreate(&e->evStart); cudaEventCreate(&e->evStop);
     if (const char *g = getenv("PBD_B200_GATHER")) e->gatherCA = (strcmp(g, "cg") != 0);
     if (const char *g = getenv("PBD_B200_PDL")) e->usePDL = (strcmp(g, "0") != 0);
-    if (const char *g = getenv("PBD_B200_PTHREADS")) e->persistentThreads = atoi(g);
     if (const char *g = getenv("PBD_B200_MERGE")) e->mergeColours = (strcmp(g, "0") != 0);
-    if (const char *g = getenv("PBD_B200_SWIZZLE")) e->tileSwizzle = (strcmp(g, "0") != 0);
     if (const char *g = getenv("PBD_B200_LAYOUT")) e->layout = (strcmp(g, "linear") == 0) ? 0 : 1;
     *out = e;
     return 0;
@@ -178,7 +177,7 @@ extern "C" int pbd_destroy(pbd_engine *e) {
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
     for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->stage2, &e->massStage, &e->dSlot, &e->dSlotOld, &e->relayoutTmp,
-                    &e->dTileOff, &e->dTileStart, &e->dTilePrivate, &e->dBuckets, &e->dBarrier, &e->dTrace,
+                    &e->dColourStart, &e->dTileOff, &e->dTileStart, &e->dTileSmem, &e->dXArrive, &e->dXCounter, &e->dBuckets, &e->dTrace,
                     &e->rbX, &e->rbQ, &e->rbV, &e->rbW, &e->rbOldX, &e->rbLastX, &e->rbOldQ, &e->rbLastQ, &e->rbI, &e->rbIinv}) b->release();
     for (auto &d : e->dev) {
         for (auto &b : d.idx) b.release();
@@ -357,7 +356,7 @@ extern "C" int pbd_get_rigid_bodies(pbd_engine *e, float *x, float *q, float *v,
 
 template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v, cudaStream_t s) {
     if (v.empty()) return 0;
-    if (buf.alloc(v.size() * sizeof(T) + 16)) return 1;  // +16: bulk copies of the tiled kernel round their size up to 16 bytes
+    if (buf.alloc(v.size() * sizeof(T) + 16)) return 1;
     cudaError_t e = cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return fail("upload -> %s", cudaGetErrorString(e));
     e = cudaStreamSynchronize(s);  // the host vector dies with the caller's scope
@@ -563,8 +562,8 @@ extern "C" int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsign
 }
 extern "C" int pbd_set_mode(pbd_engine *e, int mode) {
     if (!e) return fail("null engine");
-    if (mode < 0 || mode > PBD_MODE_TILED) return fail("unknown solver mode %d", mode);
-    if ((mode == PBD_MODE_TILED) != (e->mode == PBD_MODE_TILED)) e->imageDirty = true;  // the tiled image encodes indices differently
+    if (mode != PBD_MODE_GRAPH && mode != PBD_MODE_RESIDENT && mode != PBD_MODE_LAUNCH) return fail("unknown solver mode %d", mode);
+    if ((mode == PBD_MODE_RESIDENT) != (e->mode == PBD_MODE_RESIDENT)) e->imageDirty = true;  // the resident image encodes indices differently
     e->mode = mode; drop_graph(e);
     return 0;
 }
@@ -596,9 +595,8 @@ static bool factor_rank1(const float *Q, float Kp[4]) {
 }
 
 
-// Tiled mode (tiled.cuh): partition the particles into one tile per SM by recursive coordinate bisection of the rest
-// positions, classify them (private = every constraint touching it lies inside its tile), and move the device arrays to the
-// tile-major order [tile 0: private..., shared...][tile 1: ...].
+// Resident mode (resident.cuh): the particles are partitioned into G cluster regions x C tiles by recursive coordinate
+// bisection of the rest positions; the device arrays are permuted to tile-major order.
 static void bisect(std::vector<unsigned> &idx, size_t lo, size_t hi, unsigned t0, unsigned nt, const std::vector<float4> &x, std::vector<unsigned> &tileOf) {
     if (nt == 1) { for (size_t i = lo; i < hi; i++) tileOf[idx[i]] = t0; return; }
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
@@ -617,55 +615,153 @@ static void bisect(std::vector<unsigned> &idx, size_t lo, size_t hi, unsigned t0
     bisect(idx, mid, hi, t0 + ntL, nt - ntL, x, tileOf);
 }
 
-static int prepare_tiles(pbd_engine *e, std::vector<unsigned> &tileOf, std::vector<unsigned> &tileStart, std::vector<unsigned char> &inSmem) {
-    if (e->nRb || e->host[PBD_BALLJOINT].ids.size() || e->host[PBD_RB_PARTICLE_BALLJOINT].ids.size())
-        return fail("tiled mode handles particle constraints only (rigid-body joints: use the graph mode)");
-    unsigned nTiles = (unsigned)e->smCount;  // one tile per SM; PBD_B200_TILES=<k> (development knob) uses fewer, larger tiles
-    if (const char *g = getenv("PBD_B200_TILES")) { const int k = atoi(g); if (k >= 1 && k <= e->smCount) nTiles = (unsigned)k; }
-    const unsigned n = e->n;
-    e->nTiles = nTiles;
-    tileOf.assign(n, 0); inSmem.assign(n, 0); tileStart.assign(nTiles + 1, 0);
-    std::vector<unsigned> priv(nTiles, 0);
+struct ResidentPlan {
+    std::vector<unsigned> tileOf;             // host particle -> tile (cluster = tile / C, rank = tile % C)
+    std::vector<unsigned> tileStart, tileSmem;
+    std::vector<unsigned char> homedGlobal;   // host particle lives in global memory (touched by a constraint that spans clusters)
+};
+
+static bool is_rb_body(int type, int k) { return type == PBD_BALLJOINT || (type == PBD_RB_PARTICLE_BALLJOINT && k == 0); }
+
+// the compiled instantiations of k_step_resident: F(kernel pointer) for the engine's (mask, block size)
+template <class F> static int with_resident_kernel(const pbd_engine *e, F &&f) {
+    const unsigned th = e->resThreads;
+    if (e->resMask == kMaskClothXPBD) {
+        if (th == 512) return f(k_step_resident<kMaskClothXPBD, 512>);
+        if (th == 640) return f(k_step_resident<kMaskClothXPBD, 640>);
+        if (th == 768) return f(k_step_resident<kMaskClothXPBD, 768>);
+        return f(k_step_resident<kMaskClothXPBD, 1024>);
+    }
+    if (e->resMask == kMaskLight) {
+        if (th == 512) return f(k_step_resident<kMaskLight, 512>);
+        return f(k_step_resident<kMaskLight, 1024>);
+    }
+    if (th == 256) return f(k_step_resident<kMaskAll, 256>);
+    return f(k_step_resident<kMaskAll, 512>);
+}
+
+static void resident_launch_config(const pbd_engine *e, unsigned C, unsigned grid, size_t smem, cudaStream_t s, cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(e->resThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+}
+
+// how many clusters of C CTAs (one CTA per SM, `smem` bytes each) the device keeps resident at the same time
+static int resident_max_clusters(const pbd_engine *e, unsigned C, size_t smem, int *out) {
+    return with_resident_kernel(e, [&](auto kernel) -> int {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynamicSmem));
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+        resident_launch_config(e, C, C, smem, e->stream, cfg, attr);
+        cudaError_t err = cudaOccupancyMaxActiveClusters(out, kernel, &cfg);
+        if (err != cudaSuccess) { cudaGetLastError(); *out = 0; }
+        return 0;
+    });
+}
+
+// shape of the launch: type mask / block size of the instantiation, clusters x CTAs per cluster
+static int choose_resident_shape(pbd_engine *e) {
+    unsigned present = 0, nTypes = 0;
+    for (int t = 0; t < PBD_NUM_TYPES; t++) if (!e->host[t].ids.empty()) { present |= 1u << t; nTypes++; }
+    e->resMask = ((present & ~kMaskClothXPBD) == 0) ? kMaskClothXPBD : (((present & ~kMaskLight) == 0) ? kMaskLight : kMaskAll);
+    // the block sizes the instantiations compile for without spilling (cloth 96 registers, light 128, everything 236)
+    e->resThreads = (e->resMask == kMaskClothXPBD) ? 640u : ((e->resMask == kMaskLight) ? 512u : 256u);
+    if (const char *g = getenv("PBD_B200_RTHREADS")) { const int k = atoi(g); if (k == 256 || k == 512 || k == 640 || k == 768 || k == 1024) e->resThreads = (unsigned)k; }
+    if (e->resMask == kMaskAll && e->resThreads > 512u) e->resThreads = 512u;
+    if (e->resMask == kMaskLight && (e->resThreads == 768u || e->resThreads == 640u)) e->resThreads = 1024u;
+    if (e->resMask == kMaskClothXPBD && e->resThreads == 256u) e->resThreads = 512u;
+    const unsigned nGroups = (unsigned)std::max<size_t>(e->groupOff.size(), 2) - 1;
+    const unsigned perPhase = e->numConstraints / std::max(1u, nGroups);
+    // particles a tile can hold: what is left of the CTA's shared memory after the phase tables (bound: one bucket per colour and type)
+    const size_t tables = resident_smem_bytes(0u, nGroups * std::max(1u, nTypes), nGroups);
+    if (tables + 1024 * sizeof(float4) > kMaxDynamicSmem) return fail("resident mode: %u colour groups need %zu bytes of phase tables (use PBD_MODE_GRAPH)", nGroups, tables);
+    const unsigned cap = (unsigned)(0.97 * (double)((kMaxDynamicSmem - tables) / sizeof(float4)));  // bisection splits counts evenly; slack for rounding
+    unsigned G = 1, C = 1;
+    if (e->n <= (unsigned)kMaxClusterCtas * cap && perPhase <= (unsigned)kMaxClusterCtas * 1024u) {
+        // one cluster: enough CTAs that a colour phase is about one item per thread, and that the tiles fit
+        while (C < (unsigned)kMaxClusterCtas && (perPhase > C * 256u || e->n > C * cap)) C *= 2;
+    } else {
+        // several clusters: the shape that puts the most SMs to work (ties: the larger cluster, fewer global-homed particles)
+        unsigned bestT = 0;
+        for (unsigned c : {16u, 8u}) {
+            int mc = 0;
+            CKE(resident_max_clusters(e, c, kMaxDynamicSmem, &mc));
+            if ((unsigned)mc * c > bestT) { bestT = (unsigned)mc * c; G = (unsigned)mc; C = c; }
+        }
+        if (bestT == 0) return fail("resident mode: no thread-block cluster of 8 or 16 CTAs with %zu bytes of shared memory is schedulable on this device", kMaxDynamicSmem);
+    }
+    if (const char *g = getenv("PBD_B200_CLUSTERS")) {  // development knob "GxC"
+        unsigned gg = 0, cc = 0;
+        if (sscanf(g, "%ux%u", &gg, &cc) == 2 && gg >= 1 && cc >= 1 && cc <= (unsigned)kMaxClusterCtas && (cc & (cc - 1)) == 0) { G = gg; C = cc; }
+    }
+    if ((unsigned long long)G * C * cap < e->n)
+        return fail("resident mode: %u particles do not fit %u x %u tiles of %u (use PBD_MODE_GRAPH)", e->n, G, C, cap);
+    if (G > 1 && (e->nRb || !e->host[PBD_BALLJOINT].ids.empty() || !e->host[PBD_RB_PARTICLE_BALLJOINT].ids.empty()))
+        return fail("resident mode: rigid-body coupling is supported for scenes that fit one cluster (use PBD_MODE_GRAPH)");
+    e->resG = G; e->resC = C; e->nTiles = G * C;
+    e->resXThreads = (G > 1) ? 128u : 0u;
+    if (const char *g = getenv("PBD_B200_XTHREADS")) { const int k = atoi(g); if (G > 1 && k >= 32 && k % 32 == 0 && (unsigned)k < e->resThreads) e->resXThreads = (unsigned)k; }
+    return 0;
+}
+
+static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
+    CKE(choose_resident_shape(e));
+    const unsigned n = e->n, G = e->resG, C = e->resC, T = e->nTiles;
+    pl.tileOf.assign(n, 0); pl.homedGlobal.assign(n, 0); pl.tileStart.assign(T + 1, 0); pl.tileSmem.assign(T, 0);
     if (n) {
         // rest positions by host index
         std::vector<float4> raw(n), x(n);
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaMemcpy(raw.data(), e->pos0.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
         for (unsigned i = 0; i < n; i++) x[i] = raw[e->slot[i]];
-        std::vector<unsigned> idx(n);
+        std::vector<unsigned> idx(n), region(n);
         for (unsigned i = 0; i < n; i++) idx[i] = i;
-        bisect(idx, 0, n, 0, nTiles, x, tileOf);
-        // shared = touched by a constraint whose particles lie in more than one tile
-        std::vector<unsigned char> shared(n, 0);
-        for (int t = 0; t < PBD_NUM_TYPES; t++) {
-            const HostType &h = e->host[t];
-            const int nb = type_shape(t).nBodies;
-            for (size_t c = 0; c < h.ids.size(); c++) {
-                const unsigned *b = &h.bodies[c * nb];
-                bool spans = false;
-                for (int k = 1; k < nb; k++) spans |= (tileOf[b[k]] != tileOf[b[0]]);
-                if (spans) for (int k = 0; k < nb; k++) shared[b[k]] = 1;
+        bisect(idx, 0, n, 0, G, x, region);  // cluster regions; idx is now grouped region by region
+        size_t lo = 0;
+        for (unsigned g = 0; g < G; g++) {
+            size_t hi = lo;
+            while (hi < n && region[idx[hi]] == g) hi++;
+            bisect(idx, lo, hi, g * C, C, x, pl.tileOf);
+            lo = hi;
+        }
+        // global-homed = touched by a constraint whose particles lie in more than one cluster
+        if (G > 1)
+            for (int t = 0; t < PBD_NUM_TYPES; t++) {
+                const HostType &h = e->host[t];
+                const int nb = type_shape(t).nBodies;
+                for (size_t c = 0; c < h.ids.size(); c++) {
+                    const unsigned *b = &h.bodies[c * nb];
+                    bool spans = false;
+                    for (int k = 1; k < nb; k++) spans |= (pl.tileOf[b[k]] / C != pl.tileOf[b[0]] / C);
+                    if (spans) for (int k = 0; k < nb; k++) pl.homedGlobal[b[k]] = 1;
+                }
             }
+        // tile-major slots: shared-memory particles first (host order), global-homed behind them
+        std::vector<unsigned> cntS(T, 0), cntG(T, 0);
+        for (unsigned i = 0; i < n; i++) (pl.homedGlobal[i] ? cntG : cntS)[pl.tileOf[i]]++;
+        for (unsigned t = 0; t < T; t++) {
+            pl.tileStart[t + 1] = pl.tileStart[t] + cntS[t] + cntG[t];
+            pl.tileSmem[t] = cntS[t];
         }
-        // tile-major slots: private particles first (host order), shared behind them
-        std::vector<unsigned> cntP(nTiles, 0), cntS(nTiles, 0);
-        for (unsigned i = 0; i < n; i++) (shared[i] ? cntS : cntP)[tileOf[i]]++;
-        for (unsigned t = 0; t < nTiles; t++) tileStart[t + 1] = tileStart[t] + cntP[t] + cntS[t];
-        std::vector<unsigned> curP(nTiles), curS(nTiles), newSlot(n);
-        for (unsigned t = 0; t < nTiles; t++) { curP[t] = tileStart[t]; curS[t] = tileStart[t] + cntP[t]; priv[t] = std::min<unsigned>(cntP[t], (unsigned)kTileCapacity); }
-        for (unsigned i = 0; i < n; i++) {
-            const unsigned t = tileOf[i];
-            newSlot[i] = shared[i] ? curS[t]++ : curP[t]++;
-            inSmem[i] = !shared[i] && (newSlot[i] - tileStart[t] < priv[t]);
-        }
+        std::vector<unsigned> curS(T), curG(T), newSlot(n);
+        for (unsigned t = 0; t < T; t++) { curS[t] = pl.tileStart[t]; curG[t] = pl.tileStart[t] + cntS[t]; }
+        for (unsigned i = 0; i < n; i++) newSlot[i] = pl.homedGlobal[i] ? curG[pl.tileOf[i]]++ : curS[pl.tileOf[i]]++;
         CKE(relayout(e, newSlot));
-        unsigned long long nShared = 0;
-        for (unsigned i = 0; i < n; i++) nShared += shared[i];
-        if (getenv("PBD_B200_VERBOSE")) fprintf(stderr, "[pbd_b200] tiled: %u tiles, %u particles, %.1f %% shared, max private/tile %u\n", nTiles, n, 100.0 * nShared / n, *std::max_element(cntP.begin(), cntP.end()));
+        if (getenv("PBD_B200_VERBOSE")) {
+            unsigned long long nGl = 0;
+            for (unsigned i = 0; i < n; i++) nGl += pl.homedGlobal[i];
+            fprintf(stderr, "[pbd_b200] resident: %u clusters x %u CTAs, %u threads (%u for X items), %u particles, %.2f %% global-homed, max tile %u\n", G, C, e->resThreads, e->resXThreads, n,
+                    100.0 * nGl / n, *std::max_element(cntS.begin(), cntS.end()));
+        }
     }
     e->slotIsTiled = true;
-    CKE(upload_vec(e->dTileStart, tileStart, e->stream));
-    CKE(upload_vec(e->dTilePrivate, priv, e->stream));
+    e->resTileCap = 64u;  // multiple of 64: the bank swizzle permutes inside aligned 64-slot blocks
+    for (unsigned t = 0; t < T; t++) e->resTileCap = std::max(e->resTileCap, (pl.tileSmem[t] + 63u) & ~63u);
+    e->resChecked = false;
+    CKE(upload_vec(e->dTileStart, pl.tileStart, e->stream));
+    CKE(upload_vec(e->dTileSmem, pl.tileSmem, e->stream));
     return 0;
 }
 
@@ -681,11 +777,12 @@ static int flatten(pbd_engine *e) {
     CKE(build_id_map(e, map));
     const unsigned nGroups = (unsigned)e->groupOff.size() - 1;
 
-    // 0. particle placement: tile-major for the tiled mode, the formula layout otherwise
-    const bool tiled = (e->mode == PBD_MODE_TILED);
-    std::vector<unsigned> tileOf, tileStart, tileOff;
-    std::vector<unsigned char> inSmem;
-    if (tiled) CKE(prepare_tiles(e, tileOf, tileStart, inSmem));
+    // 0. particle placement: tile-major for the resident mode, the formula layout otherwise
+    const bool tiled = (e->mode == PBD_MODE_RESIDENT);
+    ResidentPlan pl;
+    std::vector<unsigned> tileOff;
+    std::vector<unsigned> &tileOf = pl.tileOf;
+    if (tiled) CKE(prepare_resident(e, pl));
     else if (e->slotIsTiled) {
         std::vector<unsigned> m;
         formula_slot_map(e, m);
@@ -705,21 +802,33 @@ static int flatten(pbd_engine *e) {
         }
         for (int t = 0; t < PBD_NUM_TYPES; t++) {
             if (tmp[t].empty()) continue;
-            if ((e->sortBuckets || tiled) && t != PBD_BALLJOINT && t != PBD_RB_PARTICLE_BALLJOINT) {  // order inside a colour is free: sort by lowest particle slot for gather locality
+            const bool joint = (t == PBD_BALLJOINT || t == PBD_RB_PARTICLE_BALLJOINT);
+            if ((e->sortBuckets && !joint) || tiled) {  // order inside a colour is free: sort by lowest particle slot for gather locality
                 const int nb = type_shape(t).nBodies;
                 const unsigned *bod = e->host[t].bodies.data();
                 std::vector<std::pair<unsigned long long, unsigned>> keyed(tmp[t].size());
                 #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)tmp[t].size(); i++) {
                     const unsigned *b = bod + (size_t)tmp[t][i] * nb;
-                    unsigned mn = e->slot[b[0]];
-                    for (int k = 1; k < nb; k++) mn = std::min(mn, e->slot[b[k]]);
-                    // tiled: major key = executing tile (tile of the first particle), then "all particles in shared memory?"
+                    unsigned mn = 0xffffffffu;
+                    for (int k = 0; k < nb; k++) if (!is_rb_body(t, k)) mn = std::min(mn, e->slot[b[k]]);
+                    if (joint) mn = (unsigned)i;  // joints keep their order
+                    // resident: major key = executing tile, then X items (touching a global-homed particle) before the others
                     unsigned long long major = 0;
                     if (tiled) {
-                        bool pure = true;
-                        for (int k = 0; k < nb; k++) pure &= (inSmem[b[k]] != 0);
-                        major = 2ull * tileOf[b[0]] + (pure ? 1u : 0u);
+                        bool x = false;
+                        unsigned best = 0xffffffffu, bestCnt = 0, first = 0xffffffffu;
+                        for (int k = 0; k < nb; k++) {
+                            if (is_rb_body(t, k)) continue;
+                            if (first == 0xffffffffu) first = tileOf[b[k]];
+                            if (pl.homedGlobal[b[k]]) { x = true; continue; }
+                            unsigned cnt = 0;
+                            for (int j = 0; j < nb; j++) cnt += (!is_rb_body(t, j) && !pl.homedGlobal[b[j]] && tileOf[b[j]] == tileOf[b[k]]);
+                            if (cnt > bestCnt || (cnt == bestCnt && tileOf[b[k]] < best)) { best = tileOf[b[k]]; bestCnt = cnt; }
+                        }
+                        // executing tile: the one that holds most of the constraint's shared-memory particles; none -> tile of its first particle
+                        const unsigned exec = (best != 0xffffffffu) ? best : (first != 0xffffffffu ? first : 0u);
+                        major = 2ull * exec + (x ? 0u : 1u);
                     }
                     keyed[i] = std::make_pair((major << 32) | mn, tmp[t][i]);
                 }
@@ -727,7 +836,7 @@ static int flatten(pbd_engine *e) {
                                             __gnu_parallel::default_parallel_tag(host_threads()));
                 #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)keyed.size(); i++) tmp[t][i] = keyed[i].second;
-                if (tiled) {  // runs of every tile inside this bucket: [2 tile] spanning, [2 tile + 1] private
+                if (tiled) {  // runs of every tile inside this bucket: [2 tile] X items, [2 tile + 1] the others
                     const size_t base = tileOff.size();
                     tileOff.resize(base + 2 * e->nTiles + 1, 0u);
                     for (size_t i = 0; i < keyed.size(); i++) tileOff[base + (keyed[i].first >> 32) + 1]++;
@@ -780,11 +889,10 @@ static int flatten(pbd_engine *e) {
         auto P = [&](unsigned i, int k) { return h.params[(size_t)order[t][i] * s.nParams + k]; };
         auto B = [&](unsigned i, int k) {
             const unsigned raw = h.bodies[(size_t)order[t][i] * s.nBodies + k];
-            const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && k == 0);
-            if (isRb) return raw;
-            if (tiled && inSmem[raw]) {  // lives in the executing CTA's shared memory
-                const unsigned local = e->slot[raw] - tileStart[tileOf[raw]];
-                return kSmemFlag | (e->tileSwizzle ? tile_swizzle(local) : local);
+            if (is_rb_body(t, k)) return raw;
+            if (tiled && !pl.homedGlobal[raw]) {  // lives in the shared memory of CTA (tile % C) of the executing cluster
+                const unsigned tl = tileOf[raw];
+                return kSmemFlag | ((tl % e->resC) << kRankShift) | tile_swizzle(e->slot[raw] - pl.tileStart[tl]);
             }
             return e->slot[raw];
         };
@@ -832,6 +940,7 @@ static int flatten(pbd_engine *e) {
                 gv[0][i] = make_float4(Kp[0], Kp[1], Kp[2], Kp[3]);
             }
             const bool rank1 = !notRank1;
+            if (!rank1 && tiled) return fail("resident mode: IsometricBending with a user-modified Q matrix (not of the rank-one form) is evaluated by the per-bucket kernels only (use PBD_MODE_GRAPH)");
             if (!rank1) {  // user-modified Q somewhere in this type: literal 4x4 evaluation for the whole type
                 variant = 1;
                 for (int r = 0; r < 4; r++) {
@@ -920,15 +1029,53 @@ static int flatten(pbd_engine *e) {
         bytesPerSweep += (double)cnt * algorithmic_bytes(t, variant);
     }
 
-    // 3. bucket table + type arrays for the persistent kernel
+    // 3. bucket table; resident mode: colour ranges, per-tile runs and the arrival counts of the X items
     CKE(upload_vec(e->dBuckets, e->buckets, e->stream));
-    if (tiled) CKE(upload_vec(e->dTileOff, tileOff, e->stream));
-    CKE(e->dBarrier.alloc(256));
-    CK(cudaMemsetAsync(e->dBarrier.p, 0, 256, e->stream));
-    e->barrierBase = 0;
-    e->coloursUsed = 0;
-    for (size_t i = 0; i < e->buckets.size(); i++)
-        if (i == 0 || e->buckets[i].colour != e->buckets[i - 1].colour) e->coloursUsed++;
+    if (tiled) {
+        const unsigned T = e->nTiles, warps = e->resXThreads / 32u;  // the dedicated X warps of a CTA
+        std::vector<unsigned> colourStart;
+        for (size_t i = 0; i < e->buckets.size(); i++)
+            if (i == 0 || e->buckets[i].colour != e->buckets[i - 1].colour) colourStart.push_back((unsigned)i);
+        e->resColours = (unsigned)colourStart.size();
+        colourStart.push_back((unsigned)e->buckets.size());
+        if (tileOff.size() != e->buckets.size() * (2 * (size_t)T + 1)) return fail("flatten: internal error (tile runs)");
+        // arrivals on the X counter, in warps: integration phase (warps that own global-homed particles), then every colour
+        std::vector<unsigned> xArrive(1 + e->resColours, 0u);
+        for (unsigned t = 0; t < T; t++) {
+            const unsigned nGl = pl.tileStart[t + 1] - pl.tileStart[t] - pl.tileSmem[t];
+            xArrive[0] += std::min(warps, (nGl + 31u) / 32u);
+        }
+        for (unsigned c = 0; c < e->resColours; c++)
+            for (unsigned t = 0; t < T; t++) {
+                unsigned mx = 0;
+                for (unsigned bi = colourStart[c]; bi < colourStart[c + 1]; bi++) {
+                    const unsigned *off = &tileOff[(size_t)bi * (2 * T + 1) + 2 * t];
+                    mx = std::max(mx, off[1] - off[0]);
+                }
+                xArrive[1 + c] += std::min(warps, (mx + 31u) / 32u);
+            }
+        unsigned long long perSweep = 0;
+        for (unsigned c = 0; c < e->resColours; c++) perSweep += xArrive[1 + c];
+        e->xArriveInt.assign(1, xArrive[0]); e->xArriveCol.assign(1, perSweep);
+        CKE(upload_vec(e->dColourStart, colourStart, e->stream));
+        CKE(upload_vec(e->dTileOff, tileOff, e->stream));
+        CKE(upload_vec(e->dXArrive, xArrive, e->stream));
+        CKE(e->dXCounter.alloc(256));
+        CK(cudaMemsetAsync(e->dXCounter.p, 0, 256, e->stream));
+        e->xBase = 0;
+        if (getenv("PBD_B200_VERBOSE")) {
+            unsigned long long xItems = 0, mxRun = 0;
+            for (size_t bi = 0; bi < e->buckets.size(); bi++)
+                for (unsigned t = 0; t < T; t++) {
+                    const unsigned *off = &tileOff[bi * (2 * (size_t)T + 1) + 2 * t];
+                    xItems += off[1] - off[0];
+                    mxRun = std::max<unsigned long long>(mxRun, off[2] - off[0]);
+                }
+            fprintf(stderr, "[pbd_b200] resident: %u colours, %zu buckets, %.2f %% X items, largest run of a tile in a bucket %llu (mean %.0f), X arrivals per sweep %llu\n",
+                    e->resColours, e->buckets.size(), 100.0 * xItems / std::max(1u, e->numConstraints), mxRun,
+                    (double)e->numConstraints / std::max<size_t>(1, e->buckets.size()) / T, perSweep);
+        }
+    }
     CK(cudaStreamSynchronize(e->stream));
 
     e->stats.num_constraints = e->numConstraints;
@@ -967,15 +1114,19 @@ static int launch_bucket(pbd_engine *e, const Bucket &b, float h, int iterZero, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = e->usePDL ? 1 : 0;
     cudaError_t le = cudaSuccess;
-#define LB(T) case T: le = e->gatherCA ? cudaLaunchKernelEx(&cfg, k_project<T, true>, pos, a, b.first, b.count, h, iterZero) \
-                                       : cudaLaunchKernelEx(&cfg, k_project<T, false>, pos, a, b.first, b.count, h, iterZero); break;
+#define LBV(T, V) (e->gatherCA ? cudaLaunchKernelEx(&cfg, k_project<T, true, V>, pos, a, b.first, b.count, h, iterZero) \
+                                : cudaLaunchKernelEx(&cfg, k_project<T, false, V>, pos, a, b.first, b.count, h, iterZero))
+#define LB(T) case T: le = LBV(T, 0); break;
     switch (b.type) {
-        LB(PBD_DISTANCE) LB(PBD_DISTANCE_XPBD) LB(PBD_DIHEDRAL) LB(PBD_ISOBENDING) LB(PBD_ISOBENDING_XPBD)
+    case PBD_ISOBENDING: le = a.variant ? LBV(PBD_ISOBENDING, 1) : LBV(PBD_ISOBENDING, 0); break;
+    case PBD_ISOBENDING_XPBD: le = a.variant ? LBV(PBD_ISOBENDING_XPBD, 1) : LBV(PBD_ISOBENDING_XPBD, 0); break;
+        LB(PBD_DISTANCE) LB(PBD_DISTANCE_XPBD) LB(PBD_DIHEDRAL)
         LB(PBD_FEMTRIANGLE) LB(PBD_STRAINTRIANGLE) LB(PBD_VOLUME) LB(PBD_VOLUME_XPBD) LB(PBD_FEMTET)
         LB(PBD_FEMTET_XPBD) LB(PBD_STRAINTET) LB(PBD_SHAPEMATCHING) LB(PBD_BALLJOINT) LB(PBD_RB_PARTICLE_BALLJOINT)
     default: return fail("no kernel for constraint type %d", b.type);
     }
 #undef LB
+#undef LBV
     CK(le);
     return 0;
 }
@@ -1065,113 +1216,62 @@ static int enqueue_step_launches(pbd_engine *e, cudaStream_t s, unsigned long lo
     return 0;
 }
 
-// pick the smallest compiled type mask that covers the constraint types present in the model
-template <unsigned MASK, int THREADS>
-static int launch_persistent(pbd_engine *e, cudaStream_t s, PersistentArgs &pa) {
-    void *fn = e->gatherCA ? (void *)k_step_persistent<MASK, true, THREADS> : (void *)k_step_persistent<MASK, false, THREADS>;
-    int nb = 0;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersistentSmemBytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, THREADS, kPersistentSmemBytes));
-    if (nb < 1) return fail("persistent kernel does not fit on an SM");
-    const int grid = e->smCount;  // one CTA per SM, all co-resident (cooperative launch)
-    // barriers per launch: per substep one after the prologue, one per colour phase of every sweep
-    const unsigned long long perSub = e->buckets.empty() ? 1ull : 1ull + (unsigned long long)e->maxIter * e->coloursUsed;
-    pa.barrierBase = e->barrierBase;
-    e->barrierBase += perSub * e->subSteps * (unsigned long long)grid;
-    void *args[] = {&pa};
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(THREADS), args, kPersistentSmemBytes, s));
-    return 0;
+// One step as one launch of k_step_resident: grid = nTiles CTAs in clusters of resC, one CTA per SM, all co-resident
+// (the X items of different clusters wait for each other).
+static int launch_resident(pbd_engine *e, cudaStream_t s, ResidentArgs &ra) {
+    const size_t smem = resident_smem_bytes(ra.tileCap, ra.nBuckets, ra.nColours);
+    if (smem > kMaxDynamicSmem) return fail("resident mode: a CTA needs %zu bytes of shared memory (tile of %u particles + phase tables), %zu available", smem, ra.tileCap, kMaxDynamicSmem);
+    if (e->resG > 1 && !e->resChecked) {
+        int mc = 0;
+        CKE(resident_max_clusters(e, e->resC, smem, &mc));
+        if ((unsigned)mc < e->resG)
+            return fail("resident mode: the device runs %d clusters of %u CTAs at a time, the scene needs %u co-resident", mc, e->resC, e->resG);
+        e->resChecked = true;
+    }
+    return with_resident_kernel(e, [&](auto kernel) -> int {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynamicSmem));
+        if (e->resC > 8) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+        resident_launch_config(e, e->resC, e->nTiles, smem, s, cfg, attr);
+        CK(cudaLaunchKernelEx(&cfg, kernel, ra));
+        return 0;
+    });
 }
 
-static int enqueue_step_persistent(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
-    if (e->nRb || e->dev[PBD_BALLJOINT].count || e->dev[PBD_RB_PARTICLE_BALLJOINT].count)
-        return fail("PBD_MODE_PERSISTENT does not cover rigid-body coupling (BallJoint / RigidBodyParticleBallJoint); use PBD_MODE_GRAPH");
+static int enqueue_step_resident(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
     const float h = e->dt / (float)e->subSteps;
-    const float invH = (float)(1.0 / (double)h);
-    PersistentArgs pa;
-    pa.pos = (float4 *)e->pos.p; pa.vel = (float4 *)e->vel.p; pa.oldp = (float4 *)e->oldp.p; pa.lastp = (float4 *)e->lastp.p;
-    pa.n = e->n; pa.buckets = (const Bucket *)e->dBuckets.p;
-    pa.nBuckets = (unsigned)e->buckets.size(); pa.subSteps = e->subSteps; pa.maxIter = e->maxIter;
-    pa.h = h; pa.invH = invH; pa.gx = e->g[0]; pa.gy = e->g[1]; pa.gz = e->g[2];
-    pa.secondOrder = e->velMethod; pa.trackLast = track_last(e);
-    pa.barrier = (unsigned long long *)e->dBarrier.p;
-    pa.trace = nullptr; pa.tracePhases = 0;
-    static const char *tracePath = getenv("PBD_B200_TRACE");  // development aid: dump per-phase barrier timelines of one step
-    const unsigned kTracePhases = 128;
-    if (tracePath) {
-        CKE(e->dTrace.alloc((size_t)kTracePhases * e->smCount * 4 * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(e->dTrace.p, 0, e->dTrace.bytes, s));
-        pa.trace = (unsigned long long *)e->dTrace.p; pa.tracePhases = kTracePhases;
-    }
-    unsigned present = 0;
-    for (int t = 0; t < PBD_NUM_TYPES; t++) { pa.types[t] = e->dev[t].arrays; if (e->dev[t].count) present |= 1u << t; }
-    *launches = 1;
-    struct TraceDump {  // development aid: runs after the launch below has been enqueued (scope exit)
-        pbd_engine *e; cudaStream_t s; const char *path; unsigned phases;
-        ~TraceDump() {
-            if (!path) return;
-            cudaStreamSynchronize(s);
-            std::vector<unsigned long long> h((size_t)phases * e->smCount * 4);
-            cudaMemcpy(h.data(), e->dTrace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-            if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+    ResidentArgs ra;
+    ra.pos = (float4 *)e->pos.p; ra.vel = (float4 *)e->vel.p; ra.oldp = (float4 *)e->oldp.p; ra.lastp = (float4 *)e->lastp.p;
+    ra.buckets = (const Bucket *)e->dBuckets.p;
+    ra.colourStart = (const unsigned *)e->dColourStart.p; ra.tileOff = (const unsigned *)e->dTileOff.p;
+    ra.tileStart = (const unsigned *)e->dTileStart.p; ra.tileSmem = (const unsigned *)e->dTileSmem.p; ra.xArrive = (const unsigned *)e->dXArrive.p;
+    ra.nBuckets = (unsigned)e->buckets.size(); ra.nColours = e->resColours; ra.nTiles = e->nTiles; ra.subSteps = e->subSteps; ra.maxIter = e->maxIter;
+    ra.tileCap = e->resTileCap; ra.xThreads = e->resXThreads; ra.clusterSize = e->resC;
+    {   // L2 prefetch of the operand runs pays when the constraint stream of a sweep does not stay in L2 (126 MB) anyway
+        static const char *g = getenv("PBD_B200_L2PREFETCH");
+        double streamBytes = 0.0;
+        for (int t = 0; t < PBD_NUM_TYPES; t++) {
+            const TypeShape sh = type_shape(t);
+            streamBytes += (double)e->dev[t].count * (4.0 * sh.nBodies + 16.0 * sh.nGeoV + 4.0 * sh.nGeoS + (sh.xpbd ? 4.0 : 0.0));
         }
-    } dump{e, s, tracePath, kTracePhases};
-    const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
-    if ((present & ~kMaskClothXPBD) == 0) {
-        if (pt == 512) return launch_persistent<kMaskClothXPBD, 512>(e, s, pa);
-        if (pt == 768) return launch_persistent<kMaskClothXPBD, 768>(e, s, pa);
-        return launch_persistent<kMaskClothXPBD, 1024>(e, s, pa);
+        ra.l2Prefetch = g ? atoi(g) : (streamBytes > 48.0e6 ? 1 : 0);
     }
-    if ((present & ~kMaskLight) == 0) {
-        if (pt == 512) return launch_persistent<kMaskLight, 512>(e, s, pa);
-        return launch_persistent<kMaskLight, 1024>(e, s, pa);
-    }
-    if (pt == 256) return launch_persistent<kMaskAll, 256>(e, s, pa);
-    return launch_persistent<kMaskAll, 512>(e, s, pa);
-}
-
-template <unsigned MASK, int THREADS>
-static int launch_tiled(pbd_engine *e, cudaStream_t s, TiledArgs &ta) {
-    auto kernel = k_step_tiled<MASK, THREADS>;
-    // per device and function; cheap, so not cached (engines on several devices may live in one thread)
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiledSmemBytes));
-    int perSM = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, THREADS, kTiledSmemBytes));
-    if (perSM < 1) return fail("tiled kernel does not fit on an SM");
-    void *args[] = {&ta};
-    CK(cudaLaunchCooperativeKernel((void *)kernel, dim3(e->nTiles), dim3(THREADS), args, kTiledSmemBytes, s));
-    return 0;
-}
-
-static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
-    const float h = e->dt / (float)e->subSteps;
-    TiledArgs ta;
-    ta.pos = (float4 *)e->pos.p; ta.vel = (float4 *)e->vel.p; ta.oldp = (float4 *)e->oldp.p; ta.lastp = (float4 *)e->lastp.p;
-    ta.buckets = (const Bucket *)e->dBuckets.p;
-    ta.tileOff = (const unsigned *)e->dTileOff.p; ta.tileStart = (const unsigned *)e->dTileStart.p; ta.tilePrivate = (const unsigned *)e->dTilePrivate.p;
-    ta.nBuckets = (unsigned)e->buckets.size(); ta.subSteps = e->subSteps; ta.maxIter = e->maxIter;
-    ta.h = h; ta.invH = (float)(1.0 / (double)h); ta.gx = e->g[0]; ta.gy = e->g[1]; ta.gz = e->g[2];
-    ta.secondOrder = e->velMethod; ta.trackLast = track_last(e);
-    ta.barrier = (unsigned long long *)e->dBarrier.p;
-    ta.barrierBase = e->barrierBase;
-    // barriers per substep: one after the prologue, one per colour and sweep
-    e->barrierBase += (unsigned long long)e->subSteps * (1ull + (unsigned long long)e->maxIter * e->coloursUsed) * e->nTiles;
-    unsigned present = 0;
-    for (int t = 0; t < PBD_NUM_TYPES; t++) { ta.types[t] = e->dev[t].arrays; if (e->dev[t].count) present |= 1u << t; }
+    ra.h = h; ra.invH = (float)(1.0 / (double)h); ra.twoInvH = (float)(2.0 / (double)h); ra.gx = e->g[0]; ra.gy = e->g[1]; ra.gz = e->g[2];
+    ra.secondOrder = e->velMethod;
+    ra.xCounter = (unsigned long long *)e->dXCounter.p;
+    ra.xBase = e->xBase;
+    e->xBase += (unsigned long long)e->subSteps * (e->xArriveInt[0] + (unsigned long long)e->maxIter * e->xArriveCol[0]);
+    ra.rb = RbState{(float4 *)e->rbX.p, (float4 *)e->rbQ.p, (float4 *)e->rbV.p, (float4 *)e->rbW.p, (float4 *)e->rbOldX.p, (float4 *)e->rbLastX.p,
+                    (float4 *)e->rbOldQ.p, (float4 *)e->rbLastQ.p, (const float4 *)e->rbI.p, (const float4 *)e->rbIinv.p, e->nRb};
+    for (int t = 0; t < PBD_NUM_TYPES; t++) ra.types[t] = e->dev[t].arrays;
     *launches = 1;
-    static const char *noStage = getenv("PBD_B200_NOSTAGE");  // A/B knob: constraint stream straight from global memory
-    ta.stage = noStage ? 0 : 1;
-    ta.swizzle = e->tileSwizzle ? 1 : 0;
-    ta.stageLambda = (ta.stage && e->coloursUsed >= 2) ? 1 : 0;  // the copy for phase p + 1 starts during phase p: needs another colour in between
-    ta.trace = nullptr; ta.tracePhases = 0;
-    static const char *traceWorker = getenv("PBD_B200_TRACE_WORKER");
-    ta.traceWorker = traceWorker ? atoi(traceWorker) : -1;
-    static const char *tracePath = getenv("PBD_B200_TRACE");  // development aid: dump per-phase timelines of one step
-    const unsigned kTracePhases = 128;
+    ra.trace = nullptr; ra.tracePhases = 0;
+    static const char *tracePath = getenv("PBD_B200_TRACE");  // development aid: dump per-phase timelines of one step (tools/trace_resident.py)
+    const unsigned kTracePhases = 256;
     if (tracePath) {
         CKE(e->dTrace.alloc((size_t)kTracePhases * e->nTiles * 4 * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(e->dTrace.p, 0, e->dTrace.bytes, s));
-        ta.trace = (unsigned long long *)e->dTrace.p; ta.tracePhases = kTracePhases;
+        ra.trace = (unsigned long long *)e->dTrace.p; ra.tracePhases = kTracePhases;
     }
     struct TraceDump {  // runs after the launch below has been enqueued (scope exit)
         pbd_engine *e; cudaStream_t s; const char *path; unsigned phases;
@@ -1183,15 +1283,7 @@ static int enqueue_step_tiled(pbd_engine *e, cudaStream_t s, unsigned long long 
             if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
         }
     } dump{e, s, tracePath, kTracePhases};
-    const int pt = e->persistentThreads;  // tuning knob PBD_B200_PTHREADS (0 = default)
-    if ((present & ~kMaskClothXPBD) == 0) {
-        if (pt == 1024) return launch_tiled<kMaskClothXPBD, 1024>(e, s, ta);
-        if (pt == 768) return launch_tiled<kMaskClothXPBD, 768>(e, s, ta);
-        if (pt == 512) return launch_tiled<kMaskClothXPBD, 512>(e, s, ta);
-        return launch_tiled<kMaskClothXPBD, 640>(e, s, ta);  // measured best on cfg2 (profiles/README.md section 4)
-    }
-    if ((present & ~kMaskLight) == 0) return launch_tiled<kMaskLight, 512>(e, s, ta);
-    return launch_tiled<kMaskAll, 512>(e, s, ta);
+    return launch_resident(e, s, ra);
 }
 
 static int ensure_graph(pbd_engine *e, unsigned long long *launchesPerStep) {
@@ -1220,10 +1312,8 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
         unsigned long long L = 0;
         if (e->mode == PBD_MODE_LAUNCH) {
             CKE(enqueue_step_launches(e, e->stream, &L));
-        } else if (e->mode == PBD_MODE_PERSISTENT) {
-            CKE(enqueue_step_persistent(e, e->stream, &L));
-        } else if (e->mode == PBD_MODE_TILED) {
-            CKE(enqueue_step_tiled(e, e->stream, &L));
+        } else if (e->mode == PBD_MODE_RESIDENT) {
+            CKE(enqueue_step_resident(e, e->stream, &L));
         } else {
             unsigned long long LL = 0;
             if (!e->graphValid) { CKE(ensure_graph(e, &LL)); e->graphLaunches = LL; }
@@ -1320,7 +1410,7 @@ extern "C" int pbd_get_stats(pbd_engine *e, pbd_stats *out) {
 
 extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegrate, float *msVelocity, unsigned *launchesPerType) {
     if (!e) return fail("null engine");
-    if (e->mode == PBD_MODE_TILED) return fail("pbd_profile_step: per-bucket launches do not exist in the tiled mode (select another mode first)");
+    if (e->mode == PBD_MODE_RESIDENT) return fail("pbd_profile_step: per-bucket launches do not exist in the resident mode (select another mode first)");
     CKE(use(e)); CKE(flatten(e));
     CK(cudaStreamSynchronize(e->stream));
     // One event between every pair of consecutive launches, all recorded in stream order without host synchronisation

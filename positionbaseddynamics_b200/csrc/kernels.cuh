@@ -10,7 +10,7 @@
 //                   gravity is a uniform (TimeStep::clearAccelerations sets a = g for every dynamic particle, TimeStep.cpp:28-62)
 //   k_project<T>  : one (colour,type) bucket of TimeStepController::positionConstraintProjection (TimeStepController.cpp:270-286)
 //   k_velocity    : TimeStepController.cpp:155-162 + TimeIntegration::velocityUpdateFirstOrder/SecondOrder (TimeIntegration.cpp:42-51, 69-79)
-//   k_step_persistent : the whole step in one cooperative launch, grid barrier between colour phases
+//   k_step_resident (resident.cuh): the whole step in one launch, positions resident in the shared memory of thread-block clusters
 #pragma once
 #include "device_image.h"
 #include "solvers.cuh"
@@ -42,7 +42,7 @@ __device__ __forceinline__ void stp(float4 *p, const float4 &v) { if (v.w != 0.0
 __device__ __forceinline__ float matv(const TypeArrays &a, int slot, unsigned i) {
     return a.mat[slot] ? __ldg(a.mat[slot] + i) : a.matU[slot];
 }
-__device__ __forceinline__ float xpbd_alpha(float k, float dt) { return (k != 0.0f) ? 1.0f / (k * dt * dt) : 0.0f; }
+__device__ __forceinline__ float xpbd_alpha(float k, float dt) { return (k != 0.0f) ? frcp(k * dt * dt) : 0.0f; }
 
 // What a constraint streams from HBM before it touches any particle: indices + per-constraint constants.  These never
 // change during a step, so they can be fetched ahead of the dependency on the previous colour phase (before the PDL
@@ -80,10 +80,22 @@ __device__ __forceinline__ Streamed load_streamed(const TypeArrays &a, unsigned 
     return s;
 }
 
+// Particle accessors: where a constraint's particle index points to.
+//   GlobalAcc : the float4 array in global memory (L2-resident), index = device slot
+//   ClusterAcc (resident.cuh): bit 31 set -> slot in the shared-memory tile of a CTA of the executing cluster (DSMEM), else global
+// handle(idx) resolves the address once; ld / st take the handle (a particle is read and written through the same one)
+template <bool CA> struct GlobalAcc {
+    typedef float4 *Handle;
+    float4 *pos;
+    __device__ __forceinline__ Handle handle(unsigned idx) const { return pos + idx; }
+    __device__ __forceinline__ float4 ld(Handle h) const { return ldp<CA>(h); }
+    __device__ __forceinline__ void st(Handle h, const float4 &v) const { stp(h, v); }
+};
+
 // Gather -> project -> scatter for constraint i (index into the type's arrays) whose streamed part is already here.
 // Joints couple rigid bodies (their own small state arrays, L2 only) with each other or with a particle.
-template <int T>
-__device__ __forceinline__ void project_joint(float4 *pos, const TypeArrays &a, const Streamed &s) {
+template <int T, class Acc>
+__device__ __forceinline__ void project_joint(const Acc &acc, const TypeArrays &a, const Streamed &s) {
     float4 X0 = __ldcg(a.rbX + s.b.x), Q0 = __ldcg(a.rbQ + s.b.x);
     const float4 I0 = __ldg(a.rbIinv + s.b.x);
     if (T == PBD_BALLJOINT) {
@@ -92,34 +104,27 @@ __device__ __forceinline__ void project_joint(float4 *pos, const TypeArrays &a, 
         project_balljoint(X0, Q0, mk(I0.x, I0.y, I0.z), X1, Q1, mk(I1.x, I1.y, I1.z), mk(s.g0.x, s.g0.y, s.g0.z), mk(s.g1.x, s.g1.y, s.g1.z));
         if (X1.w != 0.0f) { __stcg(a.rbX + s.b.y, X1); __stcg(a.rbQ + s.b.y, Q1); }
     } else {
-        float4 p = __ldcg(pos + s.b.y);
+        const typename Acc::Handle hp = acc.handle(s.b.y);
+        float4 p = acc.ld(hp);
         project_rb_particle_balljoint(X0, Q0, mk(I0.x, I0.y, I0.z), p, mk(s.g0.x, s.g0.y, s.g0.z));
-        stp(pos + s.b.y, p);
+        acc.st(hp, p);
     }
     if (X0.w != 0.0f) { __stcg(a.rbX + s.b.x, X0); __stcg(a.rbQ + s.b.x, Q0); }
 }
 
-// Particle accessors: where a constraint's particle index points to.
-//   GlobalAcc : the float4 array in global memory (L2-resident), index = device slot
-//   tiled kernel (tiled.cuh): bit 31 set -> slot of the CTA's shared-memory tile, else global
-template <bool CA> struct GlobalAcc {
-    float4 *pos;
-    __device__ __forceinline__ float4 ld(unsigned idx) const { return ldp<CA>(pos + idx); }
-    __device__ __forceinline__ void st(unsigned idx, const float4 &v) const { stp(pos + idx, v); }
-    __device__ __forceinline__ float4 *global() const { return pos; }
-};
-
-template <int T, class Acc>
+// VAR: compile-time layout variant of the type (IsometricBending: 0 = rank-1 Kp, 1 = full Q), -1 = read a.variant at run time
+template <int T, class Acc, int VAR = -1>
 __device__ __forceinline__ void project_streamed_acc(const Acc &acc, const TypeArrays &a, unsigned i, const Streamed &s, float dt,
-                                                     bool iterZero, const float *stagedLambda = nullptr) {
-    if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) { project_joint<T>(acc.global(), a, s); return; }
+                                                     bool iterZero, bool lambdaGiven = false, float lambdaValue = 0.0f) {
+    if (T == PBD_BALLJOINT || T == PBD_RB_PARTICLE_BALLJOINT) { project_joint<T>(acc, a, s); return; }
     constexpr bool XPBD = (T == PBD_DISTANCE_XPBD || T == PBD_VOLUME_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_FEMTET_XPBD);
     constexpr int NB = (T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD) ? 2 : ((T == PBD_FEMTRIANGLE || T == PBD_STRAINTRIANGLE) ? 3 : 4);
-    float4 p0 = acc.ld(s.b.x), p1 = acc.ld(s.b.y), p2, p3;
-    if (NB >= 3) p2 = acc.ld(s.b.z);
-    if (NB >= 4) p3 = acc.ld(s.b.w);
+    const typename Acc::Handle h0 = acc.handle(s.b.x), h1 = acc.handle(s.b.y), h2 = acc.handle(NB >= 3 ? s.b.z : s.b.x), h3 = acc.handle(NB >= 4 ? s.b.w : s.b.x);
+    float4 p0 = acc.ld(h0), p1 = acc.ld(h1), p2, p3;
+    if (NB >= 3) p2 = acc.ld(h2);
+    if (NB >= 4) p3 = acc.ld(h3);
     float lam = 0.0f;
-    if (XPBD && !iterZero) lam = stagedLambda ? *stagedLambda : __ldcg(a.lambda + i);  // m_lambda; zero at the first sweep of a substep (Constraints.cpp:1241-1242)
+    if (XPBD && !iterZero) lam = lambdaGiven ? lambdaValue : __ldcg(a.lambda + i);  // m_lambda; zero at the first sweep of a substep (Constraints.cpp:1241-1242)
 
     if (T == PBD_DISTANCE) {
         project_distance(p0, p1, s.s0, matv(a, 0, i));
@@ -141,7 +146,7 @@ __device__ __forceinline__ void project_streamed_acc(const Acc &acc, const TypeA
         constexpr bool X = (T == PBD_ISOBENDING_XPBD);
         const float k = matv(a, 0, i);
         const float alpha = X ? xpbd_alpha(k, dt) : 0.0f;
-        if (a.variant == 0) project_isobending_rank1<X>(p0, p1, p2, p3, s.g0, k, alpha, lam);
+        if (VAR == 0 || (VAR < 0 && a.variant == 0)) project_isobending_rank1<X>(p0, p1, p2, p3, s.g0, k, alpha, lam);
         else project_isobending_fullq<X>(p0, p1, p2, p3, s.g0, __ldg(a.gv[1] + i), __ldg(a.gv[2] + i), __ldg(a.gv[3] + i), k, alpha, lam);
     } else if (T == PBD_FEMTET || T == PBD_FEMTET_XPBD || T == PBD_STRAINTET) {
         M3 inv;
@@ -156,14 +161,14 @@ __device__ __forceinline__ void project_streamed_acc(const Acc &acc, const TypeA
     }
 
     if (XPBD) __stcg(a.lambda + i, lam);
-    acc.st(s.b.x, p0); acc.st(s.b.y, p1);
-    if (NB >= 3) acc.st(s.b.z, p2);
-    if (NB >= 4) acc.st(s.b.w, p3);
+    acc.st(h0, p0); acc.st(h1, p1);
+    if (NB >= 3) acc.st(h2, p2);
+    if (NB >= 4) acc.st(h3, p3);
 }
 
-template <int T, bool CA>
+template <int T, bool CA, int VAR = -1>
 __device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &a, unsigned i, const Streamed &s, float dt, bool iterZero) {
-    project_streamed_acc<T>(GlobalAcc<CA>{pos}, a, i, s, dt, iterZero);
+    project_streamed_acc<T, GlobalAcc<CA>, VAR>(GlobalAcc<CA>{pos}, a, i, s, dt, iterZero);
 }
 
 #ifndef PBD_PROJECT_THREADS
@@ -171,7 +176,7 @@ __device__ __forceinline__ void project_streamed(float4 *pos, const TypeArrays &
 #endif
 constexpr int kProjectThreads = PBD_PROJECT_THREADS;
 
-template <int T, bool CA>
+template <int T, bool CA, int VAR>
 __global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeArrays a, unsigned first,
                                                              unsigned count, float dt, int iterZero) {
     pdl_launch_dependents();
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeAr
     if (i >= count) return;  // an exited thread counts as having passed the dependency
     const Streamed s = load_streamed<T>(a, first + i);
     pdl_wait_after(s.b.x ^ s.b.y, s.g0.x + s.g1.x + s.s0 + s.s1);
-    project_streamed<T, CA>(pos, a, first + i, s, dt, iterZero != 0);
+    project_streamed<T, CA, VAR>(pos, a, first + i, s, dt, iterZero != 0);
 }
 
 // Several (colour,type) buckets of ONE colour in a single launch: buckets of a colour touch disjoint particles, so they
@@ -241,17 +246,13 @@ __global__ void __launch_bounds__(256) k_integrate(float4 *__restrict__ pos, flo
 //              first order in both modes, as in the reference)
 struct RbState { float4 *X, *Q, *V, *W, *oldX, *lastX, *oldQ, *lastQ; const float4 *I, *Iinv; unsigned n; };
 
-__global__ void k_rb_integrate(RbState r, float h, float gx, float gy, float gz) {
-    pdl_launch_dependents();
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r.n) return;
-    pdl_wait();
-    float4 X = r.X[i], Q = r.Q[i], V = r.V[i], W = r.W[i];
+__device__ __forceinline__ void rb_integrate_body(const RbState &r, unsigned i, float h, float gx, float gy, float gz) {
+    float4 X = __ldcg(r.X + i), Q = __ldcg(r.Q + i), V = r.V[i], W = r.W[i];
     r.lastX[i] = r.oldX[i]; r.oldX[i] = X;
     r.lastQ[i] = r.oldQ[i]; r.oldQ[i] = Q;
     if (V.w != 0.0f) {  // V.w = mass
-        V.x += gx * h; V.y += gy * h; V.z += gz * h;
-        X.x += V.x * h; X.y += V.y * h; X.z += V.z * h;
+        V.x = fmaf(gx, h, V.x); V.y = fmaf(gy, h, V.y); V.z = fmaf(gz, h, V.z);
+        X.x = fmaf(V.x, h, X.x); X.y = fmaf(V.y, h, X.y); X.z = fmaf(V.z, h, X.z);
         const M3 R = qmatrix(Q);
         const float4 I = r.I[i], Ii = r.Iinv[i];
         const M3 Iw = world_tensor(R, mk(I.x, I.y, I.z)), Jw = world_tensor(R, mk(Ii.x, Ii.y, Ii.z));
@@ -262,15 +263,10 @@ __global__ void k_rb_integrate(RbState r, float h, float gx, float gy, float gz)
         const float hh = h * 0.5f;
         Q = qnormalize(make_float4(Q.x + hh * dq.x, Q.y + hh * dq.y, Q.z + hh * dq.z, Q.w + hh * dq.w));
         W.x = om.x; W.y = om.y; W.z = om.z;
-        r.X[i] = X; r.Q[i] = Q; r.V[i] = V; r.W[i] = W;
+        __stcg(r.X + i, X); __stcg(r.Q + i, Q); r.V[i] = V; r.W[i] = W;
     }
 }
-
-__global__ void k_rb_velocity(RbState r, float invH, float twoInvH, int secondOrder) {
-    pdl_launch_dependents();
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r.n) return;
-    pdl_wait();
+__device__ __forceinline__ void rb_velocity_body(const RbState &r, unsigned i, float invH, float twoInvH, int secondOrder) {
     float4 V = r.V[i];
     if (V.w == 0.0f) return;
     const float4 X = __ldcg(r.X + i), Q = __ldcg(r.Q + i), o = r.oldX[i], oq = r.oldQ[i];
@@ -283,6 +279,22 @@ __global__ void k_rb_velocity(RbState r, float invH, float twoInvH, int secondOr
     float4 W = r.W[i];
     W.x = rel.x * twoInvH; W.y = rel.y * twoInvH; W.z = rel.z * twoInvH;
     r.V[i] = V; r.W[i] = W;
+}
+
+__global__ void k_rb_integrate(RbState r, float h, float gx, float gy, float gz) {
+    pdl_launch_dependents();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n) return;
+    pdl_wait();
+    rb_integrate_body(r, i, h, gx, gy, gz);
+}
+
+__global__ void k_rb_velocity(RbState r, float invH, float twoInvH, int secondOrder) {
+    pdl_launch_dependents();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.n) return;
+    pdl_wait();
+    rb_velocity_body(r, i, invH, twoInvH, secondOrder);
 }
 
 // v = (1/h)(x - oldX)   or   (1/h)(1.5 x - 2 oldX + 0.5 lastX)

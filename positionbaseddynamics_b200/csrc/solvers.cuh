@@ -28,28 +28,39 @@ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y 
 __device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
-    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 __device__ __forceinline__ float sq(V3 a) { return dot(a, a); }
 __device__ __forceinline__ float comp(const V3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// The library is compiled with -fmad=false so that a projection is the same arithmetic in every kernel it is inlined into
+// (the execution modes are bit-identical, tested); every multiply-add that should fuse is therefore written as fmaf().
+__device__ __forceinline__ V3 madd(V3 a, float s, V3 b) { return mk(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }  // a s + b
+__device__ __forceinline__ float fma3(float a0, float b0, float a1, float b1, float a2, float b2) { return fmaf(a0, b0, fmaf(a1, b1, a2 * b2)); }
+// 1/x and a/b by MUFU.RCP (<= 1 ulp / 2 ulp): none of the reference's branches tests a quotient, only its operands
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 // x += c only for dynamic particles (every <X>Constraint::solvePositionConstraint: "if (invMass != 0) x += corr")
 __device__ __forceinline__ void apply(float4 &p, V3 c) {
     if (p.w != 0.0f) { p.x += c.x; p.y += c.y; p.z += c.z; }
+}
+__device__ __forceinline__ void apply(float4 &p, V3 g, float s) {  // x += g s
+    if (p.w != 0.0f) { p.x = fmaf(g.x, s, p.x); p.y = fmaf(g.y, s, p.y); p.z = fmaf(g.z, s, p.z); }
 }
 
 struct M3 { float m[3][3]; };  // always indexed with compile-time constants after unrolling -> registers
 
 __device__ __forceinline__ float det3(const M3 &a) {
-    return a.m[0][0] * (a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1]) -
-           a.m[0][1] * (a.m[1][0] * a.m[2][2] - a.m[1][2] * a.m[2][0]) +
-           a.m[0][2] * (a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0]);
+    const float c0 = fmaf(a.m[1][1], a.m[2][2], -(a.m[1][2] * a.m[2][1]));
+    const float c1 = fmaf(a.m[1][0], a.m[2][2], -(a.m[1][2] * a.m[2][0]));
+    const float c2 = fmaf(a.m[1][0], a.m[2][1], -(a.m[1][1] * a.m[2][0]));
+    return fmaf(a.m[0][0], c0, fmaf(a.m[0][2], c2, -(a.m[0][1] * c1)));
 }
 __device__ __forceinline__ M3 mul(const M3 &a, const M3 &b) {
     M3 r;
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+        for (int j = 0; j < 3; j++) r.m[i][j] = fma3(a.m[i][0], b.m[0][j], a.m[i][1], b.m[1][j], a.m[i][2], b.m[2][j]);
     return r;
 }
 __device__ __forceinline__ M3 mulT(const M3 &a, const M3 &b) {  // a * b^T
@@ -57,7 +68,7 @@ __device__ __forceinline__ M3 mulT(const M3 &a, const M3 &b) {  // a * b^T
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[j][0] + a.m[i][1] * b.m[j][1] + a.m[i][2] * b.m[j][2];
+        for (int j = 0; j < 3; j++) r.m[i][j] = fma3(a.m[i][0], b.m[j][0], a.m[i][1], b.m[j][1], a.m[i][2], b.m[j][2]);
     return r;
 }
 __device__ __forceinline__ M3 Tmul(const M3 &a, const M3 &b) {  // a^T * b
@@ -65,7 +76,7 @@ __device__ __forceinline__ M3 Tmul(const M3 &a, const M3 &b) {  // a^T * b
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) r.m[i][j] = a.m[0][i] * b.m[0][j] + a.m[1][i] * b.m[1][j] + a.m[2][i] * b.m[2][j];
+        for (int j = 0; j < 3; j++) r.m[i][j] = fma3(a.m[0][i], b.m[0][j], a.m[1][i], b.m[1][j], a.m[2][i], b.m[2][j]);
     return r;
 }
 
@@ -78,10 +89,10 @@ __device__ __forceinline__ void project_distance(float4 &p0, float4 &p1, float r
     V3 n = xyz(p1) - xyz(p0);
     const float d2 = sq(n);
     const float d = sqrtf(d2);
-    if (d2 > 0.0f) n = n * (1.0f / d);  // Eigen normalize() leaves the zero vector untouched
-    const V3 corr = (n * k) * ((d - rest) / wSum);
-    apply(p0, corr * p0.w);
-    apply(p1, corr * (-p1.w));
+    if (d2 > 0.0f) n = n * frcp(d);  // Eigen normalize() leaves the zero vector untouched
+    const float c = k * fdiv(d - rest, wSum);
+    apply(p0, n, c * p0.w);
+    apply(p1, n, -(c * p1.w));
 }
 
 // XPBD::solve_DistanceConstraint (XPBD.cpp:14-60).  alpha = 1/(k dt^2) (0 when k == 0) is a bucket uniform.
@@ -91,14 +102,13 @@ __device__ __forceinline__ void project_distance_xpbd(float4 &p0, float4 &p1, fl
     const float d = sqrtf(sq(n));
     const float C = d - rest;
     if (!(d > 1.0e-6f)) return;
-    n = n * (1.0f / d);
     K += alpha;
     if (!(fabsf(K) > 1.0e-6f)) return;
-    const float dl = -(C + alpha * lambda) / K;
+    const float dl = -fdiv(fmaf(alpha, lambda, C), K);
     lambda += dl;
-    const V3 pt = n * dl;
-    apply(p0, pt * p0.w);
-    apply(p1, pt * (-p1.w));
+    const float c = dl * frcp(d);  // pt = (n / d) dl
+    apply(p0, n, c * p0.w);
+    apply(p1, n, -(c * p1.w));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -115,22 +125,22 @@ __device__ __forceinline__ void project_volume(float4 &q0, float4 &q1, float4 &q
     const V3 g1 = cross(p2 - p0, p3 - p0);
     const V3 g2 = cross(p0 - p1, p3 - p1);
     const V3 g3 = cross(p1 - p0, p2 - p0);
-    float K = q0.w * sq(g0) + q1.w * sq(g1) + q2.w * sq(g2) + q3.w * sq(g3);
+    float K = fmaf(q0.w, sq(g0), fmaf(q1.w, sq(g1), fmaf(q2.w, sq(g2), q3.w * sq(g3))));
     float s;
     if (XPBD) {
         K += alpha;
         if (fabsf(K) < PBD_EPS) return;
-        const float dl = -((volume - restVolume) + alpha * lambda) / K;
+        const float dl = -fdiv(fmaf(alpha, lambda, volume - restVolume), K);
         lambda += dl;
         s = dl;
     } else {
         if (fabsf(K) < PBD_EPS) return;
-        s = -(k * (volume - restVolume) / K);
+        s = -fdiv(k * (volume - restVolume), K);
     }
-    apply(q0, g0 * (s * q0.w));
-    apply(q1, g1 * (s * q1.w));
-    apply(q2, g2 * (s * q2.w));
-    apply(q3, g3 * (s * q3.w));
+    apply(q0, g0, s * q0.w);
+    apply(q1, g1, s * q1.w);
+    apply(q2, g2, s * q2.w);
+    apply(q3, g3, s * q3.w);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -150,26 +160,27 @@ __device__ __forceinline__ void project_isobending_rank1(float4 &q0, float4 &q1,
                                                          float k, float alpha, float &lambda) {
     // solver order: x[0]=p2, x[1]=p3, x[2]=p0, x[3]=p1
     const V3 x0 = xyz(q2);
-    const V3 y = (xyz(q3) - x0) * Kp.y + (xyz(q0) - x0) * Kp.z + (xyz(q1) - x0) * Kp.w;
+    const V3 y = madd(xyz(q3) - x0, Kp.y, madd(xyz(q0) - x0, Kp.z, (xyz(q1) - x0) * Kp.w));
     const float yy = sq(y);
     const float energy = -0.5f * yy;
     // sum_j w_j |grad_j|^2 = |y|^2 sum_j w_j Kp_j^2   (w_j == 0 contributes nothing, as in the reference's skip)
-    float sum = yy * (q2.w * Kp.x * Kp.x + q3.w * Kp.y * Kp.y + q0.w * Kp.z * Kp.z + q1.w * Kp.w * Kp.w);
+    const float wk0 = q0.w * Kp.z, wk1 = q1.w * Kp.w, wk2 = q2.w * Kp.x, wk3 = q3.w * Kp.y;  // w_j Kp_j
+    float sum = yy * fmaf(wk2, Kp.x, fmaf(wk3, Kp.y, fmaf(wk0, Kp.z, wk1 * Kp.w)));
     float s;  // corr_j = s * w_j * grad_j = -s * w_j * Kp_j * y
     if (XPBD) {
         sum += alpha;
         if (!(fabsf(sum) > PBD_EPS)) return;
-        const float dl = -(energy + alpha * lambda) / sum;
+        const float dl = -fdiv(fmaf(alpha, lambda, energy), sum);
         lambda += dl;
         s = dl;
     } else {
         if (!(fabsf(sum) > PBD_EPS)) return;
-        s = -k * (energy / sum);
+        s = -k * fdiv(energy, sum);
     }
-    apply(q0, y * (-s * q0.w * Kp.z));
-    apply(q1, y * (-s * q1.w * Kp.w));
-    apply(q2, y * (-s * q2.w * Kp.x));
-    apply(q3, y * (-s * q3.w * Kp.y));
+    apply(q0, y, -s * wk0);
+    apply(q1, y, -s * wk1);
+    apply(q2, y, -s * wk2);
+    apply(q3, y, -s * wk3);
 }
 
 // General (user-modified) Q: literal evaluation as the reference does it.  Q rows in the solver's order.
@@ -221,37 +232,37 @@ __device__ __forceinline__ void project_isobending_fullq(float4 &q0, float4 &q1,
 struct FemTriMaterial { float C00, C01, C10, C11, C22; };
 __device__ __forceinline__ FemTriMaterial femtri_material(float Ex, float Ey, float Exy, float nuxy, float nuyx) {
     FemTriMaterial m;
-    const float den = 1.0f - nuxy * nuyx;
-    m.C00 = Ex / den; m.C01 = Ex * nuyx / den; m.C11 = Ey / den; m.C10 = Ey * nuxy / den; m.C22 = Exy;
+    const float den = frcp(1.0f - nuxy * nuyx);
+    m.C00 = Ex * den; m.C01 = Ex * nuyx * den; m.C11 = Ey * den; m.C10 = Ey * nuxy * den; m.C22 = Exy;
     return m;
 }
 __device__ __forceinline__ void project_femtriangle(float4 &q0, float4 &q1, float4 &q2, float area, float4 inv,
                                                     const FemTriMaterial &mat) {
     const V3 p13 = xyz(q0) - xyz(q2), p23 = xyz(q1) - xyz(q2);
     // F (3x2) = [p13 p23] * inv
-    const V3 F0 = p13 * inv.x + p23 * inv.z;
-    const V3 F1 = p13 * inv.y + p23 * inv.w;
-    const float e00 = 0.5f * (sq(F0) - 1.0f);
-    const float e11 = 0.5f * (sq(F1) - 1.0f);
+    const V3 F0 = madd(p13, inv.x, p23 * inv.z);
+    const V3 F1 = madd(p13, inv.y, p23 * inv.w);
+    const float e00 = fmaf(0.5f, sq(F0), -0.5f);
+    const float e11 = fmaf(0.5f, sq(F1), -0.5f);
     const float e01 = 0.5f * dot(F0, F1);
-    const float s00 = mat.C00 * e00 + mat.C01 * e11;
-    const float s11 = mat.C10 * e00 + mat.C11 * e11;
+    const float s00 = fmaf(mat.C00, e00, mat.C01 * e11);
+    const float s11 = fmaf(mat.C10, e00, mat.C11 * e11);
     const float s01 = mat.C22 * e01;
     // first Piola-Kirchhoff (3x2) = F * S
-    const V3 P0 = F0 * s00 + F1 * s01;
-    const V3 P1 = F0 * s01 + F1 * s11;
-    const float psi = 0.5f * (e00 * s00 + 2.0f * e01 * s01 + e11 * s11);
+    const V3 P0 = madd(F0, s00, F1 * s01);
+    const V3 P1 = madd(F0, s01, F1 * s11);
+    const float psi = 0.5f * fmaf(e00, s00, fmaf(2.0f * e01, s01, e11 * s11));
     const float energy = area * psi;
     // H = area * P * inv^T ; gradC[0] = H col 0, gradC[1] = H col 1
-    const V3 g0 = (P0 * inv.x + P1 * inv.y) * area;
-    const V3 g1 = (P0 * inv.z + P1 * inv.w) * area;
+    const V3 g0 = madd(P0, inv.x, P1 * inv.y) * area;
+    const V3 g1 = madd(P0, inv.z, P1 * inv.w) * area;
     const V3 g2 = -g0 - g1;
-    const float sum = q0.w * sq(g0) + q1.w * sq(g1) + q2.w * sq(g2);
+    const float sum = fmaf(q0.w, sq(g0), fmaf(q1.w, sq(g1), q2.w * sq(g2)));
     if (!(fabsf(sum) > PBD_EPS)) return;
-    const float s = energy / sum;
-    apply(q0, g0 * (-(s * q0.w)));
-    apply(q1, g1 * (-(s * q1.w)));
-    apply(q2, g2 * (-(s * q2.w)));
+    const float s = -fdiv(energy, sum);
+    apply(q0, g0, s * q0.w);
+    apply(q1, g1, s * q1.w);
+    apply(q2, g2, s * q2.w);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -382,9 +393,9 @@ __device__ __forceinline__ void fem_energy_gradients(const V3 &x1, const V3 &x2,
     M3 F;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        F.m[0][c] = p14.x * inv.m[0][c] + p24.x * inv.m[1][c] + p34.x * inv.m[2][c];
-        F.m[1][c] = p14.y * inv.m[0][c] + p24.y * inv.m[1][c] + p34.y * inv.m[2][c];
-        F.m[2][c] = p14.z * inv.m[0][c] + p24.z * inv.m[1][c] + p34.z * inv.m[2][c];
+        F.m[0][c] = fma3(p14.x, inv.m[0][c], p24.x, inv.m[1][c], p34.x, inv.m[2][c]);
+        F.m[1][c] = fma3(p14.y, inv.m[0][c], p24.y, inv.m[1][c], p34.y, inv.m[2][c]);
+        F.m[2][c] = fma3(p14.z, inv.m[0][c], p24.z, inv.m[1][c], p34.z, inv.m[2][c]);
     }
     M3 sigma;
     float psi = 0.0f, trace;
@@ -394,19 +405,18 @@ __device__ __forceinline__ void fem_energy_gradients(const V3 &x1, const V3 &x2,
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int b = a; b < 3; b++) {
-                float s = F.m[0][a] * F.m[0][b] + F.m[1][a] * F.m[1][b] + F.m[2][a] * F.m[2][b];
-                if (a == b) s -= 1.0f;
-                e.m[a][b] = e.m[b][a] = 0.5f * s;
+                const float s = fma3(F.m[0][a], F.m[0][b], F.m[1][a], F.m[1][b], F.m[2][a], F.m[2][b]);
+                e.m[a][b] = e.m[b][a] = (a == b) ? fmaf(0.5f, s, -0.5f) : 0.5f * s;
             }
         trace = e.m[0][0] + e.m[1][1] + e.m[2][2];
-        const float ltrace = lambda * trace;
+        const float ltrace = lambda * trace, mu2 = 2.0f * mu;
         M3 S;
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                S.m[a][b] = 2.0f * mu * e.m[a][b] + ((a == b) ? ltrace : 0.0f);
-                psi += e.m[a][b] * e.m[a][b];
+                S.m[a][b] = (a == b) ? fmaf(mu2, e.m[a][b], ltrace) : mu2 * e.m[a][b];
+                psi = fmaf(e.m[a][b], e.m[a][b], psi);
             }
         sigma = mul(F, S);
     } else {
@@ -433,7 +443,7 @@ __device__ __forceinline__ void fem_energy_gradients(const V3 &x1, const V3 &x2,
                 psi += e.m[a][b] * e.m[a][b];
             }
     }
-    psi = mu * psi + 0.5f * lambda * trace * trace;
+    psi = fmaf(mu, psi, 0.5f * lambda * trace * trace);
     energy = restVolume * psi;
     // H = sigma * inv^T * restVolume; J[c] = column c of H
     M3 H = mulT(sigma, inv);
@@ -451,36 +461,36 @@ __device__ __forceinline__ void project_femtet(float4 &q0, float4 &q1, float4 &q
     const V3 p0 = xyz(q0), p1 = xyz(q1), p2 = xyz(q2), p3 = xyz(q3);
     // currentVolume (Constraints.cpp:1795) and volume (PositionBasedDynamics.cpp:1133) are the same triple product
     const float volume = dot(cross(p1 - p0, p2 - p0), p3 - p0) * (1.0f / 6.0f);
-    const bool handleInversion = (volume / restVolume) < 0.2f;
+    const bool handleInversion = (volume / restVolume) < 0.2f;  // a tested quotient: IEEE division
     const bool inversionBranch = handleInversion && !(volume > 0.0f);
     float mu, lambda;
     if (XPBD) {  // Lame parameters divided by E (XPBD.cpp:247-248)
-        mu = 0.5f / (1.0f + nu);
-        lambda = nu / (1.0f + nu) / (1.0f - 2.0f * nu);
+        mu = 0.5f * frcp(1.0f + nu);
+        lambda = nu * frcp((1.0f + nu) * (1.0f - 2.0f * nu));
     } else {
-        mu = E / 2.0f / (1.0f + nu);
-        lambda = E * nu / (1.0f + nu) / (1.0f - 2.0f * nu);
+        mu = 0.5f * E * frcp(1.0f + nu);
+        lambda = E * nu * frcp((1.0f + nu) * (1.0f - 2.0f * nu));
     }
     float energy; V3 J[4];
     fem_energy_gradients(p0, p1, p2, p3, inv, restVolume, mu, lambda, inversionBranch, energy, J);
-    float sum = q0.w * sq(J[0]) + q1.w * sq(J[1]) + q2.w * sq(J[2]) + q3.w * sq(J[3]);
+    float sum = fmaf(q0.w, sq(J[0]), fmaf(q1.w, sq(J[1]), fmaf(q2.w, sq(J[2]), q3.w * sq(J[3]))));
     float s;
     if (XPBD) {
         const float C = sqrtf(2.0f * energy);
-        const float alpha = 1.0f / (E * dt * dt);
-        sum += C * C * alpha;
+        const float alpha = frcp(E * dt * dt);
+        sum = fmaf(C * C, alpha, sum);
         if (sum < PBD_EPS) return;
-        const float l = -C * (C + alpha * multiplier) / sum;
+        const float l = -fdiv(C * fmaf(alpha, multiplier, C), sum);
         multiplier += l;
         s = l;
     } else {
         if (sum < PBD_EPS) return;
-        s = -(energy / sum);
+        s = -fdiv(energy, sum);
     }
-    apply(q0, J[0] * (s * q0.w));
-    apply(q1, J[1] * (s * q1.w));
-    apply(q2, J[2] * (s * q2.w));
-    apply(q3, J[3] * (s * q3.w));
+    apply(q0, J[0], s * q0.w);
+    apply(q1, J[1], s * q1.w);
+    apply(q2, J[2], s * q2.w);
+    apply(q3, J[3], s * q3.w);
 }
 
 // ---------------------------------------------------------------------------------------------------------

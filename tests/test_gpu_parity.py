@@ -84,16 +84,15 @@ def test_scene_vs_reference_f64(name, cpu_libs):
 
 @pytest.mark.parametrize("name", ["cloth_isobending_xpbd", "bar_fem_plus_volume", "cfg1_50x50", "mixed_cloth_solid"])
 def test_modes_agree_bitwise(name, cpu_libs):
-    """Plain launches, the replayed CUDA graph and the persistent cooperative kernel execute the same projections in the
-    same dependency order, so their results must be bit-identical."""
-    xs = [_run(name, mode, cpu_libs, "oracle") for mode in (2, 0, 1, 3)]
+    """Plain launches, the replayed CUDA graph and the resident cluster kernel (positions in distributed shared memory, tile-major
+    particle order) execute the same projections in the same dependency order, so their results must be bit-identical."""
+    xs = [_run(name, mode, cpu_libs, "oracle") for mode in (2, 0, 1)]
     assert (xs[0] == xs[1]).all()
     assert (xs[0] == xs[2]).all()
-    assert (xs[0] == xs[3]).all()  # tiled: particle tiles in shared memory, tile-major particle order
 
 
 def test_mode_switch_keeps_state_bitwise():
-    """Switching to the tiled mode permutes every particle array on the device (tile-major order) and back; the simulation
+    """Switching to the resident mode permutes every particle array on the device (tile-major order) and back; the simulation
     state must survive both moves bit for bit and the uploads/downloads in between must address the right particles."""
     from positionbaseddynamics_b200 import _capi
     from positionbaseddynamics_b200.model import HostModel
@@ -120,7 +119,7 @@ def test_mode_switch_keeps_state_bitwise():
         eng.close()
         return out
     a = run([(_capi.MODE_GRAPH, 6)])
-    b = run([(_capi.MODE_GRAPH, 2), (_capi.MODE_TILED, 2), (_capi.MODE_LAUNCH, 1), (_capi.MODE_TILED, 1)])
+    b = run([(_capi.MODE_GRAPH, 2), (_capi.MODE_RESIDENT, 2), (_capi.MODE_LAUNCH, 1), (_capi.MODE_RESIDENT, 1)])
     for u, w in zip(a, b):
         assert np.isfinite(u).all() and (u == w).all()
 
@@ -429,7 +428,7 @@ def test_engine_level_drop_in_with_rigid_bodies(cpu_libs):
     types, bodies, params, _ = cpu.constraints()
     off, ids = cpu.groups()
     mass, _ = cpu.masses()
-    rb = cpu.rigid_bodies()
+    rb = cpu.rigid_bodies(); rb0 = rb.copy()
     eng = _capi.Engine(0)
     eng.set_particles(cpu.get("x"), mass, x0=cpu.get("x0"))
     rb_mass = [0.0 if i % 3 == 0 else 1.0 for i in range(12)]
@@ -441,10 +440,17 @@ def test_engine_level_drop_in_with_rigid_bodies(cpu_libs):
     eng.step(6); eng.sync(); cpu.step(6)
     assert rel_position_error(eng.get_attr(_capi.ATTR_X), cpu.get("x")) <= TOL
     assert np.abs(eng.get_rigid_bodies()[:, :7] - cpu.rigid_bodies()[:, :7]).max() <= 1e-4
-    eng.set_mode(_capi.MODE_PERSISTENT)
-    with pytest.raises(_capi.PbdError):
-        eng.step(1)
-    eng.set_mode(_capi.MODE_TILED)
-    with pytest.raises(_capi.PbdError):
-        eng.step(1)
+    # the resident cluster kernel runs the joints inside its colour phases: same bits as the graph mode
+    x_graph, rb_graph = eng.get_attr(_capi.ATTR_X), eng.get_rigid_bodies()
+    eng2 = _capi.Engine(0)
+    eng2.set_particles(cpu.get("x0"), mass, x0=cpu.get("x0"))
+    eng2.set_rigid_bodies(rb_mass, rb0[:, :3], rb0[:, 3:7], inertia)
+    eng2.add_flat(types, bodies, params)
+    eng2.set_groups(off, ids)
+    eng2.set_params(dt=0.005, sub_steps=5, max_iter=1)
+    eng2.set_mode(_capi.MODE_RESIDENT)
+    eng2.step(6); eng2.sync()
+    assert (eng2.get_attr(_capi.ATTR_X) == x_graph).all()
+    assert (eng2.get_rigid_bodies() == rb_graph).all()
+    eng2.close()
     eng.close()
