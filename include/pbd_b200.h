@@ -57,7 +57,9 @@ enum pbd_solver_mode {
     PBD_MODE_GRAPH = 0,      /* one kernel per (colour,type) bucket, whole step replayed as a CUDA graph */
     PBD_MODE_RESIDENT = 1,   /* one launch per step: positions resident in the distributed shared memory of thread-block clusters,
                                 hardware cluster barrier between colours (csrc/resident.cuh); scenes up to ~1.5 M particles */
-    PBD_MODE_LAUNCH = 2      /* plain stream launches (debug / per-kernel profiling) */
+    PBD_MODE_LAUNCH = 2,     /* plain stream launches (debug / per-kernel profiling) */
+    PBD_MODE_JACOBI = 3      /* comparison path, NOT the reference's algorithm: colours ignored, one launch per type and sweep, corrections
+                                accumulated with float4 atomicAdd and averaged per particle (rigid-body joints are not supported) */
 };
 
 typedef struct pbd_stats {

@@ -45,17 +45,47 @@ public:
 
     void reset() override { TimeStep::reset(); m_boundConstraints = ~size_t(0); }
 
+    // Force a re-flatten at the next step.  The adapter notices on its own: added / removed constraints, particles and bodies
+    // (m_groupsInitialized, sizes), changed masses (compared every step) and the model-wide parameter setters (setClothStiffness,
+    // setSolidStiffness, ... rewrite every constraint of a type: sentinel constraints are compared every step).  Call this after
+    // editing members of individual constraints or rigid bodies by hand.
+    void invalidate() { m_boundConstraints = ~size_t(0); }
+    // The device owns oldX / lastX while this time step is installed (they feed the second-order velocity update); copy them back
+    // into the model before handing it to another TimeStep (TimeStepController.cpp:112-118 reads them).
+    bool downloadHistory(SimulationModel &model) {
+        ParticleData &pd = model.getParticles();
+        const unsigned n = pd.size();
+        if (!m_engine || n != m_boundParticles || n == 0) return false;
+        std::vector<float> t(3 * (size_t)n);
+        if (pbd_get_attr(m_engine, PBD_ATTR_OLDX, t.data())) { fail(); return false; }
+        for (unsigned i = 0; i < n; i++) pd.setOldPosition(i, Vector3r((Real)t[3 * i], (Real)t[3 * i + 1], (Real)t[3 * i + 2]));
+        if (pbd_get_attr(m_engine, PBD_ATTR_LASTX, t.data())) { fail(); return false; }
+        for (unsigned i = 0; i < n; i++) pd.setLastPosition(i, Vector3r((Real)t[3 * i], (Real)t[3 * i + 1], (Real)t[3 * i + 2]));
+        return true;
+    }
+
     // TimeStepController::step for the engine's path.  Host state in, host state out: the model's ParticleData / RigidBody
     // objects hold the result when this returns, so rendering and user code keep working unchanged.
     void step(SimulationModel &model) override {
         if (!m_engine) return;
+        // The contact path (TimeStepController.cpp:189-196: collision detection, then velocityConstraintProjection over the contact
+        // constraints, :298-357) is not on the GPU path: refuse such a model instead of silently simulating it without contacts.
+        if ((m_collisionDetection && !m_collisionDetection->getCollisionObjects().empty()) || !model.getRigidBodyContactConstraints().empty() ||
+            !model.getParticleRigidBodyContactConstraints().empty() || !model.getParticleSolidContactConstraints().empty()) {
+            m_error = "GpuTimeStepController: the model has collision objects / contact constraints; the contact path "
+                      "(TimeStepController.cpp:189-196, 298-357) runs on the CPU TimeStepController only";
+            return;
+        }
         ParticleData &pd = model.getParticles();
         SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
         const unsigned n = pd.size();
-        // (re)bind when the model changed: any add*Constraint clears m_groupsInitialized (SimulationModel.cpp)
+        // (re)bind when the model changed: any add*Constraint clears m_groupsInitialized (SimulationModel.cpp); parameter setters
+        // and hand edits do not (SimulationModel.h:266), hence the sentinel comparison
         if (!model.m_groupsInitialized || model.getConstraints().size() != m_boundConstraints || n != m_boundParticles ||
-            rbs.size() != m_boundBodies) {
+            rbs.size() != m_boundBodies || sentinelSignature(model) != m_signature) {
             if (!bind(model)) return;
+        } else if (m_checkMasses && massesChanged(pd, n)) {
+            if (pbd_set_masses(m_engine, m_mass.data())) return fail();  // ParticleData::setMass after the first step
         }
         TimeManager *tm = TimeManager::getCurrent();
         const Vector3r g(Simulation::getCurrent()->getVecValue<Real>(Simulation::GRAVITATION));
@@ -67,7 +97,7 @@ public:
             // Real == float: std::vector<Vector3r> is already n x 3 packed floats (Common/Common.h:31); the engine copies straight
             // from and into the model's own arrays (page-locked at bind time), no host-side conversion at all
             float *x = reinterpret_cast<float *>(&pd.getPosition(0)[0]), *v = reinterpret_cast<float *>(&pd.getVelocity(0)[0]);
-            if (x != m_pinnedX || v != m_pinnedV) pin(x, v, n);  // the vectors were reallocated
+            if (!m_pinFailed && (x != m_pinnedX || v != m_pinnedV)) pin(x, v, n);  // the vectors were (re)allocated
             if (pbd_step_host(m_engine, 1, x, v, x, v)) return fail();
         } else {
             packParticles(pd, n);
@@ -90,8 +120,56 @@ protected:
     unsigned m_boundParticles = ~0u;
     size_t m_boundBodies = ~size_t(0);
     std::string m_error;
-    std::vector<float> m_x, m_v;
+    std::vector<float> m_x, m_v, m_mass;
     float *m_pinnedX = nullptr, *m_pinnedV = nullptr;
+    bool m_pinFailed = false, m_checkMasses = true;
+    std::vector<float> m_signature;
+
+    // values of the first and the last constraint of the model plus one in the middle, per call: O(1)
+    static void appendConstraintValues(Constraint *c, std::vector<float> &sig) {
+        const int tid = c->getTypeId();
+        sig.push_back((float)tid);
+        if (tid == DistanceConstraint::TYPE_ID) sig.push_back((float)static_cast<DistanceConstraint *>(c)->m_stiffness);
+        else if (tid == DistanceConstraint_XPBD::TYPE_ID) sig.push_back((float)static_cast<DistanceConstraint_XPBD *>(c)->m_stiffness);
+        else if (tid == DihedralConstraint::TYPE_ID) sig.push_back((float)static_cast<DihedralConstraint *>(c)->m_stiffness);
+        else if (tid == IsometricBendingConstraint::TYPE_ID) sig.push_back((float)static_cast<IsometricBendingConstraint *>(c)->m_stiffness);
+        else if (tid == IsometricBendingConstraint_XPBD::TYPE_ID) sig.push_back((float)static_cast<IsometricBendingConstraint_XPBD *>(c)->m_stiffness);
+        else if (tid == FEMTriangleConstraint::TYPE_ID) { auto *d = static_cast<FEMTriangleConstraint *>(c);
+            for (Real v : {d->m_xxStiffness, d->m_yyStiffness, d->m_xyStiffness, d->m_xyPoissonRatio, d->m_yxPoissonRatio}) sig.push_back((float)v); }
+        else if (tid == StrainTriangleConstraint::TYPE_ID) { auto *d = static_cast<StrainTriangleConstraint *>(c);
+            for (Real v : {d->m_xxStiffness, d->m_yyStiffness, d->m_xyStiffness}) sig.push_back((float)v);
+            sig.push_back(d->m_normalizeStretch ? 1.f : 0.f); sig.push_back(d->m_normalizeShear ? 1.f : 0.f); }
+        else if (tid == VolumeConstraint::TYPE_ID) sig.push_back((float)static_cast<VolumeConstraint *>(c)->m_stiffness);
+        else if (tid == VolumeConstraint_XPBD::TYPE_ID) sig.push_back((float)static_cast<VolumeConstraint_XPBD *>(c)->m_stiffness);
+        else if (tid == FEMTetConstraint::TYPE_ID) { auto *d = static_cast<FEMTetConstraint *>(c); sig.push_back((float)d->m_stiffness); sig.push_back((float)d->m_poissonRatio); }
+        else if (tid == XPBD_FEMTetConstraint::TYPE_ID) { auto *d = static_cast<XPBD_FEMTetConstraint *>(c); sig.push_back((float)d->m_stiffness); sig.push_back((float)d->m_poissonRatio); }
+        else if (tid == StrainTetConstraint::TYPE_ID) { auto *d = static_cast<StrainTetConstraint *>(c); sig.push_back((float)d->m_stretchStiffness); sig.push_back((float)d->m_shearStiffness);
+            sig.push_back(d->m_normalizeStretch ? 1.f : 0.f); sig.push_back(d->m_normalizeShear ? 1.f : 0.f); }
+        else if (tid == ShapeMatchingConstraint::TYPE_ID) sig.push_back((float)static_cast<ShapeMatchingConstraint *>(c)->m_stiffness);
+    }
+    // The model-wide setters rewrite every constraint of a type, so the first and the last constraint of each run of equal type
+    // ids (the add*Constraints calls append type by type) see them; O(#runs) per step.
+    static std::vector<float> sentinelSignature(SimulationModel &model) {
+        std::vector<float> sig;
+        SimulationModel::ConstraintVector &cs = model.getConstraints();
+        const size_t N = cs.size();
+        if (N == 0) return sig;
+        // sample positions: both ends, and a binary subdivision down to 64 samples: finds every run boundary cheaply enough and
+        // does not depend on how the constraints were appended
+        const size_t samples = N < 64 ? N : 64;
+        for (size_t k = 0; k < samples; k++) appendConstraintValues(cs[(size_t)((double)k * (double)(N - 1) / (double)(samples > 1 ? samples - 1 : 1))], sig);
+        return sig;
+    }
+    bool massesChanged(ParticleData &pd, unsigned n) {
+        if (m_mass.size() != n) { m_mass.resize(n); for (unsigned i = 0; i < n; i++) m_mass[i] = (float)pd.getMass(i); return true; }
+        int changed = 0;
+#pragma omp parallel for schedule(static) reduction(| : changed)
+        for (int i = 0; i < (int)n; i++) {
+            const float m = (float)pd.getMass(i);
+            if (m != m_mass[i]) { m_mass[i] = m; changed |= 1; }
+        }
+        return changed != 0;
+    }
 
     void fail() { m_error = pbd_last_error(); }
     void unpin() {
@@ -101,8 +179,9 @@ protected:
     }
     void pin(float *x, float *v, unsigned n) {  // best effort: an unpinned array still works, only slower
         unpin();
-        if (pbd_pin_host(x, (size_t)n * 3 * sizeof(float)) == 0) m_pinnedX = x;
-        if (pbd_pin_host(v, (size_t)n * 3 * sizeof(float)) == 0) m_pinnedV = v;
+        if (m_pinFailed) return;  // do not retry every step
+        if (pbd_pin_host(x, (size_t)n * 3 * sizeof(float)) == 0) m_pinnedX = x; else m_pinFailed = true;
+        if (pbd_pin_host(v, (size_t)n * 3 * sizeof(float)) == 0) m_pinnedV = v; else m_pinFailed = true;
     }
 
     void initParameters() override {
@@ -231,6 +310,8 @@ protected:
         for (size_t gi = 0; gi < groups.size(); gi++) { gids.insert(gids.end(), groups[gi].begin(), groups[gi].end()); off[gi + 1] = (unsigned)gids.size(); }
         if (pbd_set_groups(m_engine, (unsigned)groups.size(), off.data(), gids.data())) { fail(); return false; }
         m_boundConstraints = cs.size(); m_boundParticles = n; m_boundBodies = rbs.size();
+        m_signature = sentinelSignature(model);
+        m_mass = mass;
         m_error.clear();
         return true;
     }

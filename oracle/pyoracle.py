@@ -55,11 +55,27 @@ def available(kind, precision):
     return os.path.exists(lib_path(kind, precision))
 
 
+def best_ref_variant():
+    """(path, flag) of the fastest fp32 reference build this host can run: the AVX-512 build (-march=x86-64-v4) when the CPU has
+    the x86-64-v4 feature set and the library travelled here, else the portable AVX2 build (-march=x86-64-v3)."""
+    v4 = os.path.join(HERE, "_ref", "libpbdref_f32_v4.so")
+    try:
+        flags = set()
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                flags = set(ln.split(":", 1)[1].split()); break
+        if os.path.exists(v4) and {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags:
+            return v4, "-march=x86-64-v4"
+    except OSError:
+        pass
+    return lib_path("ref", "f32"), "-march=x86-64-v3"
+
+
 class CpuPbd:
-    def __init__(self, kind="oracle", precision="f32"):
+    def __init__(self, kind="oracle", precision="f32", path=None):
         self.kind, self.precision = kind, precision
         self.prefix = "orc_" if kind == "oracle" else "ref_"
-        self.lib = C.CDLL(lib_path(kind, precision))
+        self.lib = C.CDLL(path or lib_path(kind, precision))
         for name in ("step", "time"):
             getattr(self.lib, self.prefix + name).restype = C.c_double
         assert self.f("real_size")() == (4 if precision == "f32" else 8)

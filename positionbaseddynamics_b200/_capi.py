@@ -17,7 +17,7 @@ TYPE_NAMES = ["Distance", "Distance_XPBD", "Dihedral", "IsometricBending", "Isom
               "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching", "BallJoint",
               "RigidBodyParticleBallJoint"]
 ATTR_X, ATTR_V, ATTR_X0, ATTR_OLDX, ATTR_LASTX = range(5)
-MODE_GRAPH, MODE_RESIDENT, MODE_LAUNCH = 0, 1, 2
+MODE_GRAPH, MODE_RESIDENT, MODE_LAUNCH, MODE_JACOBI = 0, 1, 2, 3
 
 # every symbol include/pbd_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "pbd_set_particles", "pbd_set_attr",

@@ -85,7 +85,7 @@ struct pbd_engine {
     int smCount = 148;
     // particles
     unsigned n = 0;
-    DevBuf pos, vel, oldp, lastp, pos0, stage, stage2, massStage;
+    DevBuf pos, vel, oldp, lastp, pos0, stage, stage2, massStage, jacobiDelta;
     // rigid bodies coupled through joints: float4 arrays X(xyz,invMass) Q(x,y,z,w) V(xyz,mass) W(omega) + history + inertia
     unsigned nRb = 0;
     DevBuf rbX, rbQ, rbV, rbW, rbOldX, rbLastX, rbOldQ, rbLastQ, rbI, rbIinv;
@@ -176,7 +176,7 @@ extern "C" int pbd_destroy(pbd_engine *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
-    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->stage2, &e->massStage, &e->dSlot, &e->dSlotOld, &e->relayoutTmp,
+    for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->stage2, &e->massStage, &e->jacobiDelta, &e->dSlot, &e->dSlotOld, &e->relayoutTmp,
                     &e->dColourStart, &e->dTileOff, &e->dTileStart, &e->dTileSmem, &e->dXArrive, &e->dXCounter, &e->dBuckets, &e->dTrace,
                     &e->rbX, &e->rbQ, &e->rbV, &e->rbW, &e->rbOldX, &e->rbLastX, &e->rbOldQ, &e->rbLastQ, &e->rbI, &e->rbIinv}) b->release();
     for (auto &d : e->dev) {
@@ -417,6 +417,9 @@ extern "C" int pbd_set_groups(pbd_engine *e, unsigned nGroups, const unsigned *o
     const unsigned N = e->numConstraints;
     if (nGroups == 0 && N != 0) return fail("pbd_set_groups: %u constraints but no groups", N);
     if (nGroups && offsets[nGroups] != N) return fail("pbd_set_groups: groups cover %u constraints, model has %u", offsets[nGroups], N);
+    if (nGroups && offsets[0] != 0) return fail("pbd_set_groups: offsets[0] must be 0");
+    for (unsigned g = 0; g < nGroups; g++)
+        if (offsets[g] > offsets[g + 1]) return fail("pbd_set_groups: offsets must be non-decreasing (group %u)", g);
     std::vector<unsigned char> seen(N, 0);
     for (unsigned i = 0; i < N; i++) {
         if (ids[i] >= N || seen[ids[i]]) return fail("pbd_set_groups: ids are not a permutation of 0..%u", N);
@@ -562,7 +565,7 @@ extern "C" int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsign
 }
 extern "C" int pbd_set_mode(pbd_engine *e, int mode) {
     if (!e) return fail("null engine");
-    if (mode != PBD_MODE_GRAPH && mode != PBD_MODE_RESIDENT && mode != PBD_MODE_LAUNCH) return fail("unknown solver mode %d", mode);
+    if (mode != PBD_MODE_GRAPH && mode != PBD_MODE_RESIDENT && mode != PBD_MODE_LAUNCH && mode != PBD_MODE_JACOBI) return fail("unknown solver mode %d", mode);
     if ((mode == PBD_MODE_RESIDENT) != (e->mode == PBD_MODE_RESIDENT)) e->imageDirty = true;  // the resident image encodes indices differently
     e->mode = mode; drop_graph(e);
     return 0;
@@ -623,21 +626,18 @@ struct ResidentPlan {
 
 static bool is_rb_body(int type, int k) { return type == PBD_BALLJOINT || (type == PBD_RB_PARTICLE_BALLJOINT && k == 0); }
 
-// the compiled instantiations of k_step_resident: F(kernel pointer) for the engine's (mask, block size)
-template <class F> static int with_resident_kernel(const pbd_engine *e, F &&f) {
+// the compiled instantiations of k_step_resident: F(kernel pointer) for the engine's (mask, block size, one CTA per cluster?)
+template <class F> static int with_resident_kernel(const pbd_engine *e, unsigned C, F &&f) {
     const unsigned th = e->resThreads;
+    const bool single = (C == 1);
     if (e->resMask == kMaskClothXPBD) {
-        if (th == 512) return f(k_step_resident<kMaskClothXPBD, 512>);
-        if (th == 640) return f(k_step_resident<kMaskClothXPBD, 640>);
-        if (th == 768) return f(k_step_resident<kMaskClothXPBD, 768>);
-        return f(k_step_resident<kMaskClothXPBD, 1024>);
+        if (th == 512) return single ? f(k_step_resident<kMaskClothXPBD, 512, true>) : f(k_step_resident<kMaskClothXPBD, 512, false>);
+        if (th == 768) return single ? f(k_step_resident<kMaskClothXPBD, 768, true>) : f(k_step_resident<kMaskClothXPBD, 768, false>);
+        return single ? f(k_step_resident<kMaskClothXPBD, 640, true>) : f(k_step_resident<kMaskClothXPBD, 640, false>);
     }
-    if (e->resMask == kMaskLight) {
-        if (th == 512) return f(k_step_resident<kMaskLight, 512>);
-        return f(k_step_resident<kMaskLight, 1024>);
-    }
-    if (th == 256) return f(k_step_resident<kMaskAll, 256>);
-    return f(k_step_resident<kMaskAll, 512>);
+    if (e->resMask == kMaskLight) return single ? f(k_step_resident<kMaskLight, 512, true>) : f(k_step_resident<kMaskLight, 512, false>);
+    if (th == 512) return single ? f(k_step_resident<kMaskAll, 512, true>) : f(k_step_resident<kMaskAll, 512, false>);
+    return single ? f(k_step_resident<kMaskAll, 256, true>) : f(k_step_resident<kMaskAll, 256, false>);
 }
 
 static void resident_launch_config(const pbd_engine *e, unsigned C, unsigned grid, size_t smem, cudaStream_t s, cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr) {
@@ -650,7 +650,7 @@ static void resident_launch_config(const pbd_engine *e, unsigned C, unsigned gri
 
 // how many clusters of C CTAs (one CTA per SM, `smem` bytes each) the device keeps resident at the same time
 static int resident_max_clusters(const pbd_engine *e, unsigned C, size_t smem, int *out) {
-    return with_resident_kernel(e, [&](auto kernel) -> int {
+    return with_resident_kernel(e, C, [&](auto kernel) -> int {
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynamicSmem));
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
@@ -668,9 +668,9 @@ static int choose_resident_shape(pbd_engine *e) {
     e->resMask = ((present & ~kMaskClothXPBD) == 0) ? kMaskClothXPBD : (((present & ~kMaskLight) == 0) ? kMaskLight : kMaskAll);
     // the block sizes the instantiations compile for without spilling (cloth 96 registers, light 128, everything 236)
     e->resThreads = (e->resMask == kMaskClothXPBD) ? 640u : ((e->resMask == kMaskLight) ? 512u : 256u);
-    if (const char *g = getenv("PBD_B200_RTHREADS")) { const int k = atoi(g); if (k == 256 || k == 512 || k == 640 || k == 768 || k == 1024) e->resThreads = (unsigned)k; }
+    if (const char *g = getenv("PBD_B200_RTHREADS")) { const int k = atoi(g); if (k == 256 || k == 512 || k == 640 || k == 768) e->resThreads = (unsigned)k; }
     if (e->resMask == kMaskAll && e->resThreads > 512u) e->resThreads = 512u;
-    if (e->resMask == kMaskLight && (e->resThreads == 768u || e->resThreads == 640u)) e->resThreads = 1024u;
+    if (e->resMask == kMaskLight) e->resThreads = 512u;
     if (e->resMask == kMaskClothXPBD && e->resThreads == 256u) e->resThreads = 512u;
     const unsigned nGroups = (unsigned)std::max<size_t>(e->groupOff.size(), 2) - 1;
     const unsigned perPhase = e->numConstraints / std::max(1u, nGroups);
@@ -683,14 +683,13 @@ static int choose_resident_shape(pbd_engine *e) {
         // one cluster: enough CTAs that a colour phase is about one item per thread, and that the tiles fit
         while (C < (unsigned)kMaxClusterCtas && (perPhase > C * 256u || e->n > C * cap)) C *= 2;
     } else {
-        // several clusters: the shape that puts the most SMs to work (ties: the larger cluster, fewer global-homed particles)
-        unsigned bestT = 0;
-        for (unsigned c : {16u, 8u}) {
-            int mc = 0;
-            CKE(resident_max_clusters(e, c, kMaxDynamicSmem, &mc));
-            if ((unsigned)mc * c > bestT) { bestT = (unsigned)mc * c; G = (unsigned)mc; C = c; }
-        }
-        if (bestT == 0) return fail("resident mode: no thread-block cluster of 8 or 16 CTAs with %zu bytes of shared memory is schedulable on this device", kMaxDynamicSmem);
+        // Too big for one cluster: one independent CTA per SM (clusters of 1).  Measured on cfg2 (profiles/README.md): 148 x 1 beats
+        // 74 x 2, 33 x 4, 15 x 8 and 7 x 16 -- larger clusters have fewer X items but idle SMs (a cluster must fit a GPC) and a
+        // colour barrier that waits for the slowest of C CTAs; with C = 1 the colour barrier is a __syncthreads.
+        int mc = 0;
+        CKE(resident_max_clusters(e, 1u, kMaxDynamicSmem, &mc));
+        if (mc < 1) return fail("resident mode: a CTA with %zu bytes of shared memory is not schedulable on this device", kMaxDynamicSmem);
+        C = 1; G = (unsigned)std::min(mc, e->smCount);
     }
     if (const char *g = getenv("PBD_B200_CLUSTERS")) {  // development knob "GxC"
         unsigned gg = 0, cc = 0;
@@ -701,8 +700,7 @@ static int choose_resident_shape(pbd_engine *e) {
     if (G > 1 && (e->nRb || !e->host[PBD_BALLJOINT].ids.empty() || !e->host[PBD_RB_PARTICLE_BALLJOINT].ids.empty()))
         return fail("resident mode: rigid-body coupling is supported for scenes that fit one cluster (use PBD_MODE_GRAPH)");
     e->resG = G; e->resC = C; e->nTiles = G * C;
-    e->resXThreads = (G > 1) ? 128u : 0u;
-    if (const char *g = getenv("PBD_B200_XTHREADS")) { const int k = atoi(g); if (G > 1 && k >= 32 && k % 32 == 0 && (unsigned)k < e->resThreads) e->resXThreads = (unsigned)k; }
+    e->resXThreads = (G > 1) ? 128u : 0u;  // refined in prepare_resident once the share of X items is known
     return 0;
 }
 
@@ -738,6 +736,25 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
                     if (spans) for (int k = 0; k < nb; k++) pl.homedGlobal[b[k]] = 1;
                 }
             }
+        // threads of a CTA dedicated to the X items: in proportion to their share, times 2.7 because an X item waits for L2 where
+        // the others read shared memory (measured on cfg2: 11 % X items, best with 192 of 640 threads)
+        if (G > 1) {
+            unsigned long long xItems = 0;
+            for (int t = 0; t < PBD_NUM_TYPES; t++) {
+                const HostType &h = e->host[t];
+                const int nb = type_shape(t).nBodies;
+                for (size_t c = 0; c < h.ids.size(); c++) {
+                    bool x = false;
+                    for (int k = 0; k < nb; k++) x |= (!is_rb_body(t, k) && pl.homedGlobal[h.bodies[c * nb + k]]);
+                    xItems += x;
+                }
+            }
+            const double share = (double)xItems / std::max(1u, e->numConstraints);
+            unsigned xt = ((unsigned)(e->resThreads * share * 2.7) + 31u) & ~31u;
+            xt = std::max(64u, std::min(xt, (e->resThreads / 2u) & ~31u));
+            if (const char *g = getenv("PBD_B200_XTHREADS")) { const int k = atoi(g); if (k >= 32 && k % 32 == 0 && (unsigned)k < e->resThreads) xt = (unsigned)k; }
+            e->resXThreads = xt;
+        }
         // tile-major slots: shared-memory particles first (host order), global-homed behind them
         std::vector<unsigned> cntS(T, 0), cntG(T, 0);
         for (unsigned i = 0; i < n; i++) (pl.homedGlobal[i] ? cntG : cntS)[pl.tileOf[i]]++;
@@ -773,6 +790,17 @@ static int flatten(pbd_engine *e) {
         else CKE(pbd_color_first_fit(e));
     }
     drop_graph(e);
+    // the particle / rigid-body counts may have shrunk since the constraints were added (pbd_set_particles, pbd_set_rigid_bodies)
+    for (int t = 0; t < PBD_NUM_TYPES; t++) {
+        const HostType &h = e->host[t];
+        const int nb = type_shape(t).nBodies;
+        for (size_t i = 0; i < h.bodies.size(); i++) {
+            const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && (i % nb) == 0);
+            if (h.bodies[i] >= (isRb ? e->nRb : e->n))
+                return fail("constraint of type %d refers to %s %u, but the engine holds %u: re-add the constraints after shrinking the model", t,
+                            isRb ? "rigid body" : "particle", h.bodies[i], isRb ? e->nRb : e->n);
+        }
+    }
     std::vector<std::pair<int, unsigned>> map;
     CKE(build_id_map(e, map));
     const unsigned nGroups = (unsigned)e->groupOff.size() - 1;
@@ -1228,7 +1256,7 @@ static int launch_resident(pbd_engine *e, cudaStream_t s, ResidentArgs &ra) {
             return fail("resident mode: the device runs %d clusters of %u CTAs at a time, the scene needs %u co-resident", mc, e->resC, e->resG);
         e->resChecked = true;
     }
-    return with_resident_kernel(e, [&](auto kernel) -> int {
+    return with_resident_kernel(e, e->resC, [&](auto kernel) -> int {
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynamicSmem));
         if (e->resC > 8) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
@@ -1255,6 +1283,8 @@ static int enqueue_step_resident(pbd_engine *e, cudaStream_t s, unsigned long lo
             streamBytes += (double)e->dev[t].count * (4.0 * sh.nBodies + 16.0 * sh.nGeoV + 4.0 * sh.nGeoS + (sh.xpbd ? 4.0 : 0.0));
         }
         ra.l2Prefetch = g ? atoi(g) : (streamBytes > 48.0e6 ? 1 : 0);
+        static const char *pm = getenv("PBD_B200_POLL");
+        ra.relaxedPoll = pm ? atoi(pm) : 0;
     }
     ra.h = h; ra.invH = (float)(1.0 / (double)h); ra.twoInvH = (float)(2.0 / (double)h); ra.gx = e->g[0]; ra.gy = e->g[1]; ra.gz = e->g[2];
     ra.secondOrder = e->velMethod;
@@ -1286,6 +1316,53 @@ static int enqueue_step_resident(pbd_engine *e, cudaStream_t s, unsigned long lo
     return launch_resident(e, s, ra);
 }
 
+// Jacobi comparison path (kernels.cuh): per sweep one launch per type over all its constraints + the averaging pass
+static int enqueue_step_jacobi(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
+    if (e->nRb || e->dev[PBD_BALLJOINT].count || e->dev[PBD_RB_PARTICLE_BALLJOINT].count)
+        return fail("PBD_MODE_JACOBI does not cover rigid-body coupling (use PBD_MODE_GRAPH)");
+    const float h = e->dt / (float)e->subSteps;
+    const float invH = (float)(1.0 / (double)h);
+    const unsigned n = e->n;
+    if (n == 0) { *launches = 0; return 0; }
+    if (!e->jacobiDelta.p || e->jacobiDelta.bytes < (size_t)n * sizeof(float4)) {
+        CKE(e->jacobiDelta.alloc((size_t)n * sizeof(float4)));
+        CK(cudaMemsetAsync(e->jacobiDelta.p, 0, (size_t)n * sizeof(float4), s));
+    }
+    const float4 *pos = (const float4 *)e->pos.p; float4 *delta = (float4 *)e->jacobiDelta.p;
+    unsigned long long L = 0;
+    for (unsigned sub = 0; sub < e->subSteps; sub++) {
+        k_integrate<<<nblk(n, 256), 256, 0, s>>>((float4 *)e->pos.p, (float4 *)e->vel.p, (float4 *)e->oldp.p, (float4 *)e->lastp.p, n, h, e->g[0], e->g[1], e->g[2], 1); L++;
+        for (unsigned it = 0; it < e->maxIter; it++) {
+            for (int t = 0; t < PBD_BALLJOINT; t++) {
+                const unsigned cnt = e->dev[t].count;
+                if (!cnt) continue;
+                const TypeArrays &a = e->dev[t].arrays;
+                const unsigned grid = nblk(cnt, 128);
+                const int iz = (it == 0);
+#define JB(T, V) k_project_jacobi<T, V><<<grid, 128, 0, s>>>(pos, delta, a, cnt, h, iz)
+                switch (t) {
+                case PBD_DISTANCE: JB(PBD_DISTANCE, 0); break; case PBD_DISTANCE_XPBD: JB(PBD_DISTANCE_XPBD, 0); break;
+                case PBD_DIHEDRAL: JB(PBD_DIHEDRAL, 0); break;
+                case PBD_ISOBENDING: if (a.variant) JB(PBD_ISOBENDING, 1); else JB(PBD_ISOBENDING, 0); break;
+                case PBD_ISOBENDING_XPBD: if (a.variant) JB(PBD_ISOBENDING_XPBD, 1); else JB(PBD_ISOBENDING_XPBD, 0); break;
+                case PBD_FEMTRIANGLE: JB(PBD_FEMTRIANGLE, 0); break; case PBD_STRAINTRIANGLE: JB(PBD_STRAINTRIANGLE, 0); break;
+                case PBD_VOLUME: JB(PBD_VOLUME, 0); break; case PBD_VOLUME_XPBD: JB(PBD_VOLUME_XPBD, 0); break;
+                case PBD_FEMTET: JB(PBD_FEMTET, 0); break; case PBD_FEMTET_XPBD: JB(PBD_FEMTET_XPBD, 0); break;
+                case PBD_STRAINTET: JB(PBD_STRAINTET, 0); break; case PBD_SHAPEMATCHING: JB(PBD_SHAPEMATCHING, 0); break;
+                default: break;
+                }
+#undef JB
+                L++;
+            }
+            k_jacobi_apply<<<nblk(n, 256), 256, 0, s>>>((float4 *)e->pos.p, delta, n); L++;
+        }
+        k_velocity<<<nblk(n, 256), 256, 0, s>>>((const float4 *)e->pos.p, (float4 *)e->vel.p, (const float4 *)e->oldp.p, (const float4 *)e->lastp.p, n, invH, e->velMethod); L++;
+    }
+    CK(cudaGetLastError());
+    *launches = L;
+    return 0;
+}
+
 static int ensure_graph(pbd_engine *e, unsigned long long *launchesPerStep) {
     if (e->graphValid) return 0;
     cudaGraph_t graph = nullptr;
@@ -1314,6 +1391,8 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
             CKE(enqueue_step_launches(e, e->stream, &L));
         } else if (e->mode == PBD_MODE_RESIDENT) {
             CKE(enqueue_step_resident(e, e->stream, &L));
+        } else if (e->mode == PBD_MODE_JACOBI) {
+            CKE(enqueue_step_jacobi(e, e->stream, &L));
         } else {
             unsigned long long LL = 0;
             if (!e->graphValid) { CKE(ensure_graph(e, &LL)); e->graphLaunches = LL; }
@@ -1343,12 +1422,14 @@ extern "C" int pbd_sync(pbd_engine *e) {
 
 extern "C" int pbd_pin_host(void *ptr, size_t bytes) {
     if (!ptr || !bytes) return fail("pbd_pin_host: null argument");
-    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    const cudaError_t err = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (err != cudaSuccess) { cudaGetLastError(); return fail("cudaHostRegister -> %s", cudaGetErrorString(err)); }  // clear the sticky per-thread error: a later CK(cudaGetLastError()) must not see it
     return 0;
 }
 extern "C" int pbd_unpin_host(void *ptr) {
     if (!ptr) return 0;
-    CK(cudaHostUnregister(ptr));
+    const cudaError_t err = cudaHostUnregister(ptr);
+    if (err != cudaSuccess) { cudaGetLastError(); return fail("cudaHostUnregister -> %s", cudaGetErrorString(err)); }
     return 0;
 }
 
@@ -1410,7 +1491,7 @@ extern "C" int pbd_get_stats(pbd_engine *e, pbd_stats *out) {
 
 extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegrate, float *msVelocity, unsigned *launchesPerType) {
     if (!e) return fail("null engine");
-    if (e->mode == PBD_MODE_RESIDENT) return fail("pbd_profile_step: per-bucket launches do not exist in the resident mode (select another mode first)");
+    if (e->mode == PBD_MODE_RESIDENT || e->mode == PBD_MODE_JACOBI) return fail("pbd_profile_step: per-bucket launches do not exist in this mode (select PBD_MODE_GRAPH or PBD_MODE_LAUNCH first)");
     CKE(use(e)); CKE(flatten(e));
     CK(cudaStreamSynchronize(e->stream));
     // One event between every pair of consecutive launches, all recorded in stream order without host synchronisation

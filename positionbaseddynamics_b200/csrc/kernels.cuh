@@ -187,6 +187,41 @@ __global__ void __launch_bounds__(kProjectThreads) k_project(float4 *pos, TypeAr
     project_streamed<T, CA, VAR>(pos, a, first + i, s, dt, iterZero != 0);
 }
 
+// ---- Jacobi comparison path (north_star: "a Jacobi path uses atomicAdd for comparison") -------------------------------------------
+// One launch per constraint TYPE and sweep over ALL its constraints, colours ignored: every projection reads the positions of the
+// sweep's start and adds its correction to a scratch float4 per particle with one vector atomicAdd (x, y, z, 1); k_jacobi_apply then
+// moves every touched particle by the average of its corrections.  A different algorithm from the reference's Gauss-Seidel sweep
+// (slower convergence, no ordering), so it is not parity-gated; it exists to price the colouring against atomics (profiles/README.md).
+struct JacobiAcc {
+    typedef unsigned Handle;
+    const float4 *pos; float4 *delta;
+    __device__ __forceinline__ Handle handle(unsigned idx) const { return idx; }
+    __device__ __forceinline__ float4 ld(Handle h) const { return __ldg(pos + h); }
+    __device__ __forceinline__ void st(Handle h, const float4 &v) const {
+        if (v.w == 0.0f) return;
+        const float4 o = __ldg(pos + h);
+        atomicAdd(delta + h, make_float4(v.x - o.x, v.y - o.y, v.z - o.z, 1.0f));  // RED.E.ADD.F32x4 (sm_90+)
+    }
+};
+template <int T, int VAR>
+__global__ void __launch_bounds__(kProjectThreads) k_project_jacobi(const float4 *pos, float4 *delta, TypeArrays a, unsigned count, float dt, int iterZero) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Streamed s = load_streamed<T>(a, i);
+    project_streamed_acc<T, JacobiAcc, VAR>(JacobiAcc{pos, delta}, a, i, s, dt, iterZero != 0);
+}
+__global__ void __launch_bounds__(256) k_jacobi_apply(float4 *__restrict__ pos, float4 *__restrict__ delta, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 d = delta[i];
+    if (d.w == 0.0f) return;
+    const float inv = 1.0f / d.w;
+    float4 x = pos[i];
+    x.x = fmaf(d.x, inv, x.x); x.y = fmaf(d.y, inv, x.y); x.z = fmaf(d.z, inv, x.z);
+    pos[i] = x;
+    delta[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Several (colour,type) buckets of ONE colour in a single launch: buckets of a colour touch disjoint particles, so they
 // need no ordering among themselves (the reference runs a whole colour group under one `omp parallel for`,
 // TimeStepController.cpp:275-285).  A CTA finds its segment from blockIdx and dispatches on the segment's type.

@@ -28,6 +28,7 @@
 // Constraint order inside a (colour,type) bucket: by executing tile, inside a tile the X items (touching a global-homed
 // particle) first; tileOff[bucket][2t], [2t+1], [2t+2] delimit the two runs of tile t (relative to the bucket's `first`).
 #pragma once
+#include <type_traits>
 #include <utility>
 #include "kernels.cuh"
 
@@ -50,6 +51,11 @@ __host__ __device__ inline size_t resident_smem_bytes(unsigned tileCap, unsigned
     return (size_t)tileCap * sizeof(float4) + (size_t)nBuckets * sizeof(RunEntry) + (size_t)(2u * nColours + 2u) * sizeof(unsigned);
 }
 
+#ifdef PBD_NO_DEEP
+constexpr bool kDeepPipeline = false;
+#else
+constexpr bool kDeepPipeline = true;
+#endif
 constexpr unsigned type_bit(int t) { return 1u << t; }
 constexpr unsigned kMaskClothXPBD = type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_ISOBENDING_XPBD);
 constexpr unsigned kMaskLight = type_bit(PBD_DISTANCE) | type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_DIHEDRAL) | type_bit(PBD_ISOBENDING) |
@@ -84,6 +90,7 @@ struct ResidentArgs {
     unsigned xThreads;            // the last xThreads threads of every CTA run the X items (and nothing else); 0 when there is one cluster
     unsigned clusterSize;         // CTAs per cluster (1: the colour barrier is a plain __syncthreads)
     int l2Prefetch;               // prefetch the next colour's operand runs into L2 (scenes whose constraint stream exceeds L2)
+    int relaxedPoll;              // X warps poll the counter with relaxed loads + back-off and fence once (else: acquire loads)
     float h, invH, twoInvH, gx, gy, gz;
     int secondOrder;
     unsigned long long *xCounter; // monotone arrival counter of the X items (global memory)
@@ -103,6 +110,11 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsigned long long v) {
@@ -146,6 +158,26 @@ struct ClusterAcc {
     __device__ __forceinline__ void st(Handle h, const float4 &v) const {
         if (v.w == 0.0f) return;
         if (h >> 63) dsmem_st((unsigned)h, v); else __stcg((float4 *)h, v);
+    }
+};
+
+// One CTA per cluster (SINGLE instantiations: big scenes, one independent CTA per SM; tiny scenes, one CTA): every shared-memory
+// particle is in this CTA's own tile -- plain LDS.128 / STS.128, no mapa, no cluster address space.
+struct LocalAcc {
+    typedef float4 *Handle;
+    float4 *tile;
+    __device__ __forceinline__ Handle handle(unsigned idx) const { return tile + (idx & kLocalMask); }
+    __device__ __forceinline__ float4 ld(Handle h) const { return *h; }
+    __device__ __forceinline__ void st(Handle h, const float4 &v) const { if (v.w != 0.0f) *h = v; }
+};
+struct LocalXAcc {
+    typedef unsigned long long Handle;  // bit 63: offset into the tile in the low word, else a global pointer
+    float4 *pos, *tile;
+    __device__ __forceinline__ Handle handle(unsigned idx) const { return (idx & kSmemFlag) ? ((1ull << 63) | (idx & kLocalMask)) : (unsigned long long)(pos + idx); }
+    __device__ __forceinline__ float4 ld(Handle h) const { return (h >> 63) ? tile[(unsigned)h] : __ldcg((const float4 *)h); }
+    __device__ __forceinline__ void st(Handle h, const float4 &v) const {
+        if (v.w == 0.0f) return;
+        if (h >> 63) tile[(unsigned)h] = v; else __stcg((float4 *)h, v);
     }
 };
 
@@ -202,30 +234,51 @@ template <int T> __device__ __forceinline__ constexpr bool is_xpbd() { return T 
 template <int T> __device__ __forceinline__ constexpr bool is_pipelined() {
     return T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD || T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD || T == PBD_VOLUME || T == PBD_VOLUME_XPBD || T == PBD_FEMTRIANGLE || T == PBD_DIHEDRAL;
 }
+// ... and the ones light enough to keep TWO items ahead in flight (an L2 hit is ~300 cycles, one cloth projection ~60 issue slots)
+template <int T> __device__ __forceinline__ constexpr bool is_pipelined2() { return T == PBD_DISTANCE_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_DISTANCE; }
 
 template <unsigned MASK>
-__device__ __forceinline__ void prefetch_first(const ResidentArgs &A, const RunEntry &r, unsigned bi, bool iterZero, unsigned tid, Prefetched &pre) {
+__device__ __forceinline__ void prefetch_first(const ResidentArgs &A, const RunEntry &r, unsigned bi, bool iterZero, unsigned tid, bool xRun, Prefetched &pre) {
     pre.bucket = 0xffffffffu;
-    if (tid >= r.nR) return;
+    const unsigned first = xRun ? r.firstX : r.firstR, n = xRun ? r.nX : r.nR;
+    if (tid >= n) return;
     PBD_FOR_TYPE(MASK, r.type,
-        pre.s = load_streamed<T>(A.types[T], r.firstR + tid);
-        if (is_xpbd<T>() && !iterZero) pre.lam = __ldcg(A.types[T].lambda + r.firstR + tid);
+        pre.s = load_streamed<T>(A.types[T], first + tid);
+        if (is_xpbd<T>() && !iterZero) pre.lam = __ldcg(A.types[T].lambda + first + tid);
         pre.bucket = bi;)
 }
 
 // items [first, first + n) of a type's arrays: item tid, tid + stride, ... on this thread; with usePre the first one is in `pre`.
 // Software pipelined: the streamed operands (and multiplier) of the next item are in flight while the current one is projected.
-template <unsigned MASK, class Acc>
+template <unsigned MASK, bool DEEP, class Acc>
 __device__ __forceinline__ void run_items(const ResidentArgs &A, const Acc &acc, int type, unsigned first, unsigned n, bool iterZero, unsigned tid, unsigned stride,
                                           bool usePre, const Prefetched &pre) {
     PBD_FOR_TYPE(MASK, type,
         const TypeArrays &ta = A.types[T];
         unsigned i = tid;
+        if (DEEP && is_pipelined2<T>()) {
+            if (i < n) {
+                auto fetch = [&](unsigned k, Streamed &sx, float &lx) { sx = load_streamed<T>(ta, first + k); if (is_xpbd<T>() && !iterZero) lx = __ldcg(ta.lambda + first + k); };
+                Streamed s0, s1, s2; float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f;
+                if (usePre) { s0 = pre.s; l0 = pre.lam; } else fetch(i, s0, l0);
+                bool h1 = i + stride < n;
+                if (h1) fetch(i + stride, s1, l1);
+                _Pragma("unroll 1")
+                for (;;) {
+                    const unsigned j2 = i + 2u * stride;
+                    const bool h2 = j2 < n;
+                    if (h2) fetch(j2, s2, l2);
+                    project_streamed_acc<T, Acc, 0>(acc, ta, first + i, s0, A.h, iterZero, true, l0);
+                    if (!h1) break;
+                    s0 = s1; l0 = l1; s1 = s2; l1 = l2; h1 = h2; i += stride;
+                }
+            }
+        } else
         if (i < n) {
             Streamed cur; float lam = 0.0f;
             if (usePre) { cur = pre.s; lam = pre.lam; }
             else { cur = load_streamed<T>(ta, first + i); if (is_xpbd<T>() && !iterZero) lam = __ldcg(ta.lambda + first + i); }
-#pragma unroll 1
+            _Pragma("unroll 1")
             for (;;) {
                 const unsigned j = i + stride;
                 const bool more = j < n;
@@ -267,8 +320,17 @@ __device__ __forceinline__ void velocity_particle(const ResidentArgs &A, unsigne
 }
 
 // the warp's lane 0 spins until every X arrival of the earlier phases is visible, then the warp proceeds
-__device__ __forceinline__ void x_wait(const unsigned long long *counter, unsigned long long target) {
-    if ((threadIdx.x & 31u) == 0) while (ld_acquire_u64(counter) < target) { }
+// (relaxed polls with a short back-off: an acquire load per poll would invalidate the SM's L1 every time and the spinning warp
+// would take issue slots from the working ones; one acquire fence after the exit orders the X loads behind the observed arrivals)
+__device__ __forceinline__ void x_wait(const unsigned long long *counter, unsigned long long target, int relaxedPoll) {
+    if ((threadIdx.x & 31u) == 0) {
+        if (relaxedPoll) {
+            while (ld_relaxed_u64(counter) < target) __nanosleep(20);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        } else {
+            while (ld_acquire_u64(counter) < target) { }
+        }
+    }
     __syncwarp();
 }
 // after the warp's X items: publish their stores and count the warp in
@@ -281,7 +343,7 @@ __device__ __forceinline__ void x_arrive(unsigned long long *counter) {
 __device__ __forceinline__ void colour_arrive(bool single) { if (!single) cluster_arrive(); }
 __device__ __forceinline__ void colour_wait(bool single) { if (single) __syncthreads(); else cluster_wait(); }
 
-template <unsigned MASK, int THREADS>
+template <unsigned MASK, int THREADS, bool SINGLE>
 __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_constant__ ResidentArgs A) {
     extern __shared__ float4 tile[];
     RunEntry *runs = reinterpret_cast<RunEntry *>(tile + A.tileCap);
@@ -295,9 +357,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
     const unsigned XT = A.xThreads, RT = THREADS - XT;
     const bool isX = threadIdx.x >= RT;
     const unsigned xtid = threadIdx.x - RT, xwarp = xtid >> 5;
-    const bool single = (A.clusterSize == 1u);
-    const ClusterAcc accX{A.pos, smem_u32(tile)};
-    const SmemAcc accR{smem_u32(tile)};
+    constexpr bool single = SINGLE;  // one CTA per cluster: plain shared-memory accesses, __syncthreads between colours
+    typedef typename std::conditional<SINGLE, LocalXAcc, ClusterAcc>::type XAcc;
+    typedef typename std::conditional<SINGLE, LocalAcc, SmemAcc>::type RAcc;
+    XAcc accX; RAcc accR;
+    if constexpr (SINGLE) { accX.pos = A.pos; accX.tile = tile; accR.tile = tile; }
+    else { accX.pos = A.pos; accX.tileBase = smem_u32(tile); accR.tileBase = smem_u32(tile); }
     unsigned long long xTarget = A.xBase;  // counter value once every arrival of the phases before the current one is in
     unsigned phase = 0;
     auto stamp = [&](unsigned k) {
@@ -346,7 +411,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
         }
         xTarget += sArrive[0];
         colour_arrive(single);
-        if (!isX && A.nColours) prefetch_first<MASK>(A, runs[sColour[0]], sColour[0], true, threadIdx.x, pre);
+        if (A.nColours) prefetch_first<MASK>(A, runs[sColour[0]], sColour[0], true, isX ? xtid : threadIdx.x, isX, pre);
         stamp(2); colour_wait(single); stamp(3);
         phase++;
 
@@ -368,9 +433,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
                     bool mine = false;
                     for (unsigned bi = b0; bi < b1; bi++) mine = mine || (runs[bi].nX > xwarp * 32u);
                     if (mine) {
-                        x_wait(A.xCounter, xTarget);
+                        x_wait(A.xCounter, xTarget, A.relaxedPoll);
 #pragma unroll 1
-                        for (unsigned bi = b0; bi < b1; bi++) run_items<MASK>(A, accX, runs[bi].type, runs[bi].firstX, runs[bi].nX, iterZero, xtid, XT, false, pre);
+                        for (unsigned bi = b0; bi < b1; bi++) run_items<MASK, false>(A, accX, runs[bi].type, runs[bi].firstX, runs[bi].nX, iterZero, xtid, XT, pre.bucket == bi, pre);
                         x_arrive(A.xCounter);
                     }
                     stamp(1);
@@ -379,17 +444,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
 #pragma unroll 1
                     for (unsigned bi = b0; bi < b1; bi++) {
                         const unsigned rot = runs[bi].rotR;  // 0 for the first bucket of a colour (the one prefetch_first serves)
-                        run_items<MASK>(A, accR, runs[bi].type, runs[bi].firstR, runs[bi].nR, iterZero, threadIdx.x >= rot ? threadIdx.x - rot : threadIdx.x + RT - rot, RT,
-                                        pre.bucket == bi, pre);
+                        run_items<MASK, kDeepPipeline && SINGLE && MASK == kMaskClothXPBD>(A, accR, runs[bi].type, runs[bi].firstR, runs[bi].nR, iterZero,
+                                                                           threadIdx.x >= rot ? threadIdx.x - rot : threadIdx.x + RT - rot, RT, pre.bucket == bi, pre);
                     }
                 }
                 xTarget += sArrive[1 + c];
                 colour_arrive(single);
-                if (!isX) {  // this thread's first item of the next colour streams in while the cluster synchronises
+                {   // this thread's first item of the next colour streams in while the CTAs synchronise
                     const bool lastColour = (c + 1 == A.nColours);
                     if (!lastColour || it + 1 < A.maxIter) {
                         const unsigned nb = sColour[lastColour ? 0u : c + 1u];
-                        prefetch_first<MASK>(A, runs[nb], nb, false, threadIdx.x, pre);
+                        prefetch_first<MASK>(A, runs[nb], nb, false, isX ? xtid : threadIdx.x, isX, pre);
                     } else pre.bucket = 0xffffffffu;
                 }
                 stamp(2); colour_wait(single); stamp(3);
@@ -399,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
 
         // ---- epilogue: velocity update (own particles only; the global-homed ones need the last colour's X items of every cluster)
         if (isX) {
-            if (xwarp * 32u < nGl) x_wait(A.xCounter, xTarget);
+            if (xwarp * 32u < nGl) x_wait(A.xCounter, xTarget, A.relaxedPoll);
             for (unsigned i = xtid; i < nGl; i += XT) velocity_particle(A, t0 + nSm + i, __ldcg(A.pos + t0 + nSm + i));
         } else {
             for (unsigned i = threadIdx.x; i < nSm; i += RT) velocity_particle(A, t0 + i, tile[tile_swizzle(i)]);

@@ -207,3 +207,67 @@ def test_facade_rigid_body_matches_the_reference_init(cpu_libs):
         w, V = np.linalg.eigh(J); Rf = _quat_to_matrix(rb.getRotation().astype(np.float64)); Jw_fac = Rf @ np.diag(w) @ Rf.T
         assert np.allclose(Jw_fac, Jw_ref, rtol=1e-5, atol=1e-6), (Jw_fac, Jw_ref)
         assert np.allclose(Jw_ref, R0 @ J @ R0.T, rtol=1e-9, atol=1e-12)
+
+
+def test_compiled_pybind_module_builds_the_same_model():
+    """The compiled pybind11 module (csrc/pybind/pypbd_module.cpp, north_star "pyPBD via pybind") exposes the pyPBD names over the
+    same C++ host mirror: scene construction, constraint counts and colour groups equal the ctypes facade's (no GPU needed until
+    getTimeStep())."""
+    import importlib, math, os, sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "positionbaseddynamics_b200")
+    sys.path.insert(0, pkg)
+    try:
+        native = importlib.import_module("pypbd_b200")
+    finally:
+        sys.path.remove(pkg)
+    from positionbaseddynamics_b200 import pypbd as facade
+    R = np.array([[1, 0, 0], [0, math.cos(math.pi / 2), -math.sin(math.pi / 2)], [0, math.sin(math.pi / 2), math.cos(math.pi / 2)]])
+    sim = native.Simulation.getCurrent(); sim.initDefault(); m1 = sim.getModel()
+    m2 = facade.SimulationModel()
+    for m in (m1, m2):
+        tm = m.addRegularTriangleModel(30, 20, (0, 1, 0), R, (6.0, 4.0))
+        pd = m.getParticles(); pd.setMass(0, 0.0); pd.setMass(29, 0.0)
+        m.addClothConstraints(tm, 4, 1.0e5, 1.0, 1.0, 1.0, 0.3, 0.3, False, False)
+        m.addBendingConstraints(tm, 3, 100.0)
+        tt = m.addRegularTetModel(5, 4, 3, (0, 3, 0), np.eye(3), (2.0, 1.0, 1.0))
+        m.addSolidConstraints(tt, 2, 1.0e6, 0.3, 1.0, False, False)
+    assert m1.numConstraints() == m2.numConstraints() > 0
+    g1, g2 = m1.getConstraintGroups(), m2.getConstraintGroups()
+    assert len(g1) == len(g2) and all((np.asarray(a) == np.asarray(b)).all() for a, b in zip(g1, g2))
+    assert (m1.getParticles().getVertices() == m2.getParticles().getVertices()).all()
+    assert m1.getParticles().getInvMass(0) == 0.0 and m1.getParticles().getMass(5) == 1.0
+    assert native.TimeStepController.NUM_SUB_STEPS == facade.TimeStepController.NUM_SUB_STEPS
+    assert m1.getTriangleModels()[0].getParticleMesh().numFaces() == 2 * 29 * 19
+    c1, c2 = m1.getConstraints(), m2.getConstraints()
+    assert all((c1[i]["bodies"] == c2[i]["bodies"]).all() for i in range(0, len(c1), 97))
+
+
+@pytest.mark.gpu
+def test_compiled_pybind_module_steps_like_the_facade():
+    """The reference's cloth example flow (pyPBD/examples/cloth_model.py:18-124) through the compiled module: same bits as the ctypes
+    facade, and the getVertices() view follows the device state."""
+    import importlib, os, sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "positionbaseddynamics_b200")
+    sys.path.insert(0, pkg)
+    try:
+        native = importlib.import_module("pypbd_b200")
+    finally:
+        sys.path.remove(pkg)
+    pbd, sim2, model2 = _build()
+    a = math.pi / 2
+    R = [[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]]
+    sim = native.Simulation.getCurrent(); sim.initDefault(); model = sim.getModel()
+    tm = model.addRegularTriangleModel(20, 20, [0, 1, 0], R, [10, 10])
+    pd = model.getParticles(); pd.setMass(0, 0.0); pd.setMass(19, 0.0)
+    model.addClothConstraints(tm, 4, 1.0e5, 1.0, 1.0, 1.0, 0.3, 0.3, False, False)
+    model.addBendingConstraints(tm, 3, 100.0)
+    for s, mdl, mod in ((sim, model, native), (sim2, model2, pbd)):
+        ts = s.getTimeStep()
+        ts.setValueUInt(mod.TimeStepController.NUM_SUB_STEPS, 1); ts.setValueUInt(mod.TimeStepController.MAX_ITERATIONS, 5)
+        mod.TimeManager.getCurrent().setTimeStepSize(0.005)
+        for _ in range(4):
+            ts.step(mdl)
+    x1 = np.array(model.getParticles().getVertices()); x2 = np.array(model2.getParticles().getVertices())
+    assert np.isfinite(x1).all() and (x1 == x2).all()
+    assert abs(native.TimeManager.getCurrent().getTime() - 0.02) < 1e-6
+    assert (x1[0] == [0.0, 1.0, 0.0]).all() or np.allclose(x1[0], model.getParticles().getPosition0(0))  # pinned corner

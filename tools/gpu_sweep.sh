@@ -7,7 +7,7 @@ out=gpurun_out/${tag}_sweep.jsonl
 : > "$out"
 for spec in "$@"; do
   IFS='|' read -r name envs args <<< "$spec"
-  line=$(env $envs timeout 300 python bench.py --no-cpu-baseline $args 2> "gpurun_out/${tag}_${name}.err" | tail -1)
+  line=$(env $envs timeout 300 python bench.py --no-cpu-baseline --no-side $args 2> "gpurun_out/${tag}_${name}.err" | tail -1)
   python - "$name" "$line" >> "$out" <<'PY'
 import sys, json
 name, line = sys.argv[1], sys.argv[2]
