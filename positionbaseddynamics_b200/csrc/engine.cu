@@ -635,7 +635,16 @@ template <class F> static int with_resident_kernel(const pbd_engine *e, unsigned
         if (th == 768) return single ? f(k_step_resident<kMaskClothXPBD, 768, true>) : f(k_step_resident<kMaskClothXPBD, 768, false>);
         return single ? f(k_step_resident<kMaskClothXPBD, 640, true>) : f(k_step_resident<kMaskClothXPBD, 640, false>);
     }
+    if (e->resMask == kMaskCloth) return single ? f(k_step_resident<kMaskCloth, 512, true>) : f(k_step_resident<kMaskCloth, 512, false>);
     if (e->resMask == kMaskLight) return single ? f(k_step_resident<kMaskLight, 512, true>) : f(k_step_resident<kMaskLight, 512, false>);
+    if (e->resMask == kMaskFem) {
+        if (th == 256) return single ? f(k_step_resident<kMaskFem, 256, true>) : f(k_step_resident<kMaskFem, 256, false>);
+        return single ? f(k_step_resident<kMaskFem, 512, true>) : f(k_step_resident<kMaskFem, 512, false>);
+    }
+    if (e->resMask == kMaskSolid) {
+        if (th == 256) return single ? f(k_step_resident<kMaskSolid, 256, true>) : f(k_step_resident<kMaskSolid, 256, false>);
+        return single ? f(k_step_resident<kMaskSolid, 512, true>) : f(k_step_resident<kMaskSolid, 512, false>);
+    }
     if (th == 512) return single ? f(k_step_resident<kMaskAll, 512, true>) : f(k_step_resident<kMaskAll, 512, false>);
     return single ? f(k_step_resident<kMaskAll, 256, true>) : f(k_step_resident<kMaskAll, 256, false>);
 }
@@ -665,12 +674,14 @@ static int resident_max_clusters(const pbd_engine *e, unsigned C, size_t smem, i
 static int choose_resident_shape(pbd_engine *e) {
     unsigned present = 0, nTypes = 0;
     for (int t = 0; t < PBD_NUM_TYPES; t++) if (!e->host[t].ids.empty()) { present |= 1u << t; nTypes++; }
-    e->resMask = ((present & ~kMaskClothXPBD) == 0) ? kMaskClothXPBD : (((present & ~kMaskLight) == 0) ? kMaskLight : kMaskAll);
+    e->resMask = kMaskAll;
+    for (unsigned m : {kMaskClothXPBD, kMaskCloth, kMaskFem, kMaskLight, kMaskSolid})  // the leanest instantiation that covers the model
+        if ((present & ~m) == 0) { e->resMask = m; break; }
     // the block sizes the instantiations compile for without spilling (cloth 96 registers, light 128, everything 236)
-    e->resThreads = (e->resMask == kMaskClothXPBD) ? 640u : ((e->resMask == kMaskLight) ? 512u : 256u);
+    e->resThreads = (e->resMask == kMaskClothXPBD) ? 640u : ((e->resMask == kMaskAll) ? 256u : 512u);
     if (const char *g = getenv("PBD_B200_RTHREADS")) { const int k = atoi(g); if (k == 256 || k == 512 || k == 640 || k == 768) e->resThreads = (unsigned)k; }
     if (e->resMask == kMaskAll && e->resThreads > 512u) e->resThreads = 512u;
-    if (e->resMask == kMaskLight) e->resThreads = 512u;
+    if (e->resMask == kMaskLight || e->resMask == kMaskCloth) e->resThreads = 512u;
     if (e->resMask == kMaskClothXPBD && e->resThreads == 256u) e->resThreads = 512u;
     const unsigned nGroups = (unsigned)std::max<size_t>(e->groupOff.size(), 2) - 1;
     const unsigned perPhase = e->numConstraints / std::max(1u, nGroups);
@@ -1067,20 +1078,18 @@ static int flatten(pbd_engine *e) {
         e->resColours = (unsigned)colourStart.size();
         colourStart.push_back((unsigned)e->buckets.size());
         if (tileOff.size() != e->buckets.size() * (2 * (size_t)T + 1)) return fail("flatten: internal error (tile runs)");
-        // arrivals on the X counter, in warps: integration phase (warps that own global-homed particles), then every colour
+        // arrivals on the X counter: one per CTA that owns X work in the phase -- integration phase (global-homed particles), then every colour
         std::vector<unsigned> xArrive(1 + e->resColours, 0u);
-        for (unsigned t = 0; t < T; t++) {
-            const unsigned nGl = pl.tileStart[t + 1] - pl.tileStart[t] - pl.tileSmem[t];
-            xArrive[0] += std::min(warps, (nGl + 31u) / 32u);
-        }
+        (void)warps;
+        for (unsigned t = 0; t < T; t++) xArrive[0] += (pl.tileStart[t + 1] - pl.tileStart[t] - pl.tileSmem[t]) ? 1u : 0u;
         for (unsigned c = 0; c < e->resColours; c++)
             for (unsigned t = 0; t < T; t++) {
-                unsigned mx = 0;
+                unsigned any = 0;
                 for (unsigned bi = colourStart[c]; bi < colourStart[c + 1]; bi++) {
                     const unsigned *off = &tileOff[(size_t)bi * (2 * T + 1) + 2 * t];
-                    mx = std::max(mx, off[1] - off[0]);
+                    any |= (off[1] - off[0]);
                 }
-                xArrive[1 + c] += std::min(warps, (mx + 31u) / 32u);
+                xArrive[1 + c] += any ? 1u : 0u;
             }
         unsigned long long perSweep = 0;
         for (unsigned c = 0; c < e->resColours; c++) perSweep += xArrive[1 + c];

@@ -58,8 +58,13 @@ constexpr bool kDeepPipeline = true;
 #endif
 constexpr unsigned type_bit(int t) { return 1u << t; }
 constexpr unsigned kMaskClothXPBD = type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_ISOBENDING_XPBD);
+constexpr unsigned kMaskCloth = kMaskClothXPBD | type_bit(PBD_DISTANCE) | type_bit(PBD_ISOBENDING);
 constexpr unsigned kMaskLight = type_bit(PBD_DISTANCE) | type_bit(PBD_DISTANCE_XPBD) | type_bit(PBD_DIHEDRAL) | type_bit(PBD_ISOBENDING) |
                                 type_bit(PBD_ISOBENDING_XPBD) | type_bit(PBD_VOLUME) | type_bit(PBD_VOLUME_XPBD) | type_bit(PBD_FEMTRIANGLE);
+// FEM solids (cfg3): tets with FEM / volume constraints; and cloth + FEM solids + the coupling joints (cfg4).  Lean instantiations
+// matter: the everything-kernel is 20k instructions and 226 registers, and every colour phase jumps through it.
+constexpr unsigned kMaskFem = type_bit(PBD_FEMTET) | type_bit(PBD_FEMTET_XPBD) | type_bit(PBD_VOLUME) | type_bit(PBD_VOLUME_XPBD);
+constexpr unsigned kMaskSolid = kMaskCloth | kMaskFem | type_bit(PBD_FEMTRIANGLE) | type_bit(PBD_BALLJOINT) | type_bit(PBD_RB_PARTICLE_BALLJOINT);
 constexpr unsigned kMaskAll = (1u << PBD_NUM_TYPES) - 1u;
 
 // dispatch a statement on the runtime type, restricted to the compiled-in mask (T is a constant inside the statement)
@@ -84,7 +89,7 @@ struct ResidentArgs {
     const unsigned *tileOff;      // [nBuckets][2 nTiles + 1], relative to the bucket's `first`: tile t = [2t] X items.. [2t+1] others.. [2t+2]
     const unsigned *tileStart;    // [nTiles + 1] device slots: tile t owns [tileStart[t], tileStart[t+1])
     const unsigned *tileSmem;     // [nTiles] leading slots of the tile that live in shared memory; the rest is global-homed
-    const unsigned *xArrive;      // [1 + nColours] counter arrivals (warps, summed over all CTAs) of the integration phase and of every colour
+    const unsigned *xArrive;      // [1 + nColours] counter arrivals (CTAs that own X work) of the integration phase and of every colour
     unsigned nBuckets, nColours, nTiles, subSteps, maxIter;
     unsigned tileCap;             // float4 slots reserved for the tile in every CTA's shared memory (>= the largest tileSmem)
     unsigned xThreads;            // the last xThreads threads of every CTA run the X items (and nothing else); 0 when there is one cluster
@@ -235,7 +240,7 @@ template <int T> __device__ __forceinline__ constexpr bool is_pipelined() {
     return T == PBD_DISTANCE || T == PBD_DISTANCE_XPBD || T == PBD_ISOBENDING || T == PBD_ISOBENDING_XPBD || T == PBD_VOLUME || T == PBD_VOLUME_XPBD || T == PBD_FEMTRIANGLE || T == PBD_DIHEDRAL;
 }
 // ... and the ones light enough to keep TWO items ahead in flight (an L2 hit is ~300 cycles, one cloth projection ~60 issue slots)
-template <int T> __device__ __forceinline__ constexpr bool is_pipelined2() { return T == PBD_DISTANCE_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_DISTANCE; }
+template <int T> __device__ __forceinline__ constexpr bool is_pipelined2() { return T == PBD_DISTANCE_XPBD || T == PBD_ISOBENDING_XPBD || T == PBD_DISTANCE || T == PBD_ISOBENDING; }
 
 template <unsigned MASK>
 __device__ __forceinline__ void prefetch_first(const ResidentArgs &A, const RunEntry &r, unsigned bi, bool iterZero, unsigned tid, bool xRun, Prefetched &pre) {
@@ -319,11 +324,14 @@ __device__ __forceinline__ void velocity_particle(const ResidentArgs &A, unsigne
     __stcs(A.vel + slot, v);
 }
 
-// the warp's lane 0 spins until every X arrival of the earlier phases is visible, then the warp proceeds
-// (relaxed polls with a short back-off: an acquire load per poll would invalidate the SM's L1 every time and the spinning warp
-// would take issue slots from the working ones; one acquire fence after the exit orders the X loads behind the observed arrivals)
-__device__ __forceinline__ void x_wait(const unsigned long long *counter, unsigned long long target, int relaxedPoll) {
-    if ((threadIdx.x & 31u) == 0) {
+// X warps of a CTA act as one party of the counter protocol (148 arrivals and 148 pollers per colour instead of one per warp: the
+// counter is ONE L2 address).  Named barrier 1 synchronises the CTA's XT threads (whole warps); its first thread talks to the counter.
+//   wait  : thread 0 spins until every arrival of the earlier phases is visible (ld.acquire.gpu), then releases its CTA's X warps;
+//   arrive: after the X warps' stores -- barrier (orders them before thread 0), then thread 0 publishes with red.release.gpu
+//           (the fence is cumulative over what the barrier ordered: the cooperative-groups grid.sync pattern).
+__device__ __forceinline__ void x_bar(unsigned xThreads) { asm volatile("bar.sync 1, %0;" :: "r"(xThreads) : "memory"); }
+__device__ __forceinline__ void x_wait(const unsigned long long *counter, unsigned long long target, unsigned xtid, unsigned xThreads, int relaxedPoll) {
+    if (xtid == 0) {
         if (relaxedPoll) {
             while (ld_relaxed_u64(counter) < target) __nanosleep(20);
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -331,12 +339,11 @@ __device__ __forceinline__ void x_wait(const unsigned long long *counter, unsign
             while (ld_acquire_u64(counter) < target) { }
         }
     }
-    __syncwarp();
+    x_bar(xThreads);
 }
-// after the warp's X items: publish their stores and count the warp in
-__device__ __forceinline__ void x_arrive(unsigned long long *counter) {
-    __syncwarp();
-    if ((threadIdx.x & 31u) == 0) red_release_add_u64(counter, 1ull);
+__device__ __forceinline__ void x_arrive(unsigned long long *counter, unsigned xtid, unsigned xThreads) {
+    x_bar(xThreads);
+    if (xtid == 0) red_release_add_u64(counter, 1ull);
 }
 
 // colour barrier of the cluster: arrive (publishes this thread's shared-memory stores), then wait; one CTA: a block barrier
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
     // global-homed particles and are the only ones that ever wait for another cluster
     const unsigned XT = A.xThreads, RT = THREADS - XT;
     const bool isX = threadIdx.x >= RT;
-    const unsigned xtid = threadIdx.x - RT, xwarp = xtid >> 5;
+    const unsigned xtid = threadIdx.x - RT;
     constexpr bool single = SINGLE;  // one CTA per cluster: plain shared-memory accesses, __syncthreads between colours
     typedef typename std::conditional<SINGLE, LocalXAcc, ClusterAcc>::type XAcc;
     typedef typename std::conditional<SINGLE, LocalAcc, SmemAcc>::type RAcc;
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
                 float4 x = __ldcg(A.pos + t0 + nSm + i);
                 if (integrate_particle(A, t0 + nSm + i, x)) __stcg(A.pos + t0 + nSm + i, x);
             }
-            if (xwarp * 32u < nGl) x_arrive(A.xCounter);
+            if (nGl) x_arrive(A.xCounter, xtid, XT);
             stamp(1);
         } else {
             for (unsigned i = threadIdx.x; i < nSm; i += RT) {
@@ -430,13 +437,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
                 }
                 if (isX) {
                     // X items of every bucket of the colour: they touch global-homed particles and are ordered across clusters by the counter
-                    bool mine = false;
-                    for (unsigned bi = b0; bi < b1; bi++) mine = mine || (runs[bi].nX > xwarp * 32u);
+                    bool mine = false;  // CTA-uniform: does this CTA own an X item of this colour?
+                    for (unsigned bi = b0; bi < b1; bi++) mine = mine || (runs[bi].nX != 0u);
                     if (mine) {
-                        x_wait(A.xCounter, xTarget, A.relaxedPoll);
+                        x_wait(A.xCounter, xTarget, xtid, XT, A.relaxedPoll);
 #pragma unroll 1
                         for (unsigned bi = b0; bi < b1; bi++) run_items<MASK, false>(A, accX, runs[bi].type, runs[bi].firstX, runs[bi].nX, iterZero, xtid, XT, pre.bucket == bi, pre);
-                        x_arrive(A.xCounter);
+                        x_arrive(A.xCounter, xtid, XT);
                     }
                     stamp(1);
                 } else {
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
 
         // ---- epilogue: velocity update (own particles only; the global-homed ones need the last colour's X items of every cluster)
         if (isX) {
-            if (xwarp * 32u < nGl) x_wait(A.xCounter, xTarget, A.relaxedPoll);
+            if (nGl) x_wait(A.xCounter, xTarget, xtid, XT, A.relaxedPoll);
             for (unsigned i = xtid; i < nGl; i += XT) velocity_particle(A, t0 + nSm + i, __ldcg(A.pos + t0 + nSm + i));
         } else {
             for (unsigned i = threadIdx.x; i < nSm; i += RT) velocity_particle(A, t0 + i, tile[tile_swizzle(i)]);

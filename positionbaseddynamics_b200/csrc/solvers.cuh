@@ -834,7 +834,8 @@ __device__ __forceinline__ void rb_correct(float4 &X, float4 &Q, const M3 &J, V3
 }
 
 // BallJoint between rigid bodies (X0,Q0) and (X1,Q1); l0/l1 = connectors in body space
-__device__ __forceinline__ void project_balljoint(float4 &X0, float4 &Q0, V3 Iinv0, float4 &X1, float4 &Q1, V3 Iinv1, V3 l0, V3 l1) {
+// (noinline: a handful of joints per scene; as a real call their registers do not count against the kernels they are compiled into)
+__device__ __noinline__ void project_balljoint(float4 &X0, float4 &Q0, V3 Iinv0, float4 &X1, float4 &Q1, V3 Iinv1, V3 l0, V3 l1) {
     const M3 R0 = qmatrix(Q0), R1 = qmatrix(Q1);
     const V3 x0 = xyz(X0), x1 = xyz(X1);
     const V3 c0 = mvec(R0, l0) + x0, c1 = mvec(R1, l1) + x1;  // update_BallJoint
@@ -852,7 +853,7 @@ __device__ __forceinline__ void project_balljoint(float4 &X0, float4 &Q0, V3 Iin
 }
 
 // RigidBodyParticleBallJoint: rigid body (X0,Q0) and particle p (xyz, invMass)
-__device__ __forceinline__ void project_rb_particle_balljoint(float4 &X0, float4 &Q0, V3 Iinv0, float4 &p, V3 l0) {
+__device__ __noinline__ void project_rb_particle_balljoint(float4 &X0, float4 &Q0, V3 Iinv0, float4 &p, V3 l0) {
     const M3 R0 = qmatrix(Q0);
     const V3 x0 = xyz(X0);
     const V3 c0 = mvec(R0, l0) + x0;
