@@ -167,6 +167,20 @@ class CpuPbd:
         self.lib.ref_gpu_error.restype = C.c_char_p
         return self.lib.ref_gpu_error().decode()
 
+    def attach_collision_object(self):
+        """refgpu only: TimeStep::setCollisionDetection with one collision object, as the reference's collision demos do."""
+        assert self.kind == "refgpu"
+        return int(self.lib.ref_attach_collision_object())
+
+    def set_cloth_stiffness(self, k):
+        """SimulationModel::setClothStiffness (ref / refgpu): rewrites m_stiffness of every cloth constraint."""
+        assert self.kind in ("ref", "refgpu")
+        self.lib.ref_set_cloth_stiffness(_D(k))
+
+    def download_history(self):
+        assert self.kind == "refgpu"
+        return int(self.lib.ref_download_history())
+
     def set_params(self, dt=0.005, sub_steps=5, max_iter=1, vel_method=0, gravity=(0, -9.81, 0)):
         self.f("set_params")(_D(dt), sub_steps, max_iter, vel_method, _dp(_f64(gravity)))
 

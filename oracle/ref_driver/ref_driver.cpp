@@ -362,6 +362,10 @@ double ref_step(int n) {
 }
 double ref_time() { return TimeManager::getCurrent()->getTime(); }
 
+// model-wide parameter setter (SimulationModel.cpp:1351-1485): rewrites the member of every constraint of the type, does not clear
+// m_groupsInitialized -- what a GPU time step has to notice on its own
+void ref_set_cloth_stiffness(double k) { g_model->setClothStiffness((Real)k); }
+
 #ifdef PBD_WITH_GPU_ADAPTER
 // Install the GPU time step the way a user of the reference would (Simulation.h:48-49), carrying over the solver parameters.
 // mode: PBD_MODE_* of include/pbd_b200.h.  Returns 0 on success.
@@ -384,6 +388,18 @@ int ref_use_gpu_timestep(int device, int mode) {
     return 0;
 }
 const char *ref_gpu_error() { if (g_gpuTs && !g_gpuTs->lastError().empty()) g_gpuErr = g_gpuTs->lastError(); return g_gpuErr.c_str(); }
+// Attach a collision detection with one collision object to the installed time step, the way the reference's demos do
+// (TimeStep::setCollisionDetection, CollisionDetection::addCollisionObject): the GPU time step must then refuse to step.
+namespace { struct NullCollisionDetection : public CollisionDetection { void collisionDetection(SimulationModel &) override {} }; }
+int ref_attach_collision_object() {
+    TimeStep *ts = Simulation::getCurrent()->getTimeStep();
+    CollisionDetection *cd = new NullCollisionDetection();
+    cd->addCollisionObject(0, CollisionDetection::CollisionObject::TriangleModelCollisionObjectType);
+    ts->setCollisionDetection(*g_model, cd);
+    return (int)cd->getCollisionObjects().size();
+}
+void ref_invalidate_gpu() { if (g_gpuTs) g_gpuTs->invalidate(); }
+int ref_download_history() { return (g_gpuTs && g_gpuTs->downloadHistory(*g_model)) ? 0 : 1; }
 #endif
 
 // ---------------------------------------------------------------------------------------------

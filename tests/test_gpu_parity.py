@@ -500,3 +500,56 @@ def test_jacobi_comparison_mode():
     v_jac = violation(_capi.MODE_JACOBI)
     print("mean |d - rest|: no projections %.3e, Gauss-Seidel %.3e, Jacobi %.3e" % (v_free, v_gs, v_jac))
     assert v_gs < 0.2 * v_free and v_jac < 0.6 * v_free
+
+
+def test_adapter_refuses_models_with_collision_objects(cpu_libs):
+    """TimeStepController.cpp:189-196 (collision detection + velocityConstraintProjection over the contacts) is not on the GPU path:
+    GpuTimeStepController must refuse such a model with lastError() instead of silently simulating it without contacts."""
+    from oracle import pyoracle
+    if not pyoracle.available("refgpu", "f32"):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_gpu_f32.so not present on this box")
+    gpu = cpu_libs.CpuPbd("refgpu", "f32")
+    scenes.cloth(gpu, 12, 12, 1, 2, dist_k=1.0, bend_k=0.01, max_iter=3)
+    gpu.use_gpu_timestep(0, 0)
+    gpu.step(1)
+    assert gpu.gpu_error() == ""
+    x1 = gpu.get("x").copy()
+    assert gpu.attach_collision_object() == 1
+    gpu.step(1)
+    assert "collision" in gpu.gpu_error() and "CPU TimeStepController" in gpu.gpu_error()
+    assert (gpu.get("x") == x1).all()  # nothing was stepped
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_adapter_notices_parameter_setters_and_mass_edits(precision, cpu_libs):
+    """ADVICE round 1: SimulationModel::setClothStiffness and ParticleData::setMass after the first step do not clear
+    m_groupsInitialized; the reference reads the values on every solve, so the adapter has to notice them itself (sentinel
+    signature of the constraint parameters, per-step mass comparison).  Twin on the reference's own TimeStepController (fp64)."""
+    from oracle import pyoracle
+    if not (pyoracle.available("refgpu", precision) and have_ref("f64")):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_gpu_%s.so not present on this box" % precision)
+    gpu = cpu_libs.CpuPbd("refgpu", precision); cpu = cpu_libs.CpuPbd("ref", "f64")
+    for m in (gpu, cpu):
+        scenes.cloth(m, 20, 20, 1, 2, dist_k=1.0, bend_k=0.01, max_iter=4)
+    gpu.use_gpu_timestep(0, 0)
+    x_start = perturb([gpu, cpu], 0.02)
+    gpu.step(2); cpu.step(2)
+    for m in (gpu, cpu):
+        m.set_cloth_stiffness(0.25)   # every DistanceConstraint::m_stiffness
+        m.set_mass(210, 0.0)          # pin a particle in the middle of the sheet
+    x_mid = cpu.get("x").copy()
+    gpu.step(3); cpu.step(3)
+    assert gpu.gpu_error() == ""
+    xg, xc = gpu.get("x"), cpu.get("x")
+    e = rel_position_error(xg, xc)
+    print("adapter after setClothStiffness + setMass, Real=%s: rel pos %.2e" % (precision, e))
+    assert e <= TOL
+    assert np.abs(xc[210] - x_mid[210]).max() == 0.0 and np.abs(xg[210] - x_mid[210]).max() <= 1e-6  # the pinned particle stopped
+    # the edits matter: a twin that ignored them is off by far more than the tolerance
+    ign = cpu_libs.CpuPbd("ref", "f64")
+    scenes.cloth(ign, 20, 20, 1, 2, dist_k=1.0, bend_k=0.01, max_iter=4)
+    ign.set("x", x_start); ign.step(5)
+    assert rel_position_error(ign.get("x"), xc) > 10 * TOL
+    # history comes back on demand (second-order velocity update of another TimeStep would read it)
+    assert gpu.download_history() == 0
+    assert rel_position_error(gpu.get("oldX"), cpu.get("oldX")) <= TOL
