@@ -76,6 +76,7 @@ public:
                       "(TimeStepController.cpp:189-196, 298-357) runs on the CPU TimeStepController only";
             return;
         }
+        m_error.clear();  // lastError() describes the current step
         ParticleData &pd = model.getParticles();
         SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
         const unsigned n = pd.size();

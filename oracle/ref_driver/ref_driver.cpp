@@ -385,9 +385,10 @@ int ref_use_gpu_timestep(int device, int mode) {
     delete old;
     sim->setTimeStep(ts);
     g_gpuTs = ts;
+    g_gpuErr.clear();
     return 0;
 }
-const char *ref_gpu_error() { if (g_gpuTs && !g_gpuTs->lastError().empty()) g_gpuErr = g_gpuTs->lastError(); return g_gpuErr.c_str(); }
+const char *ref_gpu_error() { if (g_gpuTs) g_gpuErr = g_gpuTs->lastError(); return g_gpuErr.c_str(); }
 // Attach a collision detection with one collision object to the installed time step, the way the reference's demos do
 // (TimeStep::setCollisionDetection, CollisionDetection::addCollisionObject): the GPU time step must then refuse to step.
 namespace { struct NullCollisionDetection : public CollisionDetection { void collisionDetection(SimulationModel &) override {} }; }

@@ -798,7 +798,12 @@ static int flatten(pbd_engine *e) {
     CKE(use(e));
     if (!e->groupsSet) {
         if (e->numConstraints == 0) { e->groupOff.assign(1, 0u); e->groupIds.clear(); e->groupsSet = true; }
-        else CKE(pbd_color_first_fit(e));
+        else {
+            // the reference-order-preserving first fit on the GPU (colouring.cuh); the host version is the fallback and the
+            // PBD_B200_HOST_COLOURING=1 choice
+            static const bool hostColouring = [] { const char *g = getenv("PBD_B200_HOST_COLOURING"); return g && atoi(g) != 0; }();
+            if (hostColouring || pbd_color_first_fit_device(e, nullptr, nullptr)) CKE(pbd_color_first_fit(e));
+        }
     }
     drop_graph(e);
     // the particle / rigid-body counts may have shrunk since the constraints were added (pbd_set_particles, pbd_set_rigid_bodies)

@@ -1,5 +1,9 @@
 // positionbaseddynamics_b200/csrc/host/pbd_model.cpp -- see pbd_model.h.
 #include "pbd_model.h"
+#include <algorithm>
+#include <cstdlib>
+#include <omp.h>
+#include <parallel/algorithm>
 #include <cmath>
 #include <cstring>
 #include <unordered_map>
@@ -65,22 +69,57 @@ struct FlatEdgeMap {
 };
 }  // namespace
 
+// OpenMP team of the host-side model build (capped: GPU hosts expose far more hardware threads than pay off here)
+static int model_threads() {
+    static const int n = [] { const char *g = getenv("PBD_B200_HOST_THREADS"); const int want = g ? atoi(g) : 8; return std::max(1, std::min(want, omp_get_max_threads())); }();
+    return n;
+}
+
+// Edge discovery in the reference's order (IndexedFaceMesh.cpp:118-226: faces in order, their three edges in order, an edge is
+// created by the first half-edge that mentions it), computed without a sequential hash walk: sort the half-edges by (vertex
+// pair, position), the first of every run creates the edge, the edge's index is the rank of that creating position.
 void IndexedFaceMesh::buildNeighbors() {
     m_edges.clear();
-    FlatEdgeMap lookup((size_t)numFaces() * 3 / 2 + 16);
-    m_edges.reserve((size_t)numFaces() * 3 / 2 + 16);
-    for (unsigned int f = 0; f < numFaces(); f++) {
-        const unsigned int *v = &m_indices[3 * (size_t)f];
-        for (int j = 0; j < 3; j++) {
-            const unsigned int a = v[j], b = v[(j + 1) % 3];
-            bool inserted;
-            const unsigned int id = lookup.findOrInsert(edgeKey(a, b), (unsigned int)m_edges.size(), inserted);
-            if (inserted) {
-                Edge e; e.m_vert = {a, b}; e.m_face = {f, 0xffffffffu};
-                m_edges.push_back(e);
-            } else {
-                m_edges[id].m_face[1] = f;
+    const size_t nH = (size_t)numFaces() * 3;
+    if (nH < 4096) {  // tiny meshes: the sequential walk
+        FlatEdgeMap lookup((size_t)numFaces() * 3 / 2 + 16);
+        m_edges.reserve((size_t)numFaces() * 3 / 2 + 16);
+        for (unsigned int f = 0; f < numFaces(); f++) {
+            const unsigned int *v = &m_indices[3 * (size_t)f];
+            for (int j = 0; j < 3; j++) {
+                const unsigned int a = v[j], b = v[(j + 1) % 3];
+                bool inserted;
+                const unsigned int id = lookup.findOrInsert(edgeKey(a, b), (unsigned int)m_edges.size(), inserted);
+                if (inserted) { Edge e; e.m_vert = {a, b}; e.m_face = {f, 0xffffffffu}; m_edges.push_back(e); }
+                else m_edges[id].m_face[1] = f;
             }
+        }
+    } else {
+        struct Half { uint64_t key; unsigned int pos; };
+        std::vector<Half> h(nH);
+        const int threads = model_threads();
+        #pragma omp parallel for schedule(static) num_threads(threads)
+        for (long long p = 0; p < (long long)nH; p++) {
+            const unsigned int f = (unsigned int)(p / 3), j = (unsigned int)(p % 3);
+            h[p] = Half{edgeKey(m_indices[3 * (size_t)f + j], m_indices[3 * (size_t)f + (j + 1) % 3]), (unsigned int)p};
+        }
+        __gnu_parallel::sort(h.begin(), h.end(), [](const Half &a, const Half &b) { return a.key < b.key || (a.key == b.key && a.pos < b.pos); },
+                             __gnu_parallel::default_parallel_tag(threads));
+        // creating position of every run -> rank among the creating positions = edge index
+        std::vector<unsigned int> creates(nH + 1, 0u);
+        #pragma omp parallel for schedule(static) num_threads(threads)
+        for (long long k = 0; k < (long long)nH; k++) if (k == 0 || h[k].key != h[k - 1].key) creates[h[k].pos + 1] = 1u;
+        for (size_t p = 0; p < nH; p++) creates[p + 1] += creates[p];
+        m_edges.resize(creates[nH]);
+        #pragma omp parallel for schedule(static) num_threads(threads)
+        for (long long k = 0; k < (long long)nH; k++) {
+            if (k != 0 && h[k].key == h[k - 1].key) continue;
+            size_t last = (size_t)k;
+            while (last + 1 < nH && h[last + 1].key == h[k].key) last++;  // the LAST later half-edge wins m_face[1], as in the sequential walk
+            const unsigned int p = h[k].pos, f = p / 3, j = p % 3;
+            Edge e; e.m_vert = {m_indices[3 * (size_t)f + j], m_indices[3 * (size_t)f + (j + 1) % 3]};
+            e.m_face = {f, last == (size_t)k ? 0xffffffffu : h[last].pos / 3};
+            m_edges[creates[p]] = e;
         }
     }
     m_closed = true;
@@ -375,6 +414,28 @@ bool SimulationModel::pushConstraint(int type, const unsigned int *bodies, const
     return true;
 }
 
+// Order-preserving bulk construction (host part): candidate i of `count` is computed by fill(i, bodies, params) ->
+// bool (the constraint class's initConstraint result), independently of the others and therefore in parallel; the accepted ones
+// are appended in candidate order, i.e. exactly as the reference's sequential add loop would have inserted them.
+template <class A, class F>
+static void push_bulk(TypeStore &s, std::vector<ConstraintRef> &order, int type, size_t count, A &&accept, F &&fill) {
+    const int nb = pbd_num_bodies(type), np = pbd_num_params(type);
+    std::vector<unsigned int> pos(count + 1, 0u);
+    #pragma omp parallel for schedule(static) num_threads(model_threads())
+    for (long long i = 0; i < (long long)count; i++) pos[i + 1] = accept((size_t)i) ? 1u : 0u;  // cheap topological test
+    for (size_t i = 0; i < count; i++) pos[i + 1] += pos[i];
+    const size_t add = pos[count], base = s.ids.size(), obase = order.size();
+    s.ids.resize(base + add); s.bodies.resize((base + add) * nb); s.params.resize((base + add) * np); order.resize(obase + add);
+    #pragma omp parallel for schedule(static) num_threads(model_threads())
+    for (long long i = 0; i < (long long)count; i++) {
+        if (pos[i + 1] == pos[i]) continue;
+        const size_t k = pos[i];
+        s.ids[base + k] = (unsigned int)(obase + k);
+        fill((size_t)i, &s.bodies[(base + k) * nb], &s.params[(base + k) * np]);  // straight into the store: no staging copy
+        order[obase + k] = ConstraintRef{type, (unsigned int)(base + k)};
+    }
+}
+
 // DistanceConstraint::initConstraint (Constraints.cpp:1166-1181): rest length from x0
 bool SimulationModel::addDistanceConstraint(unsigned int p1, unsigned int p2, Real stiffness) {
     const ParticleData &pd = m_particles;
@@ -538,11 +599,14 @@ void SimulationModel::addClothConstraints(const TriangleModel *tm, unsigned int 
     const unsigned int offset = tm->getIndexOffset();
     const IndexedFaceMesh &mesh = tm->getParticleMesh();
     if (clothMethod == 1 || clothMethod == 4) {
-        reserveConstraints(clothMethod == 1 ? PBD_DISTANCE : PBD_DISTANCE_XPBD, mesh.getEdges().size());
-        for (const IndexedFaceMesh::Edge &e : mesh.getEdges()) {
-            if (clothMethod == 1) addDistanceConstraint(e.m_vert[0] + offset, e.m_vert[1] + offset, distanceStiffness);
-            else addDistanceConstraint_XPBD(e.m_vert[0] + offset, e.m_vert[1] + offset, distanceStiffness);
-        }
+        const int type = clothMethod == 1 ? PBD_DISTANCE : PBD_DISTANCE_XPBD;
+        const IndexedFaceMesh::Edges &edges = mesh.getEdges();
+        const ParticleData &pd = m_particles;
+        push_bulk(m_store[type], m_order, type, edges.size(), [](size_t) { return true; }, [&](size_t i, unsigned int *b, Real *p) {
+            b[0] = edges[i].m_vert[0] + offset; b[1] = edges[i].m_vert[1] + offset;
+            p[0] = (Real)normd(d3(pd.m_x0[b[1]]) - d3(pd.m_x0[b[0]])); p[1] = distanceStiffness;  // DistanceConstraint::initConstraint
+        });
+        if (!edges.empty()) { m_groupsInitialized = false; m_generation++; }
     } else if (clothMethod == 2 || clothMethod == 3) {
         const unsigned int *tris = mesh.getFaces().data();
         reserveConstraints(clothMethod == 2 ? PBD_FEMTRIANGLE : PBD_STRAINTRIANGLE, mesh.numFaces());
@@ -561,7 +625,33 @@ void SimulationModel::addBendingConstraints(const TriangleModel *tm, unsigned in
     const unsigned int offset = tm->getIndexOffset();
     const IndexedFaceMesh &mesh = tm->getParticleMesh();
     const unsigned int *tris = mesh.getFaces().data();
-    reserveConstraints(bendingMethod == 1 ? PBD_DIHEDRAL : (bendingMethod == 2 ? PBD_ISOBENDING : PBD_ISOBENDING_XPBD), mesh.getEdges().size());
+    if (bendingMethod == 2 || bendingMethod == 3) {
+        const int type = bendingMethod == 2 ? PBD_ISOBENDING : PBD_ISOBENDING_XPBD;
+        const IndexedFaceMesh::Edges &edges = mesh.getEdges();
+        const ParticleData &pd = m_particles;
+        const size_t before = m_order.size();
+        auto opposite = [&](const IndexedFaceMesh::Edge &e, int &point1, int &point2) {
+            const unsigned int tri1 = e.m_face[0], tri2 = e.m_face[1];
+            point1 = point2 = -1;
+            if (tri1 == 0xffffffffu || tri2 == 0xffffffffu) return false;
+            const unsigned int a1 = e.m_vert[0], a2 = e.m_vert[1];
+            for (int j = 0; j < 3; j++) if (tris[3 * tri1 + j] != a1 && tris[3 * tri1 + j] != a2) { point1 = (int)tris[3 * tri1 + j]; break; }
+            for (int j = 0; j < 3; j++) if (tris[3 * tri2 + j] != a1 && tris[3 * tri2 + j] != a2) { point2 = (int)tris[3 * tri2 + j]; break; }
+            return point1 != -1 && point2 != -1;
+        };
+        push_bulk(m_store[type], m_order, type, edges.size(),
+                  [&](size_t i) { int p1, p2; return opposite(edges[i], p1, p2); },
+                  [&](size_t i, unsigned int *b, Real *p) {
+                      int point1, point2;
+                      opposite(edges[i], point1, point2);
+                      b[0] = point1 + offset; b[1] = point2 + offset; b[2] = edges[i].m_vert[0] + offset; b[3] = edges[i].m_vert[1] + offset;
+                      p[0] = stiffness;
+                      isoBendingQ(pd, b[0], b[1], b[2], b[3], p + 1);
+                  });
+        if (m_order.size() != before) { m_groupsInitialized = false; m_generation++; }
+        return;
+    }
+    reserveConstraints(PBD_DIHEDRAL, mesh.getEdges().size());
     for (const IndexedFaceMesh::Edge &e : mesh.getEdges()) {
         const unsigned int tri1 = e.m_face[0], tri2 = e.m_face[1];
         if (tri1 == 0xffffffffu || tri2 == 0xffffffffu) continue;
@@ -699,18 +789,38 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
         m_boundRigidBodies = nr; model.rigidBodiesDirty = false;
     }
     if (rebind || m_boundGeneration != model.constraintGeneration()) {
-        model.initConstraintGroups();  // TimeStepController.cpp:256
         if (pbd_clear_constraints(m_engine)) return fail("pbd_clear_constraints");
         for (int t = 0; t < PBD_NUM_TYPES; t++) {
             const TypeStore &s = model.store(t);
             if (s.ids.empty()) continue;
             if (pbd_add_constraints(m_engine, t, (unsigned int)s.ids.size(), s.bodies.data(), s.params.data(), s.ids.data())) return fail("pbd_add_constraints");
         }
-        const SimulationModel::ConstraintGroupVector &groups = model.getConstraintGroups();
-        std::vector<unsigned int> off(groups.size() + 1, 0), ids;
-        ids.reserve(model.numConstraints());
-        for (size_t g = 0; g < groups.size(); g++) { ids.insert(ids.end(), groups[g].begin(), groups[g].end()); off[g + 1] = (unsigned int)ids.size(); }
-        if (pbd_set_groups(m_engine, (unsigned int)groups.size(), off.data(), ids.data())) return fail("pbd_set_groups");
+        // Colour groups (TimeStepController.cpp:256 -> SimulationModel::initConstraintGroups).  When the model has not been coloured yet the
+        // engine does it on the GPU (pbd_color_first_fit_device: the same greedy first fit, identical groups) and the result is mirrored
+        // into the model, so getConstraintGroups() shows what is simulated; PBD_B200_HOST_COLOURING=1 keeps the host colouring.
+        static const bool hostColouring = [] { const char *g = getenv("PBD_B200_HOST_COLOURING"); return g && atoi(g) != 0; }();
+        bool coloured = false;
+        if (!model.m_groupsInitialized && !hostColouring && model.numConstraints() > 0 && pbd_color_first_fit_device(m_engine, nullptr, nullptr) == 0) {
+            unsigned int ng = 0;
+            if (pbd_get_num_groups(m_engine, &ng) == 0) {
+                std::vector<unsigned int> off(ng + 1), ids(model.numConstraints());
+                if (pbd_get_groups(m_engine, off.data(), ids.data()) == 0) {
+                    SimulationModel::ConstraintGroupVector &groups = model.getConstraintGroups();
+                    groups.assign(ng, std::vector<unsigned int>());
+                    for (unsigned int g = 0; g < ng; g++) groups[g].assign(ids.begin() + off[g], ids.begin() + off[g + 1]);
+                    model.m_groupsInitialized = true;
+                    coloured = true;
+                }
+            }
+        }
+        if (!coloured) {
+            model.initConstraintGroups();
+            const SimulationModel::ConstraintGroupVector &groups = model.getConstraintGroups();
+            std::vector<unsigned int> off(groups.size() + 1, 0), ids;
+            ids.reserve(model.numConstraints());
+            for (size_t g = 0; g < groups.size(); g++) { ids.insert(ids.end(), groups[g].begin(), groups[g].end()); off[g + 1] = (unsigned int)ids.size(); }
+            if (pbd_set_groups(m_engine, (unsigned int)groups.size(), off.data(), ids.data())) return fail("pbd_set_groups");
+        }
         m_boundGeneration = model.constraintGeneration();
     }
     m_boundModel = &model;

@@ -539,7 +539,7 @@ def test_adapter_notices_parameter_setters_and_mass_edits(precision, cpu_libs):
         m.set_mass(210, 0.0)          # pin a particle in the middle of the sheet
     x_mid = cpu.get("x").copy()
     gpu.step(3); cpu.step(3)
-    assert gpu.gpu_error() == ""
+    assert gpu.gpu_error() == "", gpu.gpu_error()
     xg, xc = gpu.get("x"), cpu.get("x")
     e = rel_position_error(xg, xc)
     print("adapter after setClothStiffness + setMass, Real=%s: rel pos %.2e" % (precision, e))
