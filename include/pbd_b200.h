@@ -58,8 +58,10 @@ enum pbd_solver_mode {
     PBD_MODE_RESIDENT = 1,   /* one launch per step: positions resident in the distributed shared memory of thread-block clusters,
                                 hardware cluster barrier between colours (csrc/resident.cuh); scenes up to ~1.5 M particles */
     PBD_MODE_LAUNCH = 2,     /* plain stream launches (debug / per-kernel profiling) */
-    PBD_MODE_JACOBI = 3      /* comparison path, NOT the reference's algorithm: colours ignored, one launch per type and sweep, corrections
+    PBD_MODE_JACOBI = 3,     /* comparison path, NOT the reference's algorithm: colours ignored, one launch per type and sweep, corrections
                                 accumulated with float4 atomicAdd and averaged per particle (rigid-body joints are not supported) */
+    PBD_MODE_AUTO = 4        /* default: RESIDENT where it is the faster exact mode (cloth and FEM models that fit), else GRAPH; both produce
+                                the same bits, so the choice is invisible in the results (pbd_get_mode reports it) */
 };
 
 typedef struct pbd_stats {
@@ -119,6 +121,7 @@ int pbd_get_groups(pbd_engine *e, unsigned *offsets, unsigned *ids);
 int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsigned maxIter, int velocityUpdateMethod,
                    const float gravity[3]);
 int pbd_set_mode(pbd_engine *e, int mode);
+int pbd_get_mode(pbd_engine *e, int *requested, int *active);  /* active = the mode the current image runs in (resolved at the first step) */
 /* sort constraints inside each (colour,type) bucket by their lowest particle index (order inside a colour is free). */
 int pbd_set_bucket_sort(pbd_engine *e, int enable);
 

@@ -17,13 +17,13 @@ TYPE_NAMES = ["Distance", "Distance_XPBD", "Dihedral", "IsometricBending", "Isom
               "StrainTriangle", "Volume", "Volume_XPBD", "FEMTet", "FEMTet_XPBD", "StrainTet", "ShapeMatching", "BallJoint",
               "RigidBodyParticleBallJoint"]
 ATTR_X, ATTR_V, ATTR_X0, ATTR_OLDX, ATTR_LASTX = range(5)
-MODE_GRAPH, MODE_RESIDENT, MODE_LAUNCH, MODE_JACOBI = 0, 1, 2, 3
+MODE_GRAPH, MODE_RESIDENT, MODE_LAUNCH, MODE_JACOBI, MODE_AUTO = 0, 1, 2, 3, 4
 
 # every symbol include/pbd_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "pbd_set_particles", "pbd_set_attr",
            "pbd_get_attr", "pbd_set_masses", "pbd_set_rigid_bodies", "pbd_get_rigid_bodies", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
            "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_color_first_fit_device", "pbd_pin_host", "pbd_unpin_host", "pbd_get_num_groups", "pbd_get_groups",
-           "pbd_set_params", "pbd_set_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host",
+           "pbd_set_params", "pbd_set_mode", "pbd_get_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host",
            "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step"]
 
 
@@ -70,6 +70,7 @@ def lib():
         _lib.pbd_get_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.pbd_set_params.argtypes = [C.c_void_p, C.c_float, C.c_uint, C.c_uint, C.c_int, C.c_void_p]
         _lib.pbd_set_mode.argtypes = [C.c_void_p, C.c_int]
+        _lib.pbd_get_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.pbd_set_bucket_sort.argtypes = [C.c_void_p, C.c_int]
         _lib.pbd_step.argtypes = [C.c_void_p, C.c_uint]
         _lib.pbd_step_host.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -216,6 +217,12 @@ class Engine:
 
     def set_mode(self, mode):
         _ck(lib().pbd_set_mode(self._h, int(mode)))
+
+    def get_mode(self):
+        """(requested, active): active is what the current image runs in (the resolution of MODE_AUTO after the first step)."""
+        r, a = C.c_int(0), C.c_int(0)
+        _ck(lib().pbd_get_mode(self._h, C.byref(r), C.byref(a)))
+        return r.value, a.value
 
     def set_bucket_sort(self, enable):
         _ck(lib().pbd_set_bucket_sort(self._h, int(bool(enable))))

@@ -102,7 +102,9 @@ struct pbd_engine {
     bool sortBuckets = true;
     // parameters
     float dt = 0.005f; unsigned subSteps = 5, maxIter = 1; int velMethod = 0; float g[3] = {0.f, -9.81f, 0.f};
-    int mode = PBD_MODE_GRAPH;
+    int mode = PBD_MODE_AUTO;             // requested (pbd_set_mode)
+    int active = PBD_MODE_GRAPH;          // what the current image runs in: == mode, or the resolution of PBD_MODE_AUTO
+    bool autoNoResident = false;          // PBD_MODE_AUTO: the resident mode was tried for this model and refused
     // graph cache
     cudaGraphExec_t graphExec = nullptr;
     bool graphValid = false;
@@ -372,7 +374,7 @@ extern "C" int pbd_clear_constraints(pbd_engine *e) {
     for (auto &h : e->host) { h.ids.clear(); h.bodies.clear(); h.params.clear(); }
     e->numConstraints = 0;
     e->groupOff.clear(); e->groupIds.clear(); e->groupsSet = false;
-    e->imageDirty = true;
+    e->imageDirty = true; e->autoNoResident = false;
     return 0;
 }
 
@@ -392,7 +394,7 @@ extern "C" int pbd_add_constraints(pbd_engine *e, int type, unsigned count, cons
     h.params.insert(h.params.end(), params, params + (size_t)count * s.nParams);
     e->numConstraints += count;
     e->groupsSet = false;  // any add invalidates the groups (SimulationModel: m_groupsInitialized = false)
-    e->imageDirty = true;
+    e->imageDirty = true; e->autoNoResident = false;
     return 0;
 }
 
@@ -565,9 +567,19 @@ extern "C" int pbd_set_params(pbd_engine *e, float dt, unsigned subSteps, unsign
 }
 extern "C" int pbd_set_mode(pbd_engine *e, int mode) {
     if (!e) return fail("null engine");
-    if (mode != PBD_MODE_GRAPH && mode != PBD_MODE_RESIDENT && mode != PBD_MODE_LAUNCH && mode != PBD_MODE_JACOBI) return fail("unknown solver mode %d", mode);
-    if ((mode == PBD_MODE_RESIDENT) != (e->mode == PBD_MODE_RESIDENT)) e->imageDirty = true;  // the resident image encodes indices differently
-    e->mode = mode; drop_graph(e);
+    if (mode != PBD_MODE_GRAPH && mode != PBD_MODE_RESIDENT && mode != PBD_MODE_LAUNCH && mode != PBD_MODE_JACOBI && mode != PBD_MODE_AUTO) return fail("unknown solver mode %d", mode);
+    if (mode == e->mode) return 0;
+    // the resident image encodes indices differently; with AUTO on either side the resolution may change
+    if (mode == PBD_MODE_AUTO || e->mode == PBD_MODE_AUTO || (mode == PBD_MODE_RESIDENT) != (e->active == PBD_MODE_RESIDENT)) e->imageDirty = true;
+    e->mode = mode; e->autoNoResident = false;
+    if (mode != PBD_MODE_AUTO) e->active = mode;
+    drop_graph(e);
+    return 0;
+}
+extern "C" int pbd_get_mode(pbd_engine *e, int *requested, int *active) {
+    if (!e) return fail("null engine");
+    if (requested) *requested = e->mode;
+    if (active) *active = e->active;
     return 0;
 }
 extern "C" int pbd_set_bucket_sort(pbd_engine *e, int enable) {
@@ -614,8 +626,11 @@ static void bisect(std::vector<unsigned> &idx, size_t lo, size_t hi, unsigned t0
     const size_t mid = lo + (size_t)((double)(hi - lo) * ntL / nt);
     auto key = [&](unsigned i) { const float4 &p = x[i]; return ax == 0 ? p.x : (ax == 1 ? p.y : p.z); };
     std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](unsigned a, unsigned b) { const float ka = key(a), kb = key(b); return ka < kb || (ka == kb && a < b); });
+    // the two halves are independent: run them as tasks while they are big enough to pay for it
+    #pragma omp task shared(idx, x, tileOf) if (hi - lo > 65536)
     bisect(idx, lo, mid, t0, ntL, x, tileOf);
     bisect(idx, mid, hi, t0 + ntL, nt - ntL, x, tileOf);
+    #pragma omp taskwait
 }
 
 struct ResidentPlan {
@@ -727,12 +742,19 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
         for (unsigned i = 0; i < n; i++) x[i] = raw[e->slot[i]];
         std::vector<unsigned> idx(n), region(n);
         for (unsigned i = 0; i < n; i++) idx[i] = i;
+        #pragma omp parallel num_threads(host_threads())
+        #pragma omp single
         bisect(idx, 0, n, 0, G, x, region);  // cluster regions; idx is now grouped region by region
         size_t lo = 0;
         for (unsigned g = 0; g < G; g++) {
             size_t hi = lo;
             while (hi < n && region[idx[hi]] == g) hi++;
-            bisect(idx, lo, hi, g * C, C, x, pl.tileOf);
+            if (C == 1) { for (size_t i = lo; i < hi; i++) pl.tileOf[idx[i]] = g; }
+            else {
+                #pragma omp parallel num_threads(host_threads())
+                #pragma omp single
+                bisect(idx, lo, hi, g * C, C, x, pl.tileOf);
+            }
             lo = hi;
         }
         // global-homed = touched by a constraint whose particles lie in more than one cluster
@@ -740,11 +762,13 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
             for (int t = 0; t < PBD_NUM_TYPES; t++) {
                 const HostType &h = e->host[t];
                 const int nb = type_shape(t).nBodies;
-                for (size_t c = 0; c < h.ids.size(); c++) {
-                    const unsigned *b = &h.bodies[c * nb];
+                unsigned char *hg = pl.homedGlobal.data();
+                #pragma omp parallel for schedule(static) num_threads(host_threads())
+                for (long long c = 0; c < (long long)h.ids.size(); c++) {
+                    const unsigned *b = &h.bodies[(size_t)c * nb];
                     bool spans = false;
                     for (int k = 1; k < nb; k++) spans |= (pl.tileOf[b[k]] / C != pl.tileOf[b[0]] / C);
-                    if (spans) for (int k = 0; k < nb; k++) pl.homedGlobal[b[k]] = 1;
+                    if (spans) for (int k = 0; k < nb; k++) hg[b[k]] = 1;  // every writer stores the same byte
                 }
             }
         // threads of a CTA dedicated to the X items: in proportion to their share, times 2.7 because an X item waits for L2 where
@@ -754,9 +778,10 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
             for (int t = 0; t < PBD_NUM_TYPES; t++) {
                 const HostType &h = e->host[t];
                 const int nb = type_shape(t).nBodies;
-                for (size_t c = 0; c < h.ids.size(); c++) {
+                #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(+ : xItems)
+                for (long long c = 0; c < (long long)h.ids.size(); c++) {
                     bool x = false;
-                    for (int k = 0; k < nb; k++) x |= (!is_rb_body(t, k) && pl.homedGlobal[h.bodies[c * nb + k]]);
+                    for (int k = 0; k < nb; k++) x |= (!is_rb_body(t, k) && pl.homedGlobal[h.bodies[(size_t)c * nb + k]]);
                     xItems += x;
                 }
             }
@@ -793,9 +818,34 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
     return 0;
 }
 
+static int flatten_image(pbd_engine *e);
+// PBD_MODE_AUTO: the resident mode where it is the faster exact mode -- models made of cloth and FEM / volume constraints (measured:
+// cfg1, cfg2, cfg3, cfg5; profiles/README.md R2.1); mixed models with rigid coupling and the heavy solver families stay in graph
+// mode (cfg4) -- falling back to the graph mode when the resident mode refuses the model.
+static bool auto_prefers_resident(const pbd_engine *e) {
+    if (e->autoNoResident || e->numConstraints == 0 || e->n == 0) return false;
+    unsigned present = 0;
+    for (int t = 0; t < PBD_NUM_TYPES; t++) if (!e->host[t].ids.empty()) present |= 1u << t;
+    return (present & ~(kMaskCloth | kMaskFem)) == 0 || (present & ~kMaskLight) == 0;
+}
 static int flatten(pbd_engine *e) {
     if (!e->imageDirty) return 0;
+    if (e->mode != PBD_MODE_AUTO) { e->active = e->mode; return flatten_image(e); }
+    e->active = auto_prefers_resident(e) ? PBD_MODE_RESIDENT : PBD_MODE_GRAPH;
+    int rc = flatten_image(e);
+    if (rc && e->active == PBD_MODE_RESIDENT) {  // refused (does not fit, user-modified bending Q, ...): the graph mode takes every model
+        if (getenv("PBD_B200_VERBOSE")) fprintf(stderr, "[pbd_b200] auto mode: resident refused (%s), using the graph mode\n", g_err.c_str());
+        e->autoNoResident = true; e->active = PBD_MODE_GRAPH; e->imageDirty = true;
+        rc = flatten_image(e);
+    }
+    return rc;
+}
+static int flatten_image(pbd_engine *e) {
+    if (!e->imageDirty) return 0;
     CKE(use(e));
+    static const bool verbose = getenv("PBD_B200_VERBOSE") != nullptr;
+    double tPrev = omp_get_wtime();
+    auto lap = [&](const char *what) { if (verbose) { const double t = omp_get_wtime(); fprintf(stderr, "[pbd_b200] flatten: %-34s %.3f s\n", what, t - tPrev); tPrev = t; } };
     if (!e->groupsSet) {
         if (e->numConstraints == 0) { e->groupOff.assign(1, 0u); e->groupIds.clear(); e->groupsSet = true; }
         else {
@@ -822,7 +872,7 @@ static int flatten(pbd_engine *e) {
     const unsigned nGroups = (unsigned)e->groupOff.size() - 1;
 
     // 0. particle placement: tile-major for the resident mode, the formula layout otherwise
-    const bool tiled = (e->mode == PBD_MODE_RESIDENT);
+    const bool tiled = (e->active == PBD_MODE_RESIDENT);
     ResidentPlan pl;
     std::vector<unsigned> tileOff;
     std::vector<unsigned> &tileOf = pl.tileOf;
@@ -834,6 +884,7 @@ static int flatten(pbd_engine *e) {
         e->slotIsTiled = false;
     }
 
+    lap("colouring + validation + placement");
     // 1. order every type's constraints bucket by bucket
     std::vector<unsigned> order[PBD_NUM_TYPES];  // device position -> local host index
     e->buckets.clear();
@@ -893,6 +944,7 @@ static int flatten(pbd_engine *e) {
         }
     }
 
+    lap("bucket ordering");
     // debug-grade safety: inside a colour no particle may be used twice (race freedom by construction)
     {
         // particles and rigid bodies are stamped in separate index spaces (the reference's colouring shares one, which only
@@ -916,6 +968,7 @@ static int flatten(pbd_engine *e) {
         }
     }
 
+    lap("colouring validity check");
     // 2. build and upload the SoA arrays of every type
     double bytesPerSweep = 0.0;
     for (int t = 0; t < PBD_NUM_TYPES; t++) {
@@ -1073,6 +1126,7 @@ static int flatten(pbd_engine *e) {
         bytesPerSweep += (double)cnt * algorithmic_bytes(t, variant);
     }
 
+    lap("SoA arrays + upload");
     // 3. bucket table; resident mode: colour ranges, per-tile runs and the arrival counts of the X items
     CKE(upload_vec(e->dBuckets, e->buckets, e->stream));
     if (tiled) {
@@ -1120,6 +1174,7 @@ static int flatten(pbd_engine *e) {
     }
     CK(cudaStreamSynchronize(e->stream));
 
+    lap("phase tables");
     e->stats.num_constraints = e->numConstraints;
     e->stats.num_groups = nGroups;
     e->stats.num_buckets = (unsigned)e->buckets.size();
@@ -1401,11 +1456,20 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
     CK(cudaEventRecord(e->evStart, e->stream));
     for (unsigned s = 0; s < nSteps; s++) {
         unsigned long long L = 0;
-        if (e->mode == PBD_MODE_LAUNCH) {
+        if (e->active == PBD_MODE_LAUNCH) {
             CKE(enqueue_step_launches(e, e->stream, &L));
-        } else if (e->mode == PBD_MODE_RESIDENT) {
-            CKE(enqueue_step_resident(e, e->stream, &L));
-        } else if (e->mode == PBD_MODE_JACOBI) {
+        } else if (e->active == PBD_MODE_RESIDENT) {
+            int rc = enqueue_step_resident(e, e->stream, &L);
+            if (rc && e->mode == PBD_MODE_AUTO) {  // e.g. the clusters cannot be co-resident on this device: run the step in graph mode instead
+                e->autoNoResident = true; e->imageDirty = true;
+                CKE(flatten(e));
+                unsigned long long LL = 0;
+                if (!e->graphValid) { CKE(ensure_graph(e, &LL)); e->graphLaunches = LL; }
+                CK(cudaGraphLaunch(e->graphExec, e->stream));
+                L = e->graphLaunches; rc = 0;
+            }
+            CKE(rc);
+        } else if (e->active == PBD_MODE_JACOBI) {
             CKE(enqueue_step_jacobi(e, e->stream, &L));
         } else {
             unsigned long long LL = 0;
@@ -1505,7 +1569,7 @@ extern "C" int pbd_get_stats(pbd_engine *e, pbd_stats *out) {
 
 extern "C" int pbd_profile_step(pbd_engine *e, float *msPerType, float *msIntegrate, float *msVelocity, unsigned *launchesPerType) {
     if (!e) return fail("null engine");
-    if (e->mode == PBD_MODE_RESIDENT || e->mode == PBD_MODE_JACOBI) return fail("pbd_profile_step: per-bucket launches do not exist in this mode (select PBD_MODE_GRAPH or PBD_MODE_LAUNCH first)");
+    if (e->active == PBD_MODE_RESIDENT || e->active == PBD_MODE_JACOBI || e->mode == PBD_MODE_AUTO) return fail("pbd_profile_step: per-bucket launches do not exist in this mode (select PBD_MODE_GRAPH or PBD_MODE_LAUNCH first)");
     CKE(use(e)); CKE(flatten(e));
     CK(cudaStreamSynchronize(e->stream));
     // One event between every pair of consecutive launches, all recorded in stream order without host synchronisation

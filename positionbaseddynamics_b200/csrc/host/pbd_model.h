@@ -330,7 +330,7 @@ private:
     unsigned int m_subSteps = 5, m_maxIterations = 1, m_maxIterationsV = 5;  // TimeStepController.cpp:28-30
     int m_velocityUpdateMethod = 0;
     Vector3r m_gravitation = Vector3r(0, static_cast<Real>(-9.81), 0);  // Simulation.cpp:16
-    int m_mode = PBD_MODE_GRAPH, m_modeSent = -1;
+    int m_mode = PBD_MODE_AUTO, m_modeSent = -1;
     struct SentParams { float dt; unsigned int subSteps, maxIter; int velMethod; float g[3]; } m_sent{};
     bool m_sentValid = false;
     const SimulationModel *m_boundModel = nullptr;

@@ -535,21 +535,76 @@ def test_adapter_notices_parameter_setters_and_mass_edits(precision, cpu_libs):
     x_start = perturb([gpu, cpu], 0.02)
     gpu.step(2); cpu.step(2)
     for m in (gpu, cpu):
-        m.set_cloth_stiffness(0.25)   # every DistanceConstraint::m_stiffness
+        m.set_cloth_stiffness(0.05)   # every DistanceConstraint::m_stiffness
         m.set_mass(210, 0.0)          # pin a particle in the middle of the sheet
-    x_mid = cpu.get("x").copy()
-    gpu.step(3); cpu.step(3)
+    x_mid = cpu.get("x").copy(); xg_mid = gpu.get("x").copy()
+    gpu.step(6); cpu.step(6)
     assert gpu.gpu_error() == "", gpu.gpu_error()
     xg, xc = gpu.get("x"), cpu.get("x")
     e = rel_position_error(xg, xc)
     print("adapter after setClothStiffness + setMass, Real=%s: rel pos %.2e" % (precision, e))
     assert e <= TOL
-    assert np.abs(xc[210] - x_mid[210]).max() == 0.0 and np.abs(xg[210] - x_mid[210]).max() <= 1e-6  # the pinned particle stopped
+    assert np.abs(xc[210] - x_mid[210]).max() == 0.0 and np.abs(xg[210] - xg_mid[210]).max() == 0.0  # the pinned particle stopped, on both sides
+    old_c = cpu.get("oldX").copy()
     # the edits matter: a twin that ignored them is off by far more than the tolerance
     ign = cpu_libs.CpuPbd("ref", "f64")
     scenes.cloth(ign, 20, 20, 1, 2, dist_k=1.0, bend_k=0.01, max_iter=4)
-    ign.set("x", x_start); ign.step(5)
-    assert rel_position_error(ign.get("x"), xc) > 10 * TOL
+    ign.set("x", x_start); ign.step(8)
+    assert rel_position_error(ign.get("x"), xc) > 10 * TOL  # 2.3e-3 (the checkers share one library instance: xc was copied before)
     # history comes back on demand (second-order velocity update of another TimeStep would read it)
     assert gpu.download_history() == 0
-    assert rel_position_error(gpu.get("oldX"), cpu.get("oldX")) <= TOL
+    assert rel_position_error(gpu.get("oldX"), old_c) <= TOL
+
+
+def test_auto_mode_picks_resident_where_it_pays_and_falls_back():
+    """PBD_MODE_AUTO (the default): cloth / FEM models run in the resident mode, models with rigid coupling in graph mode, and a model
+    the resident mode refuses (IsometricBending with a user-modified, non-rank-one Q) falls back to the graph mode without an error.
+    The bits never depend on the choice."""
+    from positionbaseddynamics_b200 import _capi
+    from positionbaseddynamics_b200.model import HostModel
+
+    def engine_of(hm, with_rb=False, edit=None):
+        types, bodies, params, _ = hm.constraints()
+        if edit is not None:
+            params = params.copy(); edit(types, params)
+        mass, _ = hm.masses()
+        eng = _capi.Engine(0)
+        eng.set_particles(hm.get("x"), mass)
+        if with_rb:
+            rb = hm.rigid_bodies()
+            eng.set_rigid_bodies([0.0 if i % 3 == 0 else 1.0 for i in range(len(rb))], rb[:, :3], rb[:, 3:7],
+                                 [scenes.box_inertia(1.0, 0.5, 0.5, 0.5) if i % 3 == 0 else scenes.box_inertia(1.0, 0.4, 2.0, 0.4) for i in range(len(rb))])
+        eng.add_flat(types, bodies, params)
+        eng.color_first_fit()
+        eng.set_params(dt=0.005, sub_steps=1, max_iter=4)
+        return eng
+
+    def run(hm, mode, **kw):
+        eng = engine_of(hm, **kw)
+        if mode is not None:
+            eng.set_mode(mode)
+        assert eng.get_mode()[0] == (_capi.MODE_AUTO if mode is None else mode)
+        eng.step(3); eng.sync()
+        out = eng.get_attr(_capi.ATTR_X).copy(), eng.get_mode()[1]
+        eng.close()
+        return out
+
+    cloth = HostModel(); scenes.cloth(cloth, 24, 24, 4, 3, dist_k=1.0e5, bend_k=100.0, max_iter=4)
+    perturb([cloth], 0.02)
+    xa, active = run(cloth, None)
+    assert active == _capi.MODE_RESIDENT
+    assert (xa == run(cloth, _capi.MODE_GRAPH)[0]).all()
+
+    rig = HostModel(); scenes.cfg4(rig, n_cloth=16, bar_dims=(5, 3, 3))
+    xr, active = run(rig, None, with_rb=True)
+    assert active == _capi.MODE_GRAPH
+    assert (xr == run(rig, _capi.MODE_RESIDENT, with_rb=True)[0]).all()  # the resident kernel runs joints too when asked to
+
+    def spoil_q(types, params):  # one bending constraint gets a Q that is not of the rank-one form
+        i = int(np.nonzero(types == _capi.ISOBENDING_XPBD)[0][0])
+        params[i, 1] += 0.5
+    xq, active = run(cloth, None, edit=spoil_q)
+    assert active == _capi.MODE_GRAPH and np.isfinite(xq).all()
+    assert (xq == run(cloth, _capi.MODE_GRAPH, edit=spoil_q)[0]).all()
+    with pytest.raises(_capi.PbdError):
+        run(cloth, _capi.MODE_RESIDENT, edit=spoil_q)
