@@ -381,6 +381,16 @@ def run_b200(args):
     else:
         e2e_max = e2e_s
     e2e_value = world * proj_per_step * e2e_steps / e2e_max
+    # the same call with the device state authoritative (x_in = v_in = NULL: the host did not edit the state between steps, only the
+    # result is downloaded) -- what integration/GpuTimeStepController.h does after setHostStateAuthoritative(false); reported beside e2e
+    for _ in range(2):
+        eng.step_host(1, None, None, xo.numpy())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.step_host(1, None, None, xo.numpy())
+    torch.cuda.synchronize()
+    e2e_dev_s = time.perf_counter() - t0
 
     if rank != 0:
         if dist is not None:
@@ -492,7 +502,9 @@ def run_b200(args):
                                                  colour_groups=int(st.num_groups), buckets=int(st.num_buckets), scene_build_s=round(info["build_s"], 2)),
             "sim_steps_per_sec": world * args.steps / (ms_max * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 12, "d2h_bytes_per_step": n * 12,
-                    "ms_per_step": 1e3 * e2e_max / e2e_steps, "api": "pbd_step_host (C ABI, pinned host buffers)"},
+                    "ms_per_step": 1e3 * e2e_max / e2e_steps, "api": "pbd_step_host (C ABI, pinned host buffers)",
+                    "download_only": {"ms_per_step": 1e3 * e2e_dev_s / e2e_steps, "value": proj_per_step * e2e_steps / e2e_dev_s, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * 12,
+                                      "note": "rank 0; x_in = v_in = NULL (device state authoritative between steps), result downloaded every step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mode_probe_ms": probe,
             "checksum": {"crc32": crcs[0], "x_sum": xsum, "per_rank_crc32": crcs, "after_steps": "mode probe + warmup + steps (deterministic for fixed K, W)"},
             "checksums_equal": all(c == crcs[0] for c in crcs), "side": side}

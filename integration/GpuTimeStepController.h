@@ -50,6 +50,13 @@ public:
     // setSolidStiffness, ... rewrite every constraint of a type: sentinel constraints are compared every step).  Call this after
     // editing members of individual constraints or rigid bodies by hand.
     void invalidate() { m_boundConstraints = ~size_t(0); }
+    // Host-state policy.  Default (true): the model's positions and velocities are uploaded before every step, so edits made by user
+    // code between steps (dragging particles, resetting velocities) are honoured exactly like the reference does -- at the price of
+    // 24 bytes per particle of PCIe traffic per step.  false: the device state is authoritative between steps; positions and
+    // velocities are still downloaded into the model after every step (rendering keeps working), uploads happen only at bind time and
+    // after invalidateState().  For pure simulation loops this removes two thirds of the per-step copies.
+    void setHostStateAuthoritative(bool on) { m_hostAuthoritative = on; m_stateInvalid = true; }
+    void invalidateState() { m_stateInvalid = true; }
     // The device owns oldX / lastX while this time step is installed (they feed the second-order velocity update); copy them back
     // into the model before handing it to another TimeStep (TimeStepController.cpp:112-118 reads them).
     bool downloadHistory(SimulationModel &model) {
@@ -99,10 +106,14 @@ public:
             // from and into the model's own arrays (page-locked at bind time), no host-side conversion at all
             float *x = reinterpret_cast<float *>(&pd.getPosition(0)[0]), *v = reinterpret_cast<float *>(&pd.getVelocity(0)[0]);
             if (!m_pinFailed && (x != m_pinnedX || v != m_pinnedV)) pin(x, v, n);  // the vectors were (re)allocated
-            if (pbd_step_host(m_engine, 1, x, v, x, v)) return fail();
+            const bool up = m_hostAuthoritative || m_stateInvalid;
+            if (pbd_step_host(m_engine, 1, up ? x : nullptr, up ? v : nullptr, x, v)) return fail();
+            m_stateInvalid = false;
         } else {
-            packParticles(pd, n);
-            if (pbd_step_host(m_engine, 1, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr)) return fail();
+            const bool up = m_hostAuthoritative || m_stateInvalid;
+            if (up) packParticles(pd, n); else { m_x.resize(3 * (size_t)n); m_v.resize(3 * (size_t)n); }
+            if (pbd_step_host(m_engine, 1, (n && up) ? m_x.data() : nullptr, (n && up) ? m_v.data() : nullptr, n ? m_x.data() : nullptr, n ? m_v.data() : nullptr)) return fail();
+            m_stateInvalid = false;
 #pragma omp parallel for schedule(static)
             for (int i = 0; i < (int)n; i++) {
                 pd.getPosition(i) = Vector3r((Real)m_x[3 * i], (Real)m_x[3 * i + 1], (Real)m_x[3 * i + 2]);
@@ -123,7 +134,7 @@ protected:
     std::string m_error;
     std::vector<float> m_x, m_v, m_mass;
     float *m_pinnedX = nullptr, *m_pinnedV = nullptr;
-    bool m_pinFailed = false, m_checkMasses = true;
+    bool m_pinFailed = false, m_checkMasses = true, m_hostAuthoritative = true, m_stateInvalid = true;
     std::vector<float> m_signature;
 
     // values of the first and the last constraint of the model plus one in the middle, per call: O(1)

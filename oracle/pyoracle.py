@@ -177,6 +177,15 @@ class CpuPbd:
         assert self.kind in ("ref", "refgpu")
         self.lib.ref_set_cloth_stiffness(_D(k))
 
+    def set_host_state_authoritative(self, on):
+        """refgpu only: GpuTimeStepController::setHostStateAuthoritative (false: no per-step upload of x and v)."""
+        assert self.kind == "refgpu"
+        self.lib.ref_set_host_state_authoritative(int(bool(on)))
+
+    def invalidate_state(self):
+        assert self.kind == "refgpu"
+        self.lib.ref_invalidate_state_gpu()
+
     def download_history(self):
         assert self.kind == "refgpu"
         return int(self.lib.ref_download_history())

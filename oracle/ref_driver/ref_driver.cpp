@@ -400,6 +400,8 @@ int ref_attach_collision_object() {
     return (int)cd->getCollisionObjects().size();
 }
 void ref_invalidate_gpu() { if (g_gpuTs) g_gpuTs->invalidate(); }
+void ref_set_host_state_authoritative(int on) { if (g_gpuTs) g_gpuTs->setHostStateAuthoritative(on != 0); }
+void ref_invalidate_state_gpu() { if (g_gpuTs) g_gpuTs->invalidateState(); }
 int ref_download_history() { return (g_gpuTs && g_gpuTs->downloadHistory(*g_model)) ? 0 : 1; }
 #endif
 

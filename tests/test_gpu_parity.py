@@ -608,3 +608,29 @@ def test_auto_mode_picks_resident_where_it_pays_and_falls_back():
     assert (xq == run(cloth, _capi.MODE_GRAPH, edit=spoil_q)[0]).all()
     with pytest.raises(_capi.PbdError):
         run(cloth, _capi.MODE_RESIDENT, edit=spoil_q)
+
+
+def test_adapter_device_authoritative_state(cpu_libs):
+    """GpuTimeStepController::setHostStateAuthoritative(false): no per-step upload of x and v (the model still receives the result
+    of every step).  Without host edits the trajectory is bit-identical to the default policy; a host edit is picked up after
+    invalidateState()."""
+    from oracle import pyoracle
+    if not pyoracle.available("refgpu", "f32"):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_gpu_f32.so not present on this box")
+    outs = []
+    for authoritative in (True, False):
+        gpu = cpu_libs.CpuPbd("refgpu", "f32")
+        scenes.cloth(gpu, 16, 16, 4, 3, dist_k=1.0e5, bend_k=100.0, max_iter=4)
+        gpu.use_gpu_timestep(0, 0)
+        gpu.set_host_state_authoritative(authoritative)
+        perturb([gpu], 0.02)
+        gpu.step(4)
+        x = gpu.get("x").copy()
+        x[100, 1] += 0.05           # a host edit between steps
+        gpu.set("x", x)
+        if not authoritative:
+            gpu.invalidate_state()
+        gpu.step(2)
+        assert gpu.gpu_error() == "", gpu.gpu_error()
+        outs.append(gpu.get("x").copy())
+    assert np.isfinite(outs[0]).all() and (outs[0] == outs[1]).all()
