@@ -137,6 +137,14 @@ int pbd_unpin_host(void *ptr);
  * (3 floats/particle each, pinned or pageable; NULL = keep the device state), run nSteps, download x (and v if
  * v_out != NULL), synchronise.  Input and output buffers may be the same arrays. */
 int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out);
+/* Pipelined form for callers that stream frames (a renderer reading frame k while frame k+1 is simulated, a batch driver): same
+ * arguments and the same per-call copies, but the call only enqueues -- the upload of the next call and the download of the
+ * previous one overlap the projection kernels (three streams, two staging slots).  The input arrays must stay untouched and the
+ * output arrays unread until pbd_step_host_wait covers the call: lag = 0 waits for every call issued so far, lag = 1 for all but
+ * the newest (so a loop "async(k); wait(1);" keeps exactly one call in flight behind the host).  Host arrays should be pinned
+ * (pbd_pin_host), otherwise the copies are staged by the driver and do not overlap. */
+int pbd_step_host_async(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out);
+int pbd_step_host_wait(pbd_engine *e, unsigned lag);
 
 int pbd_get_lambdas(pbd_engine *e, int type, float *dst, unsigned *ids); /* debug: per-type XPBD multipliers + insertion ids */
 int pbd_get_stats(pbd_engine *e, pbd_stats *out);

@@ -23,7 +23,7 @@ MODE_GRAPH, MODE_RESIDENT, MODE_LAUNCH, MODE_JACOBI, MODE_AUTO = 0, 1, 2, 3, 4
 SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "pbd_set_particles", "pbd_set_attr",
            "pbd_get_attr", "pbd_set_masses", "pbd_set_rigid_bodies", "pbd_get_rigid_bodies", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
            "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_color_first_fit_device", "pbd_pin_host", "pbd_unpin_host", "pbd_get_num_groups", "pbd_get_groups",
-           "pbd_set_params", "pbd_set_mode", "pbd_get_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host",
+           "pbd_set_params", "pbd_set_mode", "pbd_get_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host", "pbd_step_host_async", "pbd_step_host_wait",
            "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step"]
 
 
@@ -74,6 +74,8 @@ def lib():
         _lib.pbd_set_bucket_sort.argtypes = [C.c_void_p, C.c_int]
         _lib.pbd_step.argtypes = [C.c_void_p, C.c_uint]
         _lib.pbd_step_host.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.pbd_step_host_async.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.pbd_step_host_wait.argtypes = [C.c_void_p, C.c_uint]
         _lib.pbd_get_lambdas.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.pbd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         _lib.pbd_profile_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -235,6 +237,13 @@ class Engine:
 
     def step_host(self, n, x_in, v_in, x_out, v_out=None):
         _ck(lib().pbd_step_host(self._h, int(n), _ptr(x_in), _ptr(v_in), _ptr(x_out), _ptr(v_out)))
+
+    def step_host_async(self, n, x_in, v_in, x_out, v_out=None):
+        """pbd_step_host_async: enqueue only; the arrays belong to the engine until step_host_wait covers the call."""
+        _ck(lib().pbd_step_host_async(self._h, int(n), _ptr(x_in), _ptr(v_in), _ptr(x_out), _ptr(v_out)))
+
+    def step_host_wait(self, lag=0):
+        _ck(lib().pbd_step_host_wait(self._h, int(lag)))
 
     def lambdas(self, ctype):
         cnt = self.stats().constraints_per_type[ctype]

@@ -112,6 +112,14 @@ struct pbd_engine {
     // stats
     pbd_stats stats{};
     cudaEvent_t evStart = nullptr, evStop = nullptr;
+    // pbd_step_host_async: two staging slots, one upload and one download stream next to the compute stream
+    struct HostPipe {
+        cudaStream_t up = nullptr, down = nullptr;
+        DevBuf inX[2], inV[2], outX[2], outV[2];
+        cudaEvent_t uploaded[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, produced[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
+        unsigned long long issued = 0;
+        bool ready = false;
+    } pipe;
     bool timingPending = false;
     bool mergeColours = true;             // one launch per colour when it holds several types (PBD_B200_MERGE=0 disables)
     std::vector<unsigned> slot;           // host particle index -> device slot (formula layouts or the tile-major permutation)
@@ -190,6 +198,14 @@ extern "C" int pbd_destroy(pbd_engine *e) {
     }
     if (e->evStart) cudaEventDestroy(e->evStart);
     if (e->evStop) cudaEventDestroy(e->evStop);
+    if (e->pipe.ready) {
+        cudaStreamSynchronize(e->pipe.up); cudaStreamSynchronize(e->pipe.down);
+        for (int s = 0; s < 2; s++) {
+            for (auto *b : {&e->pipe.inX[s], &e->pipe.inV[s], &e->pipe.outX[s], &e->pipe.outV[s]}) b->release();
+            for (cudaEvent_t ev : {e->pipe.uploaded[s], e->pipe.consumed[s], e->pipe.produced[s], e->pipe.downloaded[s]}) cudaEventDestroy(ev);
+        }
+        cudaStreamDestroy(e->pipe.up); cudaStreamDestroy(e->pipe.down);
+    }
     if (e->ownsStream) cudaStreamDestroy(e->stream);
     delete e;
     return 0;
@@ -1540,6 +1556,67 @@ extern "C" int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, 
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// Pipelined form of pbd_step_host: the upload of call k+1 and the download of call k-1 overlap the projection kernels of call k
+// (three streams, two staging slots, ordering by events only -- the host never blocks here).
+extern "C" int pbd_step_host_async(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    if (e->n == 0) return pbd_step(e, nSteps);
+    const size_t bytes = (size_t)e->n * 3 * sizeof(float);
+    auto &P = e->pipe;
+    if (!P.ready) {
+        CK(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; s++)
+            for (cudaEvent_t *ev : {&P.uploaded[s], &P.consumed[s], &P.produced[s], &P.downloaded[s]}) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        P.ready = true;
+    }
+    const int s = (int)(P.issued & 1);
+    const bool reuse = P.issued >= 2;  // the slot was used by call k-2: its consumers are ordered before us by events
+    const unsigned *slot = (const unsigned *)e->dSlot.p;
+    if (x_in || v_in) {
+        if (reuse) CK(cudaStreamWaitEvent(P.up, P.consumed[s], 0));
+        if (x_in) { CKE(P.inX[s].alloc(bytes)); CK(cudaMemcpyAsync(P.inX[s].p, x_in, bytes, cudaMemcpyHostToDevice, P.up)); }
+        if (v_in) { CKE(P.inV[s].alloc(bytes)); CK(cudaMemcpyAsync(P.inV[s].p, v_in, bytes, cudaMemcpyHostToDevice, P.up)); }
+        CK(cudaEventRecord(P.uploaded[s], P.up));
+        CK(cudaStreamWaitEvent(e->stream, P.uploaded[s], 0));
+        if (x_in) k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)P.inX[s].p, (float4 *)e->pos.p, e->n, 1, slot);
+        if (v_in) k_pack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float *)P.inV[s].p, (float4 *)e->vel.p, e->n, 1, slot);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(P.consumed[s], e->stream));
+    CKE(pbd_step(e, nSteps));
+    if (x_out || v_out) {
+        if (reuse) CK(cudaStreamWaitEvent(e->stream, P.downloaded[s], 0));
+        if (x_out) { CKE(P.outX[s].alloc(bytes)); k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->pos.p, (float *)P.outX[s].p, e->n, slot); }
+        if (v_out) { CKE(P.outV[s].alloc(bytes)); k_unpack3<<<nblk(e->n, 256), 256, 0, e->stream>>>((const float4 *)e->vel.p, (float *)P.outV[s].p, e->n, slot); }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(P.produced[s], e->stream));
+        CK(cudaStreamWaitEvent(P.down, P.produced[s], 0));
+        if (x_out) CK(cudaMemcpyAsync(x_out, P.outX[s].p, bytes, cudaMemcpyDeviceToHost, P.down));
+        if (v_out) CK(cudaMemcpyAsync(v_out, P.outV[s].p, bytes, cudaMemcpyDeviceToHost, P.down));
+    }
+    CK(cudaEventRecord(P.downloaded[s], P.down));
+    P.issued++;
+    return 0;
+}
+
+extern "C" int pbd_step_host_wait(pbd_engine *e, unsigned lag) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    auto &P = e->pipe;
+    if (!P.ready || P.issued == 0) return 0;
+    if (lag > 1) return fail("pbd_step_host_wait: lag %u (the pipeline has two slots: 0 = everything, 1 = all but the newest call)", lag);
+    if (lag == 0) {
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaStreamSynchronize(P.down));
+        return 0;
+    }
+    if (P.issued < 2) return 0;
+    CK(cudaEventSynchronize(P.downloaded[(P.issued - 2) & 1]));
     return 0;
 }
 
