@@ -657,6 +657,23 @@ struct ResidentPlan {
 
 static bool is_rb_body(int type, int k) { return type == PBD_BALLJOINT || (type == PBD_RB_PARTICLE_BALLJOINT && k == 0); }
 
+// Executing tile of a constraint: the tile that holds most of its shared-memory particles (ties: the lowest tile); none -> the tile of
+// its first particle (0 for a joint between rigid bodies).  *touchesGlobal: one of its particles is global-homed.
+static inline unsigned exec_tile(int t, const unsigned *b, int nb, const std::vector<unsigned> &tileOf, const std::vector<unsigned char> &homedGlobal, bool *touchesGlobal) {
+    bool x = false;
+    unsigned best = 0xffffffffu, bestCnt = 0, first = 0xffffffffu;
+    for (int k = 0; k < nb; k++) {
+        if (is_rb_body(t, k)) continue;
+        if (first == 0xffffffffu) first = tileOf[b[k]];
+        if (homedGlobal[b[k]]) { x = true; continue; }
+        unsigned cnt = 0;
+        for (int j = 0; j < nb; j++) cnt += (!is_rb_body(t, j) && !homedGlobal[b[j]] && tileOf[b[j]] == tileOf[b[k]]);
+        if (cnt > bestCnt || (cnt == bestCnt && tileOf[b[k]] < best)) { best = tileOf[b[k]]; bestCnt = cnt; }
+    }
+    *touchesGlobal = x;
+    return (best != 0xffffffffu) ? best : (first != 0xffffffffu ? first : 0u);
+}
+
 // the compiled instantiations of k_step_resident: F(kernel pointer) for the engine's (mask, block size, one CTA per cluster?)
 template <class F> static int with_resident_kernel(const pbd_engine *e, unsigned C, F &&f) {
     const unsigned th = e->resThreads;
@@ -928,17 +945,7 @@ static int flatten_image(pbd_engine *e) {
                     unsigned long long major = 0;
                     if (tiled) {
                         bool x = false;
-                        unsigned best = 0xffffffffu, bestCnt = 0, first = 0xffffffffu;
-                        for (int k = 0; k < nb; k++) {
-                            if (is_rb_body(t, k)) continue;
-                            if (first == 0xffffffffu) first = tileOf[b[k]];
-                            if (pl.homedGlobal[b[k]]) { x = true; continue; }
-                            unsigned cnt = 0;
-                            for (int j = 0; j < nb; j++) cnt += (!is_rb_body(t, j) && !pl.homedGlobal[b[j]] && tileOf[b[j]] == tileOf[b[k]]);
-                            if (cnt > bestCnt || (cnt == bestCnt && tileOf[b[k]] < best)) { best = tileOf[b[k]]; bestCnt = cnt; }
-                        }
-                        // executing tile: the one that holds most of the constraint's shared-memory particles; none -> tile of its first particle
-                        const unsigned exec = (best != 0xffffffffu) ? best : (first != 0xffffffffu ? first : 0u);
+                        const unsigned exec = exec_tile(t, b, nb, tileOf, pl.homedGlobal, &x);
                         major = 2ull * exec + (x ? 0u : 1u);
                     }
                     keyed[i] = std::make_pair((major << 32) | mn, tmp[t][i]);
@@ -971,14 +978,19 @@ static int flatten_image(pbd_engine *e) {
             for (; bi < e->buckets.size() && e->buckets[bi].colour == g; bi++) {
                 const Bucket &b = e->buckets[bi];
                 const int nb = type_shape(b.type).nBodies;
-                for (unsigned i = 0; i < b.count; i++) {
+                long long bad = -1;  // items of a bucket in parallel: the stamp of a slot is exchanged atomically
+                #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : bad) if (b.count > 20000)
+                for (long long i = 0; i < (long long)b.count; i++) {
                     const unsigned *bd = &e->host[b.type].bodies[(size_t)order[b.type][b.first + i] * nb];
                     for (int k = 0; k < nb; k++) {
                         const bool isRb = (b.type == PBD_BALLJOINT) || (b.type == PBD_RB_PARTICLE_BALLJOINT && k == 0);
                         const size_t slot = isRb ? (size_t)e->n + bd[k] : bd[k];
-                        if (stamp[slot] == g) return fail("colour group %u uses %s %u twice: the groups are not a valid colouring", g, isRb ? "rigid body" : "particle", bd[k]);
-                        stamp[slot] = g;
+                        if (__atomic_exchange_n(&stamp[slot], g, __ATOMIC_RELAXED) == g) bad = std::max(bad, (long long)slot);
                     }
+                }
+                if (bad >= 0) {
+                    const bool isRb = (size_t)bad >= e->n;
+                    return fail("colour group %u uses %s %u twice: the groups are not a valid colouring", g, isRb ? "rigid body" : "particle", (unsigned)(isRb ? bad - e->n : bad));
                 }
             }
         }

@@ -127,11 +127,11 @@ def test_translation_invariance_large_cloth():
 
 
 def test_modes_and_layouts_agree_at_scale():
-    """Graph, resident (one cluster and several clusters with X items) and plain-launch execution of a 300x300 XPBD cloth
-    (540k constraints): bit-identical."""
+    """Graph, resident (default shape: one CTA per SM with X items through global memory; one cluster of 8 / 16 CTAs with early and
+    late items over DSMEM; 37 independent CTAs) and plain-launch execution of a 300x300 XPBD cloth (540k constraints): bit-identical."""
     import os
     out = []
-    for mode, clusters in ((0, None), (1, None), (2, None), (1, "4x4"), (1, "3x8")):
+    for mode, clusters in ((0, None), (1, None), (2, None), (1, "1x8"), (1, "1x16"), (1, "37x1")):
         if clusters: os.environ["PBD_B200_CLUSTERS"] = clusters
         try:
             gpu = _gpu(lambda m: scenes.cfg2(m, 300, 8), mode)
@@ -144,8 +144,8 @@ def test_modes_and_layouts_agree_at_scale():
 
 
 def test_resident_mode_full_size_cfg2_bitwise():
-    """cfg2 at full size in the resident mode: 8 clusters x 16 CTAs, ~7,800 particles per tile in shared memory, ~1 % of the
-    particles global-homed with their constraints ordered across clusters by the X counter.  Must reproduce the graph mode bit
+    """cfg2 at full size in the resident mode: one CTA per SM, ~6,300 particles per tile in shared memory, ~7 % of the
+    particles global-homed with their constraints ordered across the CTAs by the X counter.  Must reproduce the graph mode bit
     for bit, positions and velocities."""
     res = []
     for mode in (0, 1):
