@@ -146,6 +146,39 @@ int pbd_step_host(pbd_engine *e, unsigned nSteps, const float *x_in, const float
 int pbd_step_host_async(pbd_engine *e, unsigned nSteps, const float *x_in, const float *v_in, float *x_out, float *v_out);
 int pbd_step_host_wait(pbd_engine *e, unsigned lag);
 
+/* ---- Contact path (its data-parallel part) ----------------------------------------------------
+ * Particles of triangle / tet models against analytic distance fields carried by STATIC rigid bodies, and the velocity-level
+ * contact solve: DistanceFieldCollisionDetection::collisionDetection + collisionDetectionRBSolid
+ * (Simulation/DistanceFieldCollisionDetection.cpp:26-197, 290-357; distance functions :598-728), TimeStep::contactCallbackFunction ->
+ * SimulationModel::addParticleRigidBodyContactConstraint (Simulation/SimulationModel.cpp:538-549),
+ * ParticleRigidBodyContactConstraint (Simulation/Constraints.cpp:2115-2186) and TimeStepController::velocityConstraintProjection
+ * (Simulation/TimeStepController.cpp:189-196, 298-357).  Runs once per pbd_step after the substeps, as in the reference.
+ * A collider on a rigid body with mass != 0 is refused (its contacts couple through the body and are inherently sequential);
+ * rigid-rigid and particle-tet contacts are not covered -- such models stay on the reference's CPU time step.
+ *   pbd_particle_collider: one DistanceFieldCollisionObjectWithoutGeometry (particles [offset, offset+count) of a model, the
+ *                          model's restitution / friction coefficients);
+ *   pbd_rigid_collider:    one DistanceFieldCollision{Box,Sphere,Torus,Cylinder,HollowSphere,HollowBox} in the order of
+ *                          CollisionDetection::getCollisionObjects(): `dim` = m_box (half extents) | m_radius | m_radii | m_dim
+ *                          (radius, half height), m_thickness, m_invertSDF, the body's coefficients, RigidBody::getTransformationR
+ *                          (row-major) / V1 / V2 and the object's m_aabb (after updateAABB, i.e. extended by the tolerance). */
+enum pbd_collider_shape { PBD_SHAPE_BOX = 0, PBD_SHAPE_SPHERE = 1, PBD_SHAPE_TORUS = 2, PBD_SHAPE_CYLINDER = 3, PBD_SHAPE_HOLLOW_SPHERE = 4, PBD_SHAPE_HOLLOW_BOX = 5 };
+typedef struct pbd_particle_collider { unsigned offset, count; float restitution, friction; } pbd_particle_collider;
+typedef struct pbd_rigid_collider {
+    int shape; unsigned body;
+    float dim[3], thickness; int invert_sdf;
+    float restitution, friction;
+    float R[9], v1[3], v2[3];
+    float aabb_min[3], aabb_max[3];
+} pbd_rigid_collider;
+typedef struct pbd_contact { unsigned particle, body; float cp0[3], cp1[3], normal[3], dist; } pbd_contact;
+int pbd_set_colliders(pbd_engine *e, unsigned nParticleColliders, const pbd_particle_collider *pc, unsigned nRigidColliders, const pbd_rigid_collider *rc);
+/* CollisionDetection::m_tolerance, SimulationModel::m_contactStiffnessParticleRigidBody, TimeStepController::m_maxIterationsV */
+int pbd_set_contact_params(pbd_engine *e, float tolerance, float stiffness, unsigned maxIterationsV);
+/* debug / rendering: keep the contacts of every step (up to `capacity`); pbd_get_contacts returns those of the last step sorted by
+ * (particle, body) and the number found (which may exceed what was kept) */
+int pbd_record_contacts(pbd_engine *e, unsigned capacity);
+int pbd_get_contacts(pbd_engine *e, pbd_contact *out, unsigned capacity, unsigned *count);
+
 int pbd_get_lambdas(pbd_engine *e, int type, float *dst, unsigned *ids); /* debug: per-type XPBD multipliers + insertion ids */
 int pbd_get_stats(pbd_engine *e, pbd_stats *out);
 /* per-type device time of one profiled step (plain launches bracketed by CUDA events; ms per type + prologue/epilogue) */

@@ -21,7 +21,9 @@
 #include "Simulation/RigidBody.h"
 #include "Simulation/TimeManager.h"
 #include "Simulation/Simulation.h"
+#include "Simulation/DistanceFieldCollisionDetection.h"
 #include "pbd_b200.h"
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -76,13 +78,19 @@ public:
     void step(SimulationModel &model) override {
         if (!m_engine) return;
         // The contact path (TimeStepController.cpp:189-196: collision detection, then velocityConstraintProjection over the contact
-        // constraints, :298-357) is not on the GPU path: refuse such a model instead of silently simulating it without contacts.
-        if ((m_collisionDetection && !m_collisionDetection->getCollisionObjects().empty()) || !model.getRigidBodyContactConstraints().empty() ||
-            !model.getParticleRigidBodyContactConstraints().empty() || !model.getParticleSolidContactConstraints().empty()) {
-            m_error = "GpuTimeStepController: the model has collision objects / contact constraints; the contact path "
-                      "(TimeStepController.cpp:189-196, 298-357) runs on the CPU TimeStepController only";
+        // constraints, :298-357).  On the GPU: particles of triangle / tet models against analytic distance fields on static rigid
+        // bodies (collectColliders below); anything else -- dynamic bodies in contact, rigid-rigid or particle-tet contacts, another
+        // CollisionDetection class, hand-made contact constraints -- is refused instead of being simulated without its contacts.
+        const bool haveObjects = m_collisionDetection && !m_collisionDetection->getCollisionObjects().empty();
+        if (!haveObjects && (!model.getRigidBodyContactConstraints().empty() || !model.getParticleRigidBodyContactConstraints().empty() ||
+                             !model.getParticleSolidContactConstraints().empty())) {
+            m_error = "GpuTimeStepController: the model holds contact constraints but no collision detection that produces them; the "
+                      "contact path of such a model (TimeStepController.cpp:298-357) runs on the CPU TimeStepController only";
             return;
         }
+        std::vector<pbd_particle_collider> pcs;
+        std::vector<pbd_rigid_collider> rcs;
+        if (haveObjects && !collectColliders(model, pcs, rcs)) return;  // m_error says why
         m_error.clear();  // lastError() describes the current step
         ParticleData &pd = model.getParticles();
         SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
@@ -99,6 +107,17 @@ public:
         const Vector3r g(Simulation::getCurrent()->getVecValue<Real>(Simulation::GRAVITATION));
         const float grav[3] = {(float)g[0], (float)g[1], (float)g[2]};
         if (pbd_set_params(m_engine, (float)tm->getTimeStepSize(), m_subSteps, m_maxIterations, m_velocityUpdateMethod, grav)) return fail();
+        if (haveObjects || m_hadColliders) {
+            if (!sameColliders(pcs, rcs)) {
+                if (pbd_set_colliders(m_engine, (unsigned)pcs.size(), pcs.data(), (unsigned)rcs.size(), rcs.data())) return fail();
+                m_pcs = pcs; m_rcs = rcs;
+            }
+            m_hadColliders = haveObjects;
+            if (haveObjects) {
+                if (pbd_set_contact_params(m_engine, (float)m_collisionDetection->getTolerance(), (float)model.getContactStiffnessParticleRigidBody(), m_maxIterationsV)) return fail();
+                model.resetContacts();  // DistanceFieldCollisionDetection::collisionDetection starts with this; the contacts of the step live on the device
+            }
+        }
         // rigid bodies: uploaded at bind time, device state is authoritative afterwards (their history feeds the second-order
         // velocity update); particles: x and v come from the host every step, so user edits between steps are honoured
         if (sizeof(Real) == sizeof(float) && n) {
@@ -136,6 +155,65 @@ protected:
     float *m_pinnedX = nullptr, *m_pinnedV = nullptr;
     bool m_pinFailed = false, m_checkMasses = true, m_hostAuthoritative = true, m_stateInvalid = true;
     std::vector<float> m_signature;
+    std::vector<pbd_particle_collider> m_pcs;
+    std::vector<pbd_rigid_collider> m_rcs;
+    bool m_hadColliders = false;
+
+    bool sameColliders(const std::vector<pbd_particle_collider> &p, const std::vector<pbd_rigid_collider> &r) const {
+        return p.size() == m_pcs.size() && r.size() == m_rcs.size() &&
+               (p.empty() || std::memcmp(p.data(), m_pcs.data(), p.size() * sizeof(p[0])) == 0) &&
+               (r.empty() || std::memcmp(r.data(), m_rcs.data(), r.size() * sizeof(r[0])) == 0);
+    }
+    // The collision objects of the attached DistanceFieldCollisionDetection in the layout of pbd_set_colliders, following the pair
+    // dispatch of DistanceFieldCollisionDetection::collisionDetection (DistanceFieldCollisionDetection.cpp:96-165): a pair produces
+    // contacts when co1 has m_testMesh and co2 is a rigid body or a tet model, both being distance-field objects.
+    bool collectColliders(SimulationModel &model, std::vector<pbd_particle_collider> &pcs, std::vector<pbd_rigid_collider> &rcs) {
+        typedef DistanceFieldCollisionDetection D;
+        D *cd = dynamic_cast<D *>(m_collisionDetection);
+        if (!cd) { m_error = "GpuTimeStepController: the attached collision detection is not a DistanceFieldCollisionDetection; its contact path runs on the CPU TimeStepController only"; return false; }
+        SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
+        unsigned tetObjects = 0;
+        for (CollisionDetection::CollisionObject *co : cd->getCollisionObjects()) {
+            if (!cd->isDistanceFieldCollisionObject(co)) continue;  // the reference skips every pair with such an object
+            D::DistanceFieldCollisionObject *dco = static_cast<D::DistanceFieldCollisionObject *>(co);
+            const int id = co->getTypeId();
+            if (co->m_bodyType == CollisionDetection::CollisionObject::TriangleModelCollisionObjectType ||
+                co->m_bodyType == CollisionDetection::CollisionObject::TetModelCollisionObjectType) {
+                const bool tet = (co->m_bodyType == CollisionDetection::CollisionObject::TetModelCollisionObjectType);
+                if (tet && ++tetObjects > 1) { m_error = "GpuTimeStepController: two tet models as collision objects produce particle-tet contacts (collisionDetectionSolidSolid), which run on the CPU TimeStepController only"; return false; }
+                if (!dco->m_testMesh) continue;  // never a co1, and as co2 only a tet model matters (counted above)
+                pbd_particle_collider pc;
+                if (tet) { TetModel *tm = model.getTetModels()[co->m_bodyIndex]; pc.offset = tm->getIndexOffset(); pc.count = tm->getParticleMesh().numVertices();
+                           pc.restitution = (float)tm->getRestitutionCoeff(); pc.friction = (float)tm->getFrictionCoeff(); }
+                else { TriangleModel *tm = model.getTriangleModels()[co->m_bodyIndex]; pc.offset = tm->getIndexOffset(); pc.count = tm->getParticleMesh().numVertices();
+                       pc.restitution = (float)tm->getRestitutionCoeff(); pc.friction = (float)tm->getFrictionCoeff(); }
+                pcs.push_back(pc);
+                continue;
+            }
+            if (co->m_bodyType != CollisionDetection::CollisionObject::RigidBodyCollisionObjectType) continue;
+            pbd_rigid_collider rc;
+            std::memset(&rc, 0, sizeof(rc));
+            if (id == D::DistanceFieldCollisionBox::TYPE_ID) { rc.shape = PBD_SHAPE_BOX; auto *o = static_cast<D::DistanceFieldCollisionBox *>(co); for (int k = 0; k < 3; k++) rc.dim[k] = (float)o->m_box[k]; }
+            else if (id == D::DistanceFieldCollisionSphere::TYPE_ID) { rc.shape = PBD_SHAPE_SPHERE; rc.dim[0] = (float)static_cast<D::DistanceFieldCollisionSphere *>(co)->m_radius; }
+            else if (id == D::DistanceFieldCollisionTorus::TYPE_ID) { rc.shape = PBD_SHAPE_TORUS; auto *o = static_cast<D::DistanceFieldCollisionTorus *>(co); rc.dim[0] = (float)o->m_radii[0]; rc.dim[1] = (float)o->m_radii[1]; }
+            else if (id == D::DistanceFieldCollisionCylinder::TYPE_ID) { rc.shape = PBD_SHAPE_CYLINDER; auto *o = static_cast<D::DistanceFieldCollisionCylinder *>(co); rc.dim[0] = (float)o->m_dim[0]; rc.dim[1] = (float)o->m_dim[1]; }
+            else if (id == D::DistanceFieldCollisionHollowSphere::TYPE_ID) { rc.shape = PBD_SHAPE_HOLLOW_SPHERE; auto *o = static_cast<D::DistanceFieldCollisionHollowSphere *>(co); rc.dim[0] = (float)o->m_radius; rc.thickness = (float)o->m_thickness; }
+            else if (id == D::DistanceFieldCollisionHollowBox::TYPE_ID) { rc.shape = PBD_SHAPE_HOLLOW_BOX; auto *o = static_cast<D::DistanceFieldCollisionHollowBox *>(co); for (int k = 0; k < 3; k++) rc.dim[k] = (float)o->m_box[k]; rc.thickness = (float)o->m_thickness; }
+            else continue;  // a rigid body without geometry: never a co2 that produces contacts
+            RigidBody *rb = rbs[co->m_bodyIndex];
+            if (rb->getMass() != 0.0) { m_error = "GpuTimeStepController: rigid body " + std::to_string(co->m_bodyIndex) + " is a dynamic collision object; contacts with dynamic bodies (and rigid-rigid contacts) run on the CPU TimeStepController only"; return false; }
+            if (dco->m_invertSDF < 0) { m_error = "GpuTimeStepController: collision object with an inverted distance field; its candidate pruning is specific to the reference's bounding-sphere hierarchy (CPU TimeStepController only)"; return false; }
+            rc.body = co->m_bodyIndex; rc.invert_sdf = 0;
+            rc.restitution = (float)rb->getRestitutionCoeff(); rc.friction = (float)rb->getFrictionCoeff();
+            const Matrix3r &R = rb->getTransformationR();
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rc.R[3 * r + c] = (float)R(r, c);
+            for (int k = 0; k < 3; k++) { rc.v1[k] = (float)rb->getTransformationV1()[k]; rc.v2[k] = (float)rb->getTransformationV2()[k]; }
+            cd->updateAABB(model, co);  // what collisionDetection does first (DistanceFieldCollisionDetection.cpp:63)
+            for (int k = 0; k < 3; k++) { rc.aabb_min[k] = (float)co->m_aabb.m_p[0][k]; rc.aabb_max[k] = (float)co->m_aabb.m_p[1][k]; }
+            rcs.push_back(rc);
+        }
+        return true;
+    }
 
     // values of the first and the last constraint of the model plus one in the middle, per call: O(1)
     static void appendConstraintValues(Constraint *c, std::vector<float> &sig) {
@@ -208,7 +286,7 @@ protected:
         static_cast<GenParam::NumericParameter<unsigned int> *>(getParameter(MAX_ITERATIONS))->setMinValue(1);
         MAX_ITERATIONS_V = createNumericParameter("maxIterationsV", "Max. velocity iterations", &m_maxIterationsV);
         setGroup(MAX_ITERATIONS_V, "Simulation|PBD");
-        setDescription(MAX_ITERATIONS_V, "Maximal number of iterations of the velocity solver (contacts: not on the GPU path).");
+        setDescription(MAX_ITERATIONS_V, "Maximal number of iterations of the velocity solver (particle / static-body contacts).");
         VELOCITY_UPDATE_METHOD = createEnumParameter("velocityUpdateMethod", "Velocity update method", &m_velocityUpdateMethod);
         setGroup(VELOCITY_UPDATE_METHOD, "Simulation|PBD");
         setDescription(VELOCITY_UPDATE_METHOD, "Velocity method.");

@@ -144,6 +144,49 @@ class CpuPbd:
         out = np.zeros(11); self.lib.ref_get_rigid_body_props(i, _dp(out))
         return i, out
 
+    # -- contact path (reference builds only): DistanceFieldCollisionDetection as Demos/DistanceFieldDemos/ClothCollisionDemo.cpp sets it up
+    def use_distance_field_cd(self, tolerance=0.01):
+        assert self.kind != "oracle"
+        self.lib.ref_use_distance_field_cd(_D(tolerance))
+
+    def set_rigid_body_mass(self, i, m):
+        self.lib.ref_set_rigid_body_mass(int(i), _D(m))
+
+    def add_rigid_collider(self, body, shape, dims, thickness=0.0, invert=False, restitution=0.6, friction=0.2):
+        """shape 0 box (full extents) | 1 sphere (radius) | 2 torus (radii) | 3 cylinder (radius, height) | 4 hollow sphere | 5 hollow box."""
+        d = np.zeros(3); d[:len(np.atleast_1d(dims))] = np.atleast_1d(dims)
+        rc = self.lib.ref_add_rigid_collider(int(body), int(shape), _dp(d), _D(thickness), int(bool(invert)), _D(restitution), _D(friction))
+        assert rc == 0, rc
+
+    def add_model_collider(self, kind, model_index, restitution=0.6, friction=0.2):
+        """kind 0: triangle model, 1: tet model (addCollisionObjectWithoutGeometry, testMesh = true)."""
+        assert self.lib.ref_add_model_collider(int(kind), int(model_index), _D(restitution), _D(friction)) == 0
+
+    def set_contact_params(self, stiffness=100.0, max_iter_v=5):
+        self.lib.ref_set_contact_params(_D(stiffness), int(max_iter_v))
+
+    def contacts(self):
+        """Particle / rigid-body contacts of the last step: (particle[n], body[n], info[n, 10] = cp0 | cp1 | normal | 1/(n^T K n)), plus the
+        counts of the contact kinds the GPU path does not cover (rigid-rigid, particle-tet)."""
+        rr = C.c_uint(0); pt = C.c_uint(0)
+        self.lib.ref_num_contacts.restype = C.c_uint
+        n = self.lib.ref_num_contacts(C.byref(rr), C.byref(pt))
+        particle = np.zeros(max(n, 1), dtype=np.uint32); body = np.zeros(max(n, 1), dtype=np.uint32); info = np.zeros((max(n, 1), 10))
+        self.lib.ref_get_contacts(particle.ctypes.data_as(C.c_void_p), body.ctypes.data_as(C.c_void_p), _dp(info))
+        return particle[:n], body[:n], info[:n], rr.value, pt.value
+
+    def collision_objects(self):
+        """What an adapter passes to pbd_set_colliders: ([(offset, count, restitution, friction)], [30 doubles per rigid collider]) in list order."""
+        self.lib.ref_num_collision_objects.restype = C.c_uint
+        models, rigid = [], []
+        for i in range(self.lib.ref_num_collision_objects()):
+            out = np.zeros(32)
+            kind = self.lib.ref_collision_object_info(i, _dp(out))
+            if kind == 0: rigid.append(out[:30].copy())
+            elif kind in (1, 2): models.append((int(out[0]), int(out[1]), float(out[2]), float(out[3])))
+            else: raise RuntimeError("collision object %d is of a kind the contact path does not cover" % i)
+        return models, rigid
+
     def add_ball_joint(self, rb0, rb1, pos):
         return self.add_constraint(BALLJOINT, [rb0, rb1], list(pos))
 

@@ -15,6 +15,7 @@
 #include "Simulation/TimeStepController.h"
 #include "Simulation/Constraints.h"
 #include "Simulation/RigidBody.h"
+#include "Simulation/DistanceFieldCollisionDetection.h"
 #include "Utils/IndexedFaceMesh.h"
 #include "PositionBasedDynamics/PositionBasedDynamics.h"
 #include "PositionBasedDynamics/XPBD.h"
@@ -46,6 +47,7 @@ enum { T_DISTANCE = 0, T_DISTANCE_XPBD, T_DIHEDRAL, T_ISOBENDING, T_ISOBENDING_X
        T_BALLJOINT, T_RB_PARTICLE_BALLJOINT, T_UNKNOWN = -1 };
 
 static SimulationModel *g_model = nullptr;
+static DistanceFieldCollisionDetection *g_cd = nullptr;  // the reference's collision detection, attached to whichever time step is installed
 #ifdef PBD_WITH_GPU_ADAPTER
 static GpuTimeStepController *g_gpuTs = nullptr;  // owned by Simulation once installed
 static std::string g_gpuErr;
@@ -82,6 +84,7 @@ void ref_reset() {
         if (g_model) { g_model->cleanup(); delete g_model; g_model = nullptr; }
         delete s;  // deletes TimeStep and TimeManager (Simulation.cpp:22-28)
         TimeManager::setCurrent(nullptr);
+        delete g_cd; g_cd = nullptr;
 #ifdef PBD_WITH_GPU_ADAPTER
         g_gpuTs = nullptr;
 #endif
@@ -366,6 +369,114 @@ double ref_time() { return TimeManager::getCurrent()->getTime(); }
 // m_groupsInitialized -- what a GPU time step has to notice on its own
 void ref_set_cloth_stiffness(double k) { g_model->setClothStiffness((Real)k); }
 
+// ---------------------------------------------------------------------------------------------
+// Contact path: the reference's DistanceFieldCollisionDetection set up the way Demos/DistanceFieldDemos/ClothCollisionDemo.cpp:120-182
+// does -- static rigid bodies with analytic distance fields, triangle / tet models as point clouds.
+// ---------------------------------------------------------------------------------------------
+void ref_use_distance_field_cd(double tolerance) {
+    if (!g_cd) { g_cd = new DistanceFieldCollisionDetection(); g_cd->init(); }
+    Simulation::getCurrent()->getTimeStep()->setCollisionDetection(*g_model, g_cd);
+    g_cd->setTolerance((Real)tolerance);
+}
+void ref_set_rigid_body_mass(unsigned i, double m) { g_model->getRigidBodies()[i]->setMass((Real)m); }
+// shape: 0 box (dims = full extents), 1 sphere (radius), 2 torus (radii), 3 cylinder (radius, height), 4 hollow sphere (radius; thickness),
+// 5 hollow box (full extents; thickness) -- the arguments of DistanceFieldCollisionDetection::addCollision* (:498-582)
+int ref_add_rigid_collider(unsigned body, int shape, const double *dims, double thickness, int invert, double restitution, double friction) {
+    if (!g_cd) return 1;
+    RigidBody *rb = g_model->getRigidBodies()[body];
+    rb->setRestitutionCoeff((Real)restitution); rb->setFrictionCoeff((Real)friction);
+    const std::vector<Vector3r> &v = rb->getGeometry().getVertexDataLocal().getVertices();
+    const unsigned nv = (unsigned)v.size();
+    const unsigned type = CollisionDetection::CollisionObject::RigidBodyCollisionObjectType;
+    switch (shape) {
+    case 0: g_cd->addCollisionBox(body, type, v.data(), nv, v3(dims), true, invert != 0); break;
+    case 1: g_cd->addCollisionSphere(body, type, v.data(), nv, (Real)dims[0], true, invert != 0); break;
+    case 2: g_cd->addCollisionTorus(body, type, v.data(), nv, Vector2r((Real)dims[0], (Real)dims[1]), true, invert != 0); break;
+    case 3: g_cd->addCollisionCylinder(body, type, v.data(), nv, Vector2r((Real)dims[0], (Real)dims[1]), true, invert != 0); break;
+    case 4: g_cd->addCollisionHollowSphere(body, type, v.data(), nv, (Real)dims[0], (Real)thickness, true, invert != 0); break;
+    case 5: g_cd->addCollisionHollowBox(body, type, v.data(), nv, v3(dims), (Real)thickness, true, invert != 0); break;
+    default: return 2;
+    }
+    return 0;
+}
+// kind 0: triangle model, 1: tet model
+int ref_add_model_collider(int kind, unsigned modelIndex, double restitution, double friction) {
+    if (!g_cd) return 1;
+    ParticleData &pd = g_model->getParticles();
+    if (kind == 0) {
+        TriangleModel *tm = g_model->getTriangleModels()[modelIndex];
+        tm->setRestitutionCoeff((Real)restitution); tm->setFrictionCoeff((Real)friction);
+        g_cd->addCollisionObjectWithoutGeometry(modelIndex, CollisionDetection::CollisionObject::TriangleModelCollisionObjectType,
+                                                &pd.getPosition(tm->getIndexOffset()), tm->getParticleMesh().numVertices(), true);
+    } else {
+        TetModel *tm = g_model->getTetModels()[modelIndex];
+        tm->setRestitutionCoeff((Real)restitution); tm->setFrictionCoeff((Real)friction);
+        g_cd->addCollisionObjectWithoutGeometry(modelIndex, CollisionDetection::CollisionObject::TetModelCollisionObjectType,
+                                                &pd.getPosition(tm->getIndexOffset()), tm->getParticleMesh().numVertices(), true);
+    }
+    return 0;
+}
+void ref_set_contact_params(double stiffnessParticleRigidBody, unsigned maxIterV) {
+    g_model->setContactStiffnessParticleRigidBody((Real)stiffnessParticleRigidBody);
+    TimeStep *ts = Simulation::getCurrent()->getTimeStep();
+    ts->setValue<unsigned int>(TimeStepController::MAX_ITERATIONS_V, maxIterV);
+}
+// the contact list of the last step (SimulationModel::getParticleRigidBodyContactConstraints); out: 10 doubles per contact = cp0 | cp1 | n | 1/(n^T K n)
+unsigned ref_num_contacts(unsigned *rigidRigid, unsigned *particleTet) {
+    if (rigidRigid) *rigidRigid = (unsigned)g_model->getRigidBodyContactConstraints().size();
+    if (particleTet) *particleTet = (unsigned)g_model->getParticleSolidContactConstraints().size();
+    return (unsigned)g_model->getParticleRigidBodyContactConstraints().size();
+}
+void ref_get_contacts(unsigned *particle, unsigned *body, double *out) {
+    auto &cs = g_model->getParticleRigidBodyContactConstraints();
+    for (size_t i = 0; i < cs.size(); i++) {
+        particle[i] = cs[i].m_bodies[0]; body[i] = cs[i].m_bodies[1];
+        for (int col = 0; col < 3; col++) for (int k = 0; k < 3; k++) out[10 * i + 3 * col + k] = (double)cs[i].m_constraintInfo(k, col);
+        out[10 * i + 9] = (double)cs[i].m_constraintInfo(0, 4);
+    }
+}
+// what an adapter hands to pbd_set_colliders for collision object i: returns its kind (0 rigid analytic, 1 triangle model, 2 tet model,
+// -1 other); out (rigid): shape, body, dim[3], thickness, invert, restitution, friction, R[9] row-major, v1[3], v2[3], aabbMin[3], aabbMax[3]
+// = 30 doubles; out (model): offset, count, restitution, friction
+unsigned ref_num_collision_objects() { return g_cd ? (unsigned)g_cd->getCollisionObjects().size() : 0u; }
+int ref_collision_object_info(unsigned i, double *out) {
+    typedef DistanceFieldCollisionDetection D;
+    CollisionDetection::CollisionObject *co = g_cd->getCollisionObjects()[i];
+    g_cd->updateAABB(*g_model, co);
+    if (co->m_bodyType == CollisionDetection::CollisionObject::TriangleModelCollisionObjectType) {
+        TriangleModel *tm = g_model->getTriangleModels()[co->m_bodyIndex];
+        out[0] = tm->getIndexOffset(); out[1] = tm->getParticleMesh().numVertices(); out[2] = tm->getRestitutionCoeff(); out[3] = tm->getFrictionCoeff();
+        return 1;
+    }
+    if (co->m_bodyType == CollisionDetection::CollisionObject::TetModelCollisionObjectType) {
+        TetModel *tm = g_model->getTetModels()[co->m_bodyIndex];
+        out[0] = tm->getIndexOffset(); out[1] = tm->getParticleMesh().numVertices(); out[2] = tm->getRestitutionCoeff(); out[3] = tm->getFrictionCoeff();
+        return 2;
+    }
+    if (co->m_bodyType != CollisionDetection::CollisionObject::RigidBodyCollisionObjectType) return -1;
+    int shape = -1; double dim[3] = {0, 0, 0}, thickness = 0;
+    const int id = co->getTypeId();
+    if (id == D::DistanceFieldCollisionBox::TYPE_ID) { shape = 0; auto *o = (D::DistanceFieldCollisionBox *)co; for (int k = 0; k < 3; k++) dim[k] = o->m_box[k]; }
+    else if (id == D::DistanceFieldCollisionSphere::TYPE_ID) { shape = 1; dim[0] = ((D::DistanceFieldCollisionSphere *)co)->m_radius; }
+    else if (id == D::DistanceFieldCollisionTorus::TYPE_ID) { shape = 2; auto *o = (D::DistanceFieldCollisionTorus *)co; dim[0] = o->m_radii[0]; dim[1] = o->m_radii[1]; }
+    else if (id == D::DistanceFieldCollisionCylinder::TYPE_ID) { shape = 3; auto *o = (D::DistanceFieldCollisionCylinder *)co; dim[0] = o->m_dim[0]; dim[1] = o->m_dim[1]; }
+    else if (id == D::DistanceFieldCollisionHollowSphere::TYPE_ID) { shape = 4; auto *o = (D::DistanceFieldCollisionHollowSphere *)co; dim[0] = o->m_radius; thickness = o->m_thickness; }
+    else if (id == D::DistanceFieldCollisionHollowBox::TYPE_ID) { shape = 5; auto *o = (D::DistanceFieldCollisionHollowBox *)co; for (int k = 0; k < 3; k++) dim[k] = o->m_box[k]; thickness = o->m_thickness; }
+    else return -1;
+    RigidBody *rb = g_model->getRigidBodies()[co->m_bodyIndex];
+    auto *dco = (D::DistanceFieldCollisionObject *)co;
+    int n = 0;
+    out[n++] = shape; out[n++] = co->m_bodyIndex; for (int k = 0; k < 3; k++) out[n++] = dim[k];
+    out[n++] = thickness; out[n++] = (dco->m_invertSDF < 0) ? 1 : 0; out[n++] = rb->getRestitutionCoeff(); out[n++] = rb->getFrictionCoeff();
+    const Matrix3r &R = rb->getTransformationR();
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) out[n++] = R(r, c);
+    for (int k = 0; k < 3; k++) out[n++] = rb->getTransformationV1()[k];
+    for (int k = 0; k < 3; k++) out[n++] = rb->getTransformationV2()[k];
+    for (int k = 0; k < 3; k++) out[n++] = co->m_aabb.m_p[0][k];
+    for (int k = 0; k < 3; k++) out[n++] = co->m_aabb.m_p[1][k];
+    return 0;
+}
+
 #ifdef PBD_WITH_GPU_ADAPTER
 // Install the GPU time step the way a user of the reference would (Simulation.h:48-49), carrying over the solver parameters.
 // mode: PBD_MODE_* of include/pbd_b200.h.  Returns 0 on success.
@@ -384,6 +495,7 @@ int ref_use_gpu_timestep(int device, int mode) {
     ts->setValue<int>(GpuTimeStepController::VELOCITY_UPDATE_METHOD, velMethod);
     delete old;
     sim->setTimeStep(ts);
+    if (g_cd) ts->setCollisionDetection(*g_model, g_cd);  // what the user of the reference does after installing a time step
     g_gpuTs = ts;
     g_gpuErr.clear();
     return 0;

@@ -24,7 +24,25 @@ SYMBOLS = ["pbd_last_error", "pbd_device_count", "pbd_create", "pbd_destroy", "p
            "pbd_get_attr", "pbd_set_masses", "pbd_set_rigid_bodies", "pbd_get_rigid_bodies", "pbd_clear_constraints", "pbd_add_constraints", "pbd_num_bodies",
            "pbd_num_params", "pbd_set_groups", "pbd_color_first_fit", "pbd_color_first_fit_device", "pbd_pin_host", "pbd_unpin_host", "pbd_get_num_groups", "pbd_get_groups",
            "pbd_set_params", "pbd_set_mode", "pbd_get_mode", "pbd_set_bucket_sort", "pbd_step", "pbd_sync", "pbd_step_host", "pbd_step_host_async", "pbd_step_host_wait",
-           "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step"]
+           "pbd_get_lambdas", "pbd_get_stats", "pbd_profile_step",
+           "pbd_set_colliders", "pbd_set_contact_params", "pbd_record_contacts", "pbd_get_contacts"]
+
+
+SHAPE_BOX, SHAPE_SPHERE, SHAPE_TORUS, SHAPE_CYLINDER, SHAPE_HOLLOW_SPHERE, SHAPE_HOLLOW_BOX = range(6)
+
+
+class ParticleCollider(C.Structure):
+    _fields_ = [("offset", C.c_uint), ("count", C.c_uint), ("restitution", C.c_float), ("friction", C.c_float)]
+
+
+class RigidCollider(C.Structure):
+    _fields_ = [("shape", C.c_int), ("body", C.c_uint), ("dim", C.c_float * 3), ("thickness", C.c_float), ("invert_sdf", C.c_int),
+                ("restitution", C.c_float), ("friction", C.c_float), ("R", C.c_float * 9), ("v1", C.c_float * 3), ("v2", C.c_float * 3),
+                ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3)]
+
+
+class Contact(C.Structure):
+    _fields_ = [("particle", C.c_uint), ("body", C.c_uint), ("cp0", C.c_float * 3), ("cp1", C.c_float * 3), ("normal", C.c_float * 3), ("dist", C.c_float)]
 
 
 class Stats(C.Structure):
@@ -76,6 +94,10 @@ def lib():
         _lib.pbd_step_host.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.pbd_step_host_async.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.pbd_step_host_wait.argtypes = [C.c_void_p, C.c_uint]
+        _lib.pbd_set_colliders.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p]
+        _lib.pbd_set_contact_params.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint]
+        _lib.pbd_record_contacts.argtypes = [C.c_void_p, C.c_uint]
+        _lib.pbd_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
         _lib.pbd_get_lambdas.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.pbd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         _lib.pbd_profile_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -244,6 +266,23 @@ class Engine:
 
     def step_host_wait(self, lag=0):
         _ck(lib().pbd_step_host_wait(self._h, int(lag)))
+
+    def set_colliders(self, particle_colliders, rigid_colliders):
+        """pbd_set_colliders: lists of ParticleCollider / RigidCollider (rigid ones in the order of the reference's collision object list)."""
+        pa = (ParticleCollider * max(len(particle_colliders), 1))(*particle_colliders)
+        ra = (RigidCollider * max(len(rigid_colliders), 1))(*rigid_colliders)
+        _ck(lib().pbd_set_colliders(self._h, len(particle_colliders), C.cast(pa, C.c_void_p), len(rigid_colliders), C.cast(ra, C.c_void_p)))
+
+    def set_contact_params(self, tolerance=0.01, stiffness=100.0, max_iter_v=5):
+        _ck(lib().pbd_set_contact_params(self._h, float(tolerance), float(stiffness), int(max_iter_v)))
+
+    def record_contacts(self, capacity):
+        _ck(lib().pbd_record_contacts(self._h, int(capacity)))
+
+    def contacts(self, capacity=1 << 16):
+        buf = (Contact * capacity)(); cnt = C.c_uint(0)
+        _ck(lib().pbd_get_contacts(self._h, C.cast(buf, C.c_void_p), capacity, C.byref(cnt)))
+        return [buf[i] for i in range(min(cnt.value, capacity))], cnt.value
 
     def lambdas(self, ctype):
         cnt = self.stats().constraints_per_type[ctype]

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "resident.cuh"
 #include "colouring.cuh"
+#include "contacts.cuh"
 #include <cub/cub.cuh>
 #include <omp.h>
 #include <parallel/algorithm>  // libstdc++ parallel mode (OpenMP): the per-bucket sorts of flatten
@@ -120,6 +121,13 @@ struct pbd_engine {
         unsigned long long issued = 0;
         bool ready = false;
     } pipe;
+    // contact path (contacts.cuh): colliders, parameters, optional record of the last step's contacts
+    std::vector<float> rbMass;
+    std::vector<ParticleCollider> pColliders;
+    std::vector<RigidCollider> rColliders;
+    DevBuf dPColliders, dRColliders, dRangeStart, dContacts, dContactCount;
+    unsigned contactTotal = 0, contactCap = 0;
+    float contactTolerance = 0.01f, contactStiffness = 100.0f; unsigned maxIterV = 5;  // CollisionDetection.cpp:25, SimulationModel.cpp:34, TimeStepController.cpp:23
     bool timingPending = false;
     bool mergeColours = true;             // one launch per colour when it holds several types (PBD_B200_MERGE=0 disables)
     std::vector<unsigned> slot;           // host particle index -> device slot (formula layouts or the tile-major permutation)
@@ -187,7 +195,7 @@ extern "C" int pbd_destroy(pbd_engine *e) {
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
     for (auto *b : {&e->pos, &e->vel, &e->oldp, &e->lastp, &e->pos0, &e->stage, &e->stage2, &e->massStage, &e->jacobiDelta, &e->dSlot, &e->dSlotOld, &e->relayoutTmp,
-                    &e->dColourStart, &e->dTileOff, &e->dTileStart, &e->dTileSmem, &e->dXArrive, &e->dXCounter, &e->dBuckets, &e->dTrace,
+                    &e->dPColliders, &e->dRColliders, &e->dRangeStart, &e->dContacts, &e->dContactCount, &e->dColourStart, &e->dTileOff, &e->dTileStart, &e->dTileSmem, &e->dXArrive, &e->dXCounter, &e->dBuckets, &e->dTrace,
                     &e->rbX, &e->rbQ, &e->rbV, &e->rbW, &e->rbOldX, &e->rbLastX, &e->rbOldQ, &e->rbLastQ, &e->rbI, &e->rbIinv}) b->release();
     for (auto &d : e->dev) {
         for (auto &b : d.idx) b.release();
@@ -338,6 +346,7 @@ extern "C" int pbd_set_rigid_bodies(pbd_engine *e, unsigned n, const float *mass
     if (n != e->nRb) { e->imageDirty = true; e->groupsSet = e->groupsSet && n == e->nRb; }
     drop_graph(e);
     e->nRb = n;
+    e->rbMass.assign(mass, mass + n);
     if (n == 0) return 0;
     std::vector<float4> X(n), Q(n), V(n), W(n), I(n), Ii(n);
     for (unsigned i = 0; i < n; i++) {
@@ -756,7 +765,8 @@ static int choose_resident_shape(pbd_engine *e) {
     }
     if ((unsigned long long)G * C * cap < e->n)
         return fail("resident mode: %u particles do not fit %u x %u tiles of %u (use PBD_MODE_GRAPH)", e->n, G, C, cap);
-    if (G > 1 && (e->nRb || !e->host[PBD_BALLJOINT].ids.empty() || !e->host[PBD_RB_PARTICLE_BALLJOINT].ids.empty()))
+    // (bodies without joints -- e.g. the static colliders of the contact path -- are integrated by CTA 0 and touch no constraint)
+    if (G > 1 && (!e->host[PBD_BALLJOINT].ids.empty() || !e->host[PBD_RB_PARTICLE_BALLJOINT].ids.empty()))
         return fail("resident mode: rigid-body coupling is supported for scenes that fit one cluster (use PBD_MODE_GRAPH)");
     e->resG = G; e->resC = C; e->nTiles = G * C;
     e->resXThreads = (G > 1) ? 128u : 0u;  // refined in prepare_resident once the share of X items is known
@@ -1460,6 +1470,96 @@ static int enqueue_step_jacobi(pbd_engine *e, cudaStream_t s, unsigned long long
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// contact path (contacts.cuh)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int pbd_set_colliders(pbd_engine *e, unsigned nP, const pbd_particle_collider *pc, unsigned nR, const pbd_rigid_collider *rc) {
+    if (!e || (nP && !pc) || (nR && !rc)) return fail("pbd_set_colliders: null argument");
+    CKE(use(e));
+    if (nR > (unsigned)kMaxRigidColliders) return fail("pbd_set_colliders: %u rigid colliders (the contact kernel keeps up to %d contacts per particle)", nR, kMaxRigidColliders);
+    std::vector<ParticleCollider> P(nP);
+    std::vector<RigidCollider> R(nR);
+    std::vector<unsigned> start(nP + 1, 0u);
+    for (unsigned i = 0; i < nP; i++) {
+        if ((unsigned long long)pc[i].offset + pc[i].count > e->n) return fail("pbd_set_colliders: particle collider %u covers [%u, %u), the engine holds %u particles", i, pc[i].offset, pc[i].offset + pc[i].count, e->n);
+        P[i].offset = pc[i].offset; P[i].count = pc[i].count; P[i].restitution = pc[i].restitution; P[i].friction = pc[i].friction;
+        start[i + 1] = start[i] + pc[i].count;
+    }
+    for (unsigned i = 0; i < nR; i++) {
+        const pbd_rigid_collider &c = rc[i];
+        if (c.shape < 0 || c.shape >= kNumShapes) return fail("pbd_set_colliders: rigid collider %u has unknown shape %d", i, c.shape);
+        if (c.body >= e->nRb) return fail("pbd_set_colliders: rigid collider %u refers to rigid body %u, the engine holds %u (pbd_set_rigid_bodies first)", i, c.body, e->nRb);
+        if (e->rbMass[c.body] != 0.0f)
+            return fail("pbd_set_colliders: rigid body %u has mass %g; contacts with dynamic bodies couple through the body and stay on the CPU time step (static colliders only)", c.body, e->rbMass[c.body]);
+        RigidCollider &d = R[i];
+        d.shape = c.shape; d.body = c.body; d.thickness = c.thickness; d.invert = c.invert_sdf ? -1.0f : 1.0f; d.restitution = c.restitution; d.friction = c.friction;
+        for (int k = 0; k < 3; k++) { d.dim[k] = c.dim[k]; d.v1[k] = c.v1[k]; d.v2[k] = c.v2[k]; d.aabbMin[k] = c.aabb_min[k]; d.aabbMax[k] = c.aabb_max[k]; }
+        for (int k = 0; k < 9; k++) d.R[k] = c.R[k];
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->pColliders.swap(P); e->rColliders.swap(R);
+    e->contactTotal = start[nP];
+    if (nP) { CKE(upload_vec(e->dPColliders, e->pColliders, e->stream)); CKE(upload_vec(e->dRangeStart, start, e->stream)); }
+    if (nR) CKE(upload_vec(e->dRColliders, e->rColliders, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+extern "C" int pbd_set_contact_params(pbd_engine *e, float tolerance, float stiffness, unsigned maxIterationsV) {
+    if (!e) return fail("null engine");
+    e->contactTolerance = tolerance; e->contactStiffness = stiffness; e->maxIterV = maxIterationsV;
+    return 0;
+}
+extern "C" int pbd_record_contacts(pbd_engine *e, unsigned capacity) {
+    if (!e) return fail("null engine");
+    CKE(use(e));
+    CK(cudaStreamSynchronize(e->stream));
+    e->contactCap = capacity;
+    if (capacity) {
+        CKE(e->dContacts.alloc((size_t)capacity * sizeof(ContactRecord)));
+        CKE(e->dContactCount.alloc(sizeof(unsigned)));
+        CK(cudaMemset(e->dContactCount.p, 0, sizeof(unsigned)));
+    }
+    return 0;
+}
+extern "C" int pbd_get_contacts(pbd_engine *e, pbd_contact *out, unsigned capacity, unsigned *count) {
+    if (!e || !count) return fail("pbd_get_contacts: null argument");
+    CKE(use(e));
+    *count = 0;
+    if (!e->contactCap) return fail("pbd_get_contacts: recording is off (pbd_record_contacts)");
+    CK(cudaStreamSynchronize(e->stream));
+    unsigned found = 0;
+    CK(cudaMemcpy(&found, e->dContactCount.p, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    *count = found;
+    const unsigned kept = std::min(found, e->contactCap);
+    static_assert(sizeof(pbd_contact) == sizeof(ContactRecord), "pbd_contact mirrors ContactRecord");
+    std::vector<pbd_contact> tmp(kept);
+    if (kept) CK(cudaMemcpy(tmp.data(), e->dContacts.p, (size_t)kept * sizeof(pbd_contact), cudaMemcpyDeviceToHost));
+    std::sort(tmp.begin(), tmp.end(), [](const pbd_contact &a, const pbd_contact &b) { return a.particle != b.particle ? a.particle < b.particle : a.body < b.body; });
+    if (out) for (unsigned i = 0; i < std::min(kept, capacity); i++) out[i] = tmp[i];
+    return 0;
+}
+// after the substeps of a step: collision detection + velocity-level contact solve (TimeStepController.cpp:189-196)
+static int enqueue_contacts(pbd_engine *e, cudaStream_t s, unsigned long long *launches) {
+    if (e->rColliders.empty() || e->contactTotal == 0) return 0;
+    for (const RigidCollider &c : e->rColliders)  // the bodies may have been replaced since pbd_set_colliders
+        if (c.body >= e->nRb || e->rbMass[c.body] != 0.0f) return fail("contact path: collider on rigid body %u, which is missing or not static any more (pbd_set_colliders again)", c.body);
+    for (const ParticleCollider &c : e->pColliders)
+        if ((unsigned long long)c.offset + c.count > e->n) return fail("contact path: a particle collider covers particles beyond the %u the engine holds", e->n);
+    ContactArgs a;
+    a.pos = (float4 *)e->pos.p; a.vel = (float4 *)e->vel.p; a.slot = (const unsigned *)e->dSlot.p;
+    a.rbX = (const float4 *)e->rbX.p; a.rbV = (const float4 *)e->rbV.p; a.rbW = (const float4 *)e->rbW.p;
+    a.rigid = (const RigidCollider *)e->dRColliders.p; a.nRigid = (unsigned)e->rColliders.size();
+    a.ranges = (const ParticleCollider *)e->dPColliders.p; a.nRanges = (unsigned)e->pColliders.size();
+    a.rangeStart = (const unsigned *)e->dRangeStart.p; a.total = e->contactTotal;
+    a.tolerance = e->contactTolerance; a.stiffness = e->contactStiffness; a.maxIterV = e->maxIterV;
+    a.record = e->contactCap ? (ContactRecord *)e->dContacts.p : nullptr; a.recordCount = (unsigned *)e->dContactCount.p; a.recordCap = e->contactCap;
+    if (e->contactCap) CK(cudaMemsetAsync(e->dContactCount.p, 0, sizeof(unsigned), s));
+    k_contacts<<<(a.total + 127u) / 128u, 128, 0, s>>>(a);
+    CK(cudaGetLastError());
+    *launches += 1;
+    return 0;
+}
+
 static int ensure_graph(pbd_engine *e, unsigned long long *launchesPerStep) {
     if (e->graphValid) return 0;
     cudaGraph_t graph = nullptr;
@@ -1505,6 +1605,7 @@ extern "C" int pbd_step(pbd_engine *e, unsigned nSteps) {
             CK(cudaGraphLaunch(e->graphExec, e->stream));
             L = e->graphLaunches;
         }
+        CKE(enqueue_contacts(e, e->stream, &L));
         e->stats.kernel_launches += L;
         e->stats.steps++;
         e->stats.projections += (unsigned long long)e->numConstraints * e->subSteps * e->maxIter;

@@ -461,8 +461,10 @@ __device__ __forceinline__ void project_femtet(float4 &q0, float4 &q1, float4 &q
     const V3 p0 = xyz(q0), p1 = xyz(q1), p2 = xyz(q2), p3 = xyz(q3);
     // currentVolume (Constraints.cpp:1795) and volume (PositionBasedDynamics.cpp:1133) are the same triple product
     const float volume = dot(cross(p1 - p0, p2 - p0), p3 - p0) * (1.0f / 6.0f);
-    const bool handleInversion = (volume / restVolume) < 0.2f;  // a tested quotient: IEEE division
-    const bool inversionBranch = handleInversion && !(volume > 0.0f);
+    // handleInversion = (volume / restVolume) < 0.2 and the inversion branch = handleInversion && !(volume > 0).  With a positive
+    // rest volume the second condition implies the first (quotient <= 0), so the IEEE division of the tested quotient is evaluated
+    // only for non-positive rest volumes -- same decisions, one division less on the common path's dependency chain.
+    const bool inversionBranch = !(volume > 0.0f) && (restVolume > 0.0f || (volume / restVolume) < 0.2f);
     float mu, lambda;
     if (XPBD) {  // Lame parameters divided by E (XPBD.cpp:247-248)
         mu = 0.5f * frcp(1.0f + nu);

@@ -110,3 +110,39 @@ def cfg4(m, n_cloth=224, bar_dims=(51, 21, 11), cloth_method=2, with_rig=True, s
 
 def projections_per_step(num_constraints, sub_steps, max_iter):
     return num_constraints * sub_steps * max_iter
+
+
+# ---- contact path: the geometry of Demos/DistanceFieldDemos/ClothCollisionDemo.cpp (cloth dropped onto static distance-field bodies) ----
+BOX_VERTS = np.array([[-0.5, -0.5, -0.5], [0.5, -0.5, -0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, -0.5],
+                      [-0.5, -0.5, 0.5], [0.5, -0.5, 0.5], [0.5, 0.5, 0.5], [-0.5, 0.5, 0.5]], dtype=np.float64)
+BOX_FACES = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [0, 4, 7], [0, 7, 3], [1, 2, 6], [1, 6, 5]], dtype=np.uint32)
+
+
+def cloth_on_colliders(m, n=24, tolerance=0.05, max_iter=4, sub_steps=1, shapes=("box", "sphere", "torus")):
+    """Reference builds only (m = CpuPbd "ref"/"refgpu").  A (n x n) XPBD cloth above a static floor box, a static sphere and a static torus,
+    each a rigid body whose mesh is a unit cube scaled to the shape's bounding box (the mesh only feeds the AABB and the mass properties)."""
+    m.add_regular_triangle_model(n, n, t=(-2.5, 2.2, -2.5), R=RX90, scale=(5.0, 5.0))
+    m.add_cloth_constraints(0, 4, dist_k=1.0e5)
+    m.add_bending_constraints(0, 3, 100.0)
+    m.set_params(dt=0.005, sub_steps=sub_steps, max_iter=max_iter)
+    bodies = []
+    rot = np.array([[0.9553365, -0.2955202, 0.0], [0.2955202, 0.9553365, 0.0], [0.0, 0.0, 1.0]])  # 0.3 rad about z: exercises R, v1, v2
+    if "box" in shapes:
+        i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(0.0, -0.5, 0.0), R=np.eye(3), scale=(20.0, 1.0, 20.0)); bodies.append((i, 0, (20.0, 1.0, 20.0)))
+    if "sphere" in shapes:
+        i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(-0.8, 1.2, -0.6), R=np.eye(3), scale=(1.6, 1.6, 1.6)); bodies.append((i, 1, (0.8,)))
+    if "torus" in shapes:
+        i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(1.2, 1.0, 0.8), R=rot, scale=(2.4, 0.8, 2.4)); bodies.append((i, 2, (0.8, 0.4)))
+    if "cylinder" in shapes:
+        i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(-1.0, 1.0, 1.2), R=rot, scale=(1.0, 1.6, 1.0)); bodies.append((i, 3, (0.5, 1.6)))
+    if "hollow_sphere" in shapes:
+        i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(1.0, 1.3, -1.2), R=np.eye(3), scale=(1.4, 1.4, 1.4)); bodies.append((i, 4, (0.6,)))
+    if "hollow_box" in shapes:
+        i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(0.2, 1.1, -1.5), R=rot, scale=(1.2, 1.0, 1.0)); bodies.append((i, 5, (1.1, 0.9, 0.9)))
+    m.use_distance_field_cd(tolerance)
+    for i, shape, dims in bodies:
+        m.set_rigid_body_mass(i, 0.0)
+        m.add_rigid_collider(i, shape, dims, thickness=0.05, restitution=0.6, friction=0.1 if shape else 0.2)
+    m.add_model_collider(0, 0, restitution=0.5, friction=0.1)
+    m.set_contact_params(stiffness=100.0, max_iter_v=5)
+    return bodies

@@ -503,8 +503,9 @@ def test_jacobi_comparison_mode():
 
 
 def test_adapter_refuses_models_with_collision_objects(cpu_libs):
-    """TimeStepController.cpp:189-196 (collision detection + velocityConstraintProjection over the contacts) is not on the GPU path:
-    GpuTimeStepController must refuse such a model with lastError() instead of silently simulating it without contacts."""
+    """TimeStepController.cpp:189-196 (collision detection + velocityConstraintProjection over the contacts): the GPU path covers
+    DistanceFieldCollisionDetection with static analytic bodies (tests/test_gpu_contacts.py); with any other collision detection
+    GpuTimeStepController must refuse the model with lastError() instead of silently simulating it without contacts."""
     from oracle import pyoracle
     if not pyoracle.available("refgpu", "f32"):
         pytest.skip("prebuilt oracle/_ref/libpbdref_gpu_f32.so not present on this box")
