@@ -515,6 +515,36 @@ def run_b200(args):
             except Exception as ex:
                 side[w] = {"error": str(ex)}
         WORKLOAD = main
+        # the contact path (SURVEY f-4, static analytic colliders): cfg2 with a floor box, a sphere poking through the sheet and a torus
+        try:
+            e3, inf = make_engine(local, args.size, args.iters)
+            mn, md, pr = pick_mode(e3, args.mode if args.mode != "launch" else "auto", None)
+            k = 10
+            ms_plain, _ = timed_steps(e3, md, k, 3, None)
+            xc = e3.get_attr(_capi.ATTR_X)
+            cx, cy, cz = [float(v) for v in xc.mean(axis=0)]
+            ident = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+            def collider(shape, body, dim, centre, half):
+                rc = _capi.RigidCollider(); rc.shape = shape; rc.body = body; rc.dim[:] = list(dim) + [0.0] * (3 - len(dim)); rc.thickness = 0.0; rc.invert_sdf = 0
+                rc.restitution = 0.6; rc.friction = 0.2; rc.R[:] = ident; rc.v1[:] = [0.0, 0.0, 0.0]; rc.v2[:] = list(centre)
+                rc.aabb_min[:] = [c - h - 0.05 for c, h in zip(centre, half)]; rc.aabb_max[:] = [c + h + 0.05 for c, h in zip(centre, half)]
+                return rc
+            centres = [(cx, cy - 3.0, cz), (cx, cy - 1.7, cz), (cx + 3.0, cy - 0.3, cz + 2.0)]
+            e3.set_rigid_bodies([0.0, 0.0, 0.0], centres, [(1.0, 0.0, 0.0, 0.0)] * 3, [(1.0, 1.0, 1.0)] * 3)
+            e3.set_colliders([_capi.ParticleCollider(0, inf["n"], 0.5, 0.1)],
+                             [collider(_capi.SHAPE_BOX, 0, (50.0, 0.5, 50.0), centres[0], (50.0, 0.5, 50.0)),
+                              collider(_capi.SHAPE_SPHERE, 1, (2.0,), centres[1], (2.0, 2.0, 2.0)),
+                              collider(_capi.SHAPE_TORUS, 2, (1.5, 0.5), centres[2], (2.0, 0.5, 2.0))])
+            e3.set_contact_params(tolerance=0.05, stiffness=100.0, max_iter_v=5)
+            e3.record_contacts(1 << 20)
+            ms_c, _ = timed_steps(e3, md, k, 3, None)
+            _, found = e3.contacts(1)
+            side["cfg2_contacts"] = {"ms_per_step": ms_c / k, "ms_per_step_without_colliders": ms_plain / k, "contact_kernel_ms": (ms_c - ms_plain) / k, "mode": mn,
+                                     "contacts_in_last_step": int(found), "colliders": "static box + sphere + torus (analytic distance fields), 5 velocity iterations",
+                                     "particles_tested_per_step": inf["n"], "value": inf["proj_per_step"] * k / (ms_c * 1e-3), "unit": UNIT}
+            e3.close()
+        except Exception as ex:
+            side["cfg2_contacts"] = {"error": str(ex)}
 
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) ----------------------------------------------------------------
     cpu = None
