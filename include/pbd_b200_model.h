@@ -88,6 +88,24 @@ void pbdm_tet_get_tets(pbdm_model *m, unsigned tm, unsigned *out);
 unsigned pbdm_first_fit_colouring(unsigned numBodies, unsigned numConstraints, const unsigned *bodyOff, const unsigned *bodies, unsigned *colourOut);
 
 /* TimeStepController + TimeManager + Simulation::GRAVITATION.  ids: 0 NUM_SUB_STEPS, 1 MAX_ITERATIONS, 2 MAX_ITERATIONS_V, 3 VELOCITY_UPDATE_METHOD */
+/* ---- collision objects (Simulation/DistanceFieldCollisionDetection.h, Simulation/CollisionDetection.h:15-104): the registry with the
+ * reference's add* arguments; the tests run on the GPU (include/pbd_b200.h "Contact path").  bodyType: 0 rigid body, 1 triangle model,
+ * 2 tet model (CollisionObject::*CollisionObjectType).  `shape` = pbd_collider_shape, `dims` = what addCollisionBox (full extents) /
+ * Sphere (radius) / Torus (radii) / Cylinder (radius, height) / HollowSphere / HollowBox take; `vertices` (local, 3 floats each, may be
+ * NULL) feed the bounding box as the body's mesh does in the reference. */
+typedef struct pbdm_collision_detection pbdm_collision_detection;
+pbdm_collision_detection *pbdm_cd_create(void);
+void pbdm_cd_destroy(pbdm_collision_detection *cd);
+void pbdm_cd_set_tolerance(pbdm_collision_detection *cd, float tolerance);
+float pbdm_cd_get_tolerance(pbdm_collision_detection *cd);
+int pbdm_cd_add_collision_shape(pbdm_collision_detection *cd, unsigned bodyIndex, unsigned bodyType, int shape, const float *dims, float thickness,
+                                const float *vertices, unsigned numVertices, int testMesh, int invertSDF);
+int pbdm_cd_add_collision_object_without_geometry(pbdm_collision_detection *cd, unsigned bodyIndex, unsigned bodyType, int testMesh);
+unsigned pbdm_cd_num_collision_objects(pbdm_collision_detection *cd);
+/* restitution / friction coefficients of a rigid body (kind 0), triangle model (1) or tet model (2): set*Coeff of the three classes */
+int pbdm_set_contact_coefficients(pbdm_model *m, int kind, unsigned index, float restitution, float friction);
+void pbdm_set_contact_stiffness_particle_rigid_body(pbdm_model *m, float stiffness);  /* SimulationModel.h:253-254 */
+
 pbdm_timestep *pbdm_timestep_create(int device, void *stream);  /* NULL + pbd_last_error() when no CUDA device */
 void pbdm_timestep_destroy(pbdm_timestep *ts);
 int pbdm_timestep_set_uint(pbdm_timestep *ts, int id, unsigned value);
@@ -100,6 +118,8 @@ float pbdm_timestep_get_time(pbdm_timestep *ts);
 void pbdm_timestep_set_time(pbdm_timestep *ts, float t);
 void pbdm_timestep_set_gravitation(pbdm_timestep *ts, const float *g3);
 void pbdm_timestep_set_mode(pbdm_timestep *ts, int mode);
+/* TimeStep::setCollisionDetection (Simulation/TimeStep.cpp:63-68); cd = NULL detaches */
+void pbdm_timestep_set_collision_detection(pbdm_timestep *ts, pbdm_model *m, pbdm_collision_detection *cd);
 int pbdm_timestep_step(pbdm_timestep *ts, pbdm_model *m);  /* TimeStep::step(SimulationModel&) (Simulation/TimeStep.h:41) */
 const char *pbdm_timestep_error(pbdm_timestep *ts);
 pbd_engine *pbdm_timestep_engine(pbdm_timestep *ts);

@@ -835,9 +835,127 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// DistanceFieldCollisionDetection: registry only (the tests run in csrc/contacts.cuh)
+// ---------------------------------------------------------------------------------------------------------
+CollisionDetection::CollisionObject &DistanceFieldCollisionDetection::add(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices,
+                                                                          unsigned int numVertices, int shape, bool testMesh, bool invertSDF) {
+    m_collisionObjects.emplace_back();
+    CollisionObject &co = m_collisionObjects.back();
+    co.m_bodyIndex = bodyIndex; co.m_bodyType = bodyType; co.shape = shape; co.m_testMesh = testMesh; co.invertSDF = invertSDF;
+    if (vertices && bodyType == CollisionObject::RigidBodyCollisionObjectType) co.vertices.assign(vertices, vertices + numVertices);
+    return co;
+}
+void DistanceFieldCollisionDetection::addCollisionBox(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector3r &box, bool testMesh, bool invertSDF) {
+    CollisionObject &co = add(bodyIndex, bodyType, vertices, numVertices, PBD_SHAPE_BOX, testMesh, invertSDF);
+    for (int k = 0; k < 3; k++) co.dim[k] = static_cast<Real>(0.5) * box[k];  // the distance function takes half extents (:503)
+}
+void DistanceFieldCollisionDetection::addCollisionSphere(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, Real radius, bool testMesh, bool invertSDF) {
+    add(bodyIndex, bodyType, vertices, numVertices, PBD_SHAPE_SPHERE, testMesh, invertSDF).dim[0] = radius;
+}
+void DistanceFieldCollisionDetection::addCollisionTorus(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector2r &radii, bool testMesh, bool invertSDF) {
+    CollisionObject &co = add(bodyIndex, bodyType, vertices, numVertices, PBD_SHAPE_TORUS, testMesh, invertSDF);
+    co.dim[0] = radii[0]; co.dim[1] = radii[1];
+}
+void DistanceFieldCollisionDetection::addCollisionCylinder(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector2r &dim, bool testMesh, bool invertSDF) {
+    CollisionObject &co = add(bodyIndex, bodyType, vertices, numVertices, PBD_SHAPE_CYLINDER, testMesh, invertSDF);
+    co.dim[0] = dim[0]; co.dim[1] = static_cast<Real>(0.5) * dim[1];  // height / 2 (:545)
+}
+void DistanceFieldCollisionDetection::addCollisionHollowSphere(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, Real radius, Real thickness, bool testMesh, bool invertSDF) {
+    CollisionObject &co = add(bodyIndex, bodyType, vertices, numVertices, PBD_SHAPE_HOLLOW_SPHERE, testMesh, invertSDF);
+    co.dim[0] = radius; co.thickness = thickness;
+}
+void DistanceFieldCollisionDetection::addCollisionHollowBox(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector3r &box, Real thickness, bool testMesh, bool invertSDF) {
+    CollisionObject &co = add(bodyIndex, bodyType, vertices, numVertices, PBD_SHAPE_HOLLOW_BOX, testMesh, invertSDF);
+    for (int k = 0; k < 3; k++) co.dim[k] = static_cast<Real>(0.5) * box[k];
+    co.thickness = thickness;
+}
+void DistanceFieldCollisionDetection::addCollisionObjectWithoutGeometry(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, bool testMesh) {
+    add(bodyIndex, bodyType, vertices, numVertices, -1, testMesh, false);
+}
+
+// The pair dispatch of DistanceFieldCollisionDetection::collisionDetection (DistanceFieldCollisionDetection.cpp:96-165) reduced to what the GPU
+// path covers; everything else is an error (the reference would run it, this engine cannot).
+bool TimeStepController::uploadColliders(SimulationModel &model) {
+    std::vector<pbd_particle_collider> pcs;
+    std::vector<pbd_rigid_collider> rcs;
+    if (m_collisionDetection) {
+        unsigned int tetObjects = 0;
+        for (const CollisionDetection::CollisionObject &co : m_collisionDetection->getCollisionObjects()) {
+            typedef CollisionDetection::CollisionObject CO;
+            if (co.m_bodyType == CO::TriangleModelCollisionObjectType || co.m_bodyType == CO::TetModelCollisionObjectType) {
+                const bool tet = (co.m_bodyType == CO::TetModelCollisionObjectType);
+                if (tet && ++tetObjects > 1) { m_error = "two tet models as collision objects produce particle-tet contacts, which are not on the GPU path"; return false; }
+                if (!co.m_testMesh) continue;
+                pbd_particle_collider pc;
+                if (tet) {
+                    if (co.m_bodyIndex >= model.getTetModels().size()) { m_error = "collision object refers to a tet model that does not exist"; return false; }
+                    const TetModel *tm = model.getTetModels()[co.m_bodyIndex];
+                    pc.offset = tm->getIndexOffset(); pc.count = tm->getParticleMesh().numVertices(); pc.restitution = tm->getRestitutionCoeff(); pc.friction = tm->getFrictionCoeff();
+                } else {
+                    if (co.m_bodyIndex >= model.getTriangleModels().size()) { m_error = "collision object refers to a triangle model that does not exist"; return false; }
+                    const TriangleModel *tm = model.getTriangleModels()[co.m_bodyIndex];
+                    pc.offset = tm->getIndexOffset(); pc.count = tm->getParticleMesh().numVertices(); pc.restitution = tm->getRestitutionCoeff(); pc.friction = tm->getFrictionCoeff();
+                }
+                pcs.push_back(pc);
+                continue;
+            }
+            if (co.m_bodyType != CO::RigidBodyCollisionObjectType || co.shape < 0) continue;
+            if (co.m_bodyIndex >= model.getRigidBodies().size()) { m_error = "collision object refers to a rigid body that does not exist"; return false; }
+            const RigidBody &rb = *model.getRigidBodies()[co.m_bodyIndex];
+            if (rb.getMass() != 0) { m_error = "rigid body " + std::to_string(co.m_bodyIndex) + " is a dynamic collision object; contacts with dynamic bodies are not on the GPU path (static colliders only)"; return false; }
+            if (co.invertSDF) { m_error = "collision objects with an inverted distance field are not on the GPU path"; return false; }
+            pbd_rigid_collider rc;
+            std::memset(&rc, 0, sizeof(rc));
+            rc.shape = co.shape; rc.body = co.m_bodyIndex; rc.thickness = co.thickness; rc.invert_sdf = 0;
+            for (int k = 0; k < 3; k++) rc.dim[k] = co.dim[k];
+            rc.restitution = rb.getRestitutionCoeff(); rc.friction = rb.getFrictionCoeff();
+            // bodies of this mirror have no principal-axis / initial transformation: x_local = R(q)^T (x_w - x), x_w = R(q) x_local + x
+            const Quaternionr &q = rb.getRotation();
+            const Real R[9] = {1 - 2 * (q.y * q.y + q.z * q.z), 2 * (q.x * q.y - q.w * q.z), 2 * (q.x * q.z + q.w * q.y),
+                               2 * (q.x * q.y + q.w * q.z), 1 - 2 * (q.x * q.x + q.z * q.z), 2 * (q.y * q.z - q.w * q.x),
+                               2 * (q.x * q.z - q.w * q.y), 2 * (q.y * q.z + q.w * q.x), 1 - 2 * (q.x * q.x + q.y * q.y)};
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rc.R[3 * r + c] = R[3 * c + r];  // transformation R = R(q)^T
+            for (int k = 0; k < 3; k++) { rc.v1[k] = 0.0f; rc.v2[k] = rb.getPosition()[k]; }
+            // bounding box: the object's vertices in world space (CollisionDetection::updateAABB), else the shape's own box
+            Real lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+            auto extend = [&](const Real v[3]) {
+                for (int r = 0; r < 3; r++) {
+                    const Real w = R[3 * r] * v[0] + R[3 * r + 1] * v[1] + R[3 * r + 2] * v[2] + rb.getPosition()[r];
+                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
+                }
+            };
+            if (!co.vertices.empty()) { for (const Vector3r &v : co.vertices) { const Real t[3] = {v[0], v[1], v[2]}; extend(t); } }
+            else {
+                Real h[3] = {co.dim[0], co.dim[1], co.dim[2]};
+                if (co.shape == PBD_SHAPE_SPHERE || co.shape == PBD_SHAPE_HOLLOW_SPHERE) h[0] = h[1] = h[2] = co.dim[0] + co.thickness;
+                else if (co.shape == PBD_SHAPE_TORUS) { h[0] = h[2] = co.dim[0] + co.dim[1]; h[1] = co.dim[1]; }
+                else if (co.shape == PBD_SHAPE_CYLINDER) { h[0] = h[2] = co.dim[0]; h[1] = co.dim[1]; }
+                else if (co.shape == PBD_SHAPE_HOLLOW_BOX) for (int k = 0; k < 3; k++) h[k] += co.thickness;
+                for (int corner = 0; corner < 8; corner++) { const Real t[3] = {(corner & 1) ? h[0] : -h[0], (corner & 2) ? h[1] : -h[1], (corner & 4) ? h[2] : -h[2]}; extend(t); }
+            }
+            const Real tol = m_collisionDetection->getTolerance();
+            for (int k = 0; k < 3; k++) { rc.aabb_min[k] = lo[k] - tol; rc.aabb_max[k] = hi[k] + tol; }
+            rcs.push_back(rc);
+        }
+    }
+    // send only when something changed (byte image of the arguments)
+    std::vector<unsigned char> image(pcs.size() * sizeof(pbd_particle_collider) + rcs.size() * sizeof(pbd_rigid_collider) + 1, 0);
+    if (!pcs.empty()) std::memcpy(image.data(), pcs.data(), pcs.size() * sizeof(pbd_particle_collider));
+    if (!rcs.empty()) std::memcpy(image.data() + pcs.size() * sizeof(pbd_particle_collider), rcs.data(), rcs.size() * sizeof(pbd_rigid_collider));
+    image.back() = (unsigned char)pcs.size();
+    if (image != m_collidersSent) {
+        if (pbd_set_colliders(m_engine, (unsigned)pcs.size(), pcs.data(), (unsigned)rcs.size(), rcs.data())) return fail("pbd_set_colliders");
+        m_collidersSent.swap(image);
+    }
+    if (m_collisionDetection && pbd_set_contact_params(m_engine, m_collisionDetection->getTolerance(), model.getContactStiffnessParticleRigidBody(), m_maxIterationsV)) return fail("pbd_set_contact_params");
+    return true;
+}
+
 bool TimeStepController::step(SimulationModel &model) {
     if (!m_engine) { if (m_error.empty()) m_error = "no engine"; return false; }
     if (!uploadModel(model)) return false;
+    if ((m_collisionDetection || !m_collidersSent.empty()) && !uploadColliders(model)) return false;
     const float g[3] = {m_gravitation[0], m_gravitation[1], m_gravitation[2]};
     if (m_mode != m_modeSent) { if (pbd_set_mode(m_engine, m_mode)) return fail("pbd_set_mode"); m_modeSent = m_mode; }
     SentParams now = {m_tm.getTimeStepSize(), m_subSteps, m_maxIterations, m_velocityUpdateMethod, {g[0], g[1], g[2]}};

@@ -136,9 +136,14 @@ public:
     ParticleMesh &getParticleMesh() { return m_particleMesh; }
     const ParticleMesh &getParticleMesh() const { return m_particleMesh; }
     unsigned int getIndexOffset() const { return m_indexOffset; }
+    Real getRestitutionCoeff() const { return m_restitutionCoeff; }   // TriangleModel.cpp constructor: 0.6 / 0.2
+    void setRestitutionCoeff(Real v) { m_restitutionCoeff = v; }
+    Real getFrictionCoeff() const { return m_frictionCoeff; }
+    void setFrictionCoeff(Real v) { m_frictionCoeff = v; }
 private:
     unsigned int m_indexOffset = 0;
     ParticleMesh m_particleMesh;
+    Real m_restitutionCoeff = static_cast<Real>(0.6), m_frictionCoeff = static_cast<Real>(0.2);
 };
 
 class TetModel {
@@ -148,9 +153,14 @@ public:
     ParticleMesh &getParticleMesh() { return m_particleMesh; }
     const ParticleMesh &getParticleMesh() const { return m_particleMesh; }
     unsigned int getIndexOffset() const { return m_indexOffset; }
+    Real getRestitutionCoeff() const { return m_restitutionCoeff; }   // TetModel.cpp constructor: 0.6 / 0.2
+    void setRestitutionCoeff(Real v) { m_restitutionCoeff = v; }
+    Real getFrictionCoeff() const { return m_frictionCoeff; }
+    void setFrictionCoeff(Real v) { m_frictionCoeff = v; }
 private:
     unsigned int m_indexOffset = 0;
     ParticleMesh m_particleMesh;
+    Real m_restitutionCoeff = static_cast<Real>(0.6), m_frictionCoeff = static_cast<Real>(0.2);
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -170,6 +180,11 @@ public:
     const Vector3r &getAngularVelocity() const { return m_omega; }
     const Quaternionr &getRotation() const { return m_q; }
     const Vector3r &getInertiaTensor() const { return m_inertiaTensor; }
+    Real getRestitutionCoeff() const { return m_restitutionCoeff; }   // RigidBody.h:115-116: 0.6 / 0.2
+    void setRestitutionCoeff(Real v) { m_restitutionCoeff = v; }
+    Real getFrictionCoeff() const { return m_frictionCoeff; }
+    void setFrictionCoeff(Real v) { m_frictionCoeff = v; }
+    Real m_restitutionCoeff = static_cast<Real>(0.6), m_frictionCoeff = static_cast<Real>(0.2);
     Real m_mass = 0, m_invMass = 0;
     Vector3r m_x, m_x0, m_v, m_omega, m_inertiaTensor;
     Quaternionr m_q, m_q0;
@@ -260,6 +275,10 @@ public:
     void setSolidNormalizeStretch(bool val);
     void setSolidNormalizeShear(bool val);
 
+    // SimulationModel.h:253-254, SimulationModel.cpp:57
+    Real getContactStiffnessParticleRigidBody() const { return m_contactStiffnessParticleRigidBody; }
+    void setContactStiffnessParticleRigidBody(Real val) { m_contactStiffnessParticleRigidBody = val; }
+
     // flat view for the engine
     const TypeStore &store(int type) const { return m_store[type]; }
     uint64_t constraintGeneration() const { return m_generation; }  // bumps whenever constraints or their parameters change
@@ -276,6 +295,7 @@ private:
     std::vector<ConstraintRef> m_order;
     ConstraintGroupVector m_constraintGroups;
     uint64_t m_generation = 1;
+    Real m_contactStiffnessParticleRigidBody = static_cast<Real>(100.0);
 };
 
 // Greedy first-fit colouring shared by SimulationModel::initConstraintGroups and pbd_color_first_fit: constraint c uses
@@ -286,6 +306,46 @@ unsigned int firstFitColouring(unsigned int numBodies, unsigned int numConstrain
 // ---------------------------------------------------------------------------------------------------------
 // TimeManager / TimeStepController (Simulation/TimeManager.h, Simulation/TimeStepController.{h,cpp})
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// CollisionDetection / DistanceFieldCollisionDetection (Simulation/CollisionDetection.h:15-104,
+// Simulation/DistanceFieldCollisionDetection.h): the registry of collision objects with the reference's add* signatures.  The
+// tests themselves run on the GPU (csrc/contacts.cuh); this class only holds what pbd_set_colliders needs.  The reference takes
+// a collision object's bounding box from the rigid body's mesh; the bodies of this mirror carry no mesh, so the box is taken
+// from the vertices handed to add* (the same local vertices the reference builds its bounding-sphere hierarchy from).
+// ---------------------------------------------------------------------------------------------------------
+class CollisionDetection {
+public:
+    struct CollisionObject {
+        static const unsigned int RigidBodyCollisionObjectType = 0, TriangleModelCollisionObjectType = 1, TetModelCollisionObjectType = 2;
+        unsigned int m_bodyIndex = 0, m_bodyType = 0;
+        int shape = -1;                       // pbd_collider_shape, -1 = object without geometry
+        Real dim[3] = {0, 0, 0}, thickness = 0;
+        bool m_testMesh = true; bool invertSDF = false;
+        std::vector<Vector3r> vertices;       // local vertices (bounding box source)
+    };
+    virtual ~CollisionDetection() {}
+    Real getTolerance() const { return m_tolerance; }
+    void setTolerance(Real v) { m_tolerance = v; }
+    std::vector<CollisionObject> &getCollisionObjects() { return m_collisionObjects; }
+    void cleanup() { m_collisionObjects.clear(); }
+protected:
+    Real m_tolerance = static_cast<Real>(0.01);  // CollisionDetection.cpp:25
+    std::vector<CollisionObject> m_collisionObjects;
+};
+class DistanceFieldCollisionDetection : public CollisionDetection {
+public:
+    // DistanceFieldCollisionDetection.cpp:498-582 (box / hollow box take the full extents, cylinder radius and full height)
+    void addCollisionBox(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector3r &box, bool testMesh = true, bool invertSDF = false);
+    void addCollisionSphere(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, Real radius, bool testMesh = true, bool invertSDF = false);
+    void addCollisionTorus(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector2r &radii, bool testMesh = true, bool invertSDF = false);
+    void addCollisionCylinder(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector2r &dim, bool testMesh = true, bool invertSDF = false);
+    void addCollisionHollowSphere(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, Real radius, Real thickness, bool testMesh = true, bool invertSDF = false);
+    void addCollisionHollowBox(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, const Vector3r &box, Real thickness, bool testMesh = true, bool invertSDF = false);
+    void addCollisionObjectWithoutGeometry(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, bool testMesh);
+private:
+    CollisionObject &add(unsigned int bodyIndex, unsigned int bodyType, const Vector3r *vertices, unsigned int numVertices, int shape, bool testMesh, bool invertSDF);
+};
+
 class TimeManager {
 public:
     Real getTime() const { return time; }
@@ -320,10 +380,17 @@ public:
     TimeManager &timeManager() { return m_tm; }
     pbd_engine *engine() { return m_engine; }
     void setSolverMode(int mode) { m_mode = mode; }
+    // TimeStep::setCollisionDetection (TimeStep.cpp:63-68).  Covered on the GPU: particles of triangle / tet models against analytic
+    // distance fields on static rigid bodies; step() fails with error() for anything else (dynamic collision bodies, two tet models).
+    void setCollisionDetection(SimulationModel &model, CollisionDetection *cd) { (void)model; m_collisionDetection = cd; }
+    CollisionDetection *getCollisionDetection() { return m_collisionDetection; }
 
 private:
     bool uploadModel(SimulationModel &model);
+    bool uploadColliders(SimulationModel &model);
     bool fail(const char *what);
+    CollisionDetection *m_collisionDetection = nullptr;
+    std::vector<unsigned char> m_collidersSent;  // byte image of the last pbd_set_colliders arguments
     pbd_engine *m_engine = nullptr;
     std::string m_error;
     TimeManager m_tm;

@@ -8,6 +8,7 @@ using namespace pbd_b200;
 
 struct pbdm_model { SimulationModel model; };
 struct pbdm_timestep { TimeStepController ts; pbdm_timestep(int d, void *s) : ts(d, s) {} };
+struct pbdm_collision_detection { DistanceFieldCollisionDetection cd; };
 
 static inline Vector3r v3(const float *p) { return p ? Vector3r(p[0], p[1], p[2]) : Vector3r(); }
 static inline Matrix3r m3(const float *p) { Matrix3r m = Matrix3r::Identity(); if (p) std::memcpy(m.m, p, sizeof(m.m)); return m; }
@@ -239,6 +240,45 @@ float pbdm_timestep_get_time(pbdm_timestep *ts) { return ts->ts.timeManager().ge
 void pbdm_timestep_set_time(pbdm_timestep *ts, float t) { ts->ts.timeManager().setTime(t); }
 void pbdm_timestep_set_gravitation(pbdm_timestep *ts, const float *g) { ts->ts.setGravitation(v3(g)); }
 void pbdm_timestep_set_mode(pbdm_timestep *ts, int mode) { ts->ts.setSolverMode(mode); }
+pbdm_collision_detection *pbdm_cd_create(void) { return new pbdm_collision_detection(); }
+void pbdm_cd_destroy(pbdm_collision_detection *cd) { delete cd; }
+void pbdm_cd_set_tolerance(pbdm_collision_detection *cd, float t) { cd->cd.setTolerance(t); }
+float pbdm_cd_get_tolerance(pbdm_collision_detection *cd) { return cd->cd.getTolerance(); }
+int pbdm_cd_add_collision_shape(pbdm_collision_detection *cd, unsigned bodyIndex, unsigned bodyType, int shape, const float *dims, float thickness,
+                                const float *vertices, unsigned numVertices, int testMesh, int invertSDF) {
+    if (!cd || !dims) return 1;
+    std::vector<Vector3r> v(vertices ? numVertices : 0);
+    for (size_t i = 0; i < v.size(); i++) v[i] = Vector3r(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]);
+    const Vector3r *vp = v.empty() ? nullptr : v.data();
+    const unsigned nv = (unsigned)v.size();
+    switch (shape) {
+    case PBD_SHAPE_BOX: cd->cd.addCollisionBox(bodyIndex, bodyType, vp, nv, Vector3r(dims[0], dims[1], dims[2]), testMesh != 0, invertSDF != 0); break;
+    case PBD_SHAPE_SPHERE: cd->cd.addCollisionSphere(bodyIndex, bodyType, vp, nv, dims[0], testMesh != 0, invertSDF != 0); break;
+    case PBD_SHAPE_TORUS: cd->cd.addCollisionTorus(bodyIndex, bodyType, vp, nv, Vector2r{{dims[0], dims[1]}}, testMesh != 0, invertSDF != 0); break;
+    case PBD_SHAPE_CYLINDER: cd->cd.addCollisionCylinder(bodyIndex, bodyType, vp, nv, Vector2r{{dims[0], dims[1]}}, testMesh != 0, invertSDF != 0); break;
+    case PBD_SHAPE_HOLLOW_SPHERE: cd->cd.addCollisionHollowSphere(bodyIndex, bodyType, vp, nv, dims[0], thickness, testMesh != 0, invertSDF != 0); break;
+    case PBD_SHAPE_HOLLOW_BOX: cd->cd.addCollisionHollowBox(bodyIndex, bodyType, vp, nv, Vector3r(dims[0], dims[1], dims[2]), thickness, testMesh != 0, invertSDF != 0); break;
+    default: return 1;
+    }
+    return 0;
+}
+int pbdm_cd_add_collision_object_without_geometry(pbdm_collision_detection *cd, unsigned bodyIndex, unsigned bodyType, int testMesh) {
+    if (!cd) return 1;
+    cd->cd.addCollisionObjectWithoutGeometry(bodyIndex, bodyType, nullptr, 0, testMesh != 0);
+    return 0;
+}
+unsigned pbdm_cd_num_collision_objects(pbdm_collision_detection *cd) { return (unsigned)cd->cd.getCollisionObjects().size(); }
+int pbdm_set_contact_coefficients(pbdm_model *m, int kind, unsigned index, float restitution, float friction) {
+    if (kind == 0) { auto &v = m->model.getRigidBodies(); if (index >= v.size()) return 1; v[index]->setRestitutionCoeff(restitution); v[index]->setFrictionCoeff(friction); return 0; }
+    if (kind == 1) { auto &v = m->model.getTriangleModels(); if (index >= v.size()) return 1; v[index]->setRestitutionCoeff(restitution); v[index]->setFrictionCoeff(friction); return 0; }
+    if (kind == 2) { auto &v = m->model.getTetModels(); if (index >= v.size()) return 1; v[index]->setRestitutionCoeff(restitution); v[index]->setFrictionCoeff(friction); return 0; }
+    return 1;
+}
+void pbdm_set_contact_stiffness_particle_rigid_body(pbdm_model *m, float k) { m->model.setContactStiffnessParticleRigidBody(k); }
+void pbdm_timestep_set_collision_detection(pbdm_timestep *ts, pbdm_model *m, pbdm_collision_detection *cd) {
+    ts->ts.setCollisionDetection(m->model, cd ? &cd->cd : nullptr);
+}
+
 int pbdm_timestep_step(pbdm_timestep *ts, pbdm_model *m) { return ts->ts.step(m->model) ? 0 : 1; }
 const char *pbdm_timestep_error(pbdm_timestep *ts) { return ts->ts.error().c_str(); }
 pbd_engine *pbdm_timestep_engine(pbdm_timestep *ts) { return ts->ts.engine(); }

@@ -96,11 +96,24 @@ PYBIND11_MODULE(pypbd_b200, m) {
     py::class_<TriangleModel>(m, "TriangleModel")
         .def("getIndexOffset", &TriangleModel::getIndexOffset)
         .def("getParticleMesh", [](TriangleModel &t) -> IndexedFaceMesh & { return t.getParticleMesh(); }, py::return_value_policy::reference_internal)
+        .def("getRestitutionCoeff", &TriangleModel::getRestitutionCoeff).def("setRestitutionCoeff", &TriangleModel::setRestitutionCoeff)
+        .def("getFrictionCoeff", &TriangleModel::getFrictionCoeff).def("setFrictionCoeff", &TriangleModel::setFrictionCoeff)
         .def("updateMeshNormals", [](TriangleModel &, const ParticleData &) {});  // rendering helper of the reference: no normals on this path
     py::class_<TetModel>(m, "TetModel")
         .def("getIndexOffset", &TetModel::getIndexOffset)
         .def("getParticleMesh", [](TetModel &t) -> IndexedTetMesh & { return t.getParticleMesh(); }, py::return_value_policy::reference_internal)
+        .def("getRestitutionCoeff", &TetModel::getRestitutionCoeff).def("setRestitutionCoeff", &TetModel::setRestitutionCoeff)
+        .def("getFrictionCoeff", &TetModel::getFrictionCoeff).def("setFrictionCoeff", &TetModel::setFrictionCoeff)
         .def("updateMeshNormals", [](TetModel &, const ParticleData &) {});
+    // RigidBody (Simulation/RigidBody.h): the state the path uses; bodies are created with SimulationModel.addRigidBody below
+    py::class_<RigidBody>(m, "RigidBody")
+        .def("getMass", &RigidBody::getMass)
+        .def("getPosition", [](RigidBody &b) { return to_np(b.getPosition()); })
+        .def("getVelocity", [](RigidBody &b) { return to_np(b.getVelocity()); })
+        .def("getAngularVelocity", [](RigidBody &b) { return to_np(b.getAngularVelocity()); })
+        .def("getRotation", [](RigidBody &b) { const Quaternionr &q = b.getRotation(); return py::make_tuple(q.w, q.x, q.y, q.z); })
+        .def("getRestitutionCoeff", &RigidBody::getRestitutionCoeff).def("setRestitutionCoeff", &RigidBody::setRestitutionCoeff)
+        .def("getFrictionCoeff", &RigidBody::getFrictionCoeff).def("setFrictionCoeff", &RigidBody::setFrictionCoeff);
 
     py::class_<SimulationModel>(m, "SimulationModel")
         .def(py::init<>())
@@ -147,6 +160,20 @@ PYBIND11_MODULE(pypbd_b200, m) {
         .def("addFEMTetConstraint", &SimulationModel::addFEMTetConstraint)
         .def("addFEMTetConstraint_XPBD", &SimulationModel::addFEMTetConstraint_XPBD)
         .def("addStrainTetConstraint", &SimulationModel::addStrainTetConstraint)
+        // RigidBody::initBody(mass, x, inertiaTensor, rotation, ...) without the mesh arguments (the ctypes facade pypbd.py carries the
+        // density / mesh form with its volume integration); returns the body index
+        .def("addRigidBody", [](SimulationModel &s, Real mass, const py::object &x, const py::object &inertia, const py::object &q) {
+                RigidBody *rb = new RigidBody();
+                auto qa = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(q);
+                if (!qa || qa.size() != 4) throw std::invalid_argument("rotation: expected (w, x, y, z)");
+                rb->initBody(mass, vec3(x), vec3(inertia), Quaternionr((Real)qa.data()[0], (Real)qa.data()[1], (Real)qa.data()[2], (Real)qa.data()[3]));
+                s.getRigidBodies().push_back(rb);
+                s.m_groupsInitialized = false; s.rigidBodiesDirty = true;
+                return (unsigned)s.getRigidBodies().size() - 1; },
+             py::arg("mass"), py::arg("x"), py::arg("inertiaTensor"), py::arg("rotation") = py::make_tuple(1.0, 0.0, 0.0, 0.0))
+        .def("getRigidBodies", [](SimulationModel &s) { py::list l; for (RigidBody *b : s.getRigidBodies()) l.append(py::cast(b, py::return_value_policy::reference)); return l; })
+        .def("getContactStiffnessParticleRigidBody", &SimulationModel::getContactStiffnessParticleRigidBody)
+        .def("setContactStiffnessParticleRigidBody", &SimulationModel::setContactStiffnessParticleRigidBody)
         .def("addBallJoint", [](SimulationModel &s, unsigned a, unsigned b, const py::object &p) { return s.addBallJoint(a, b, vec3(p)); })
         .def("addRigidBodyParticleBallJoint", &SimulationModel::addRigidBodyParticleBallJoint)
         .def("initConstraintGroups", &SimulationModel::initConstraintGroups)
@@ -170,13 +197,67 @@ PYBIND11_MODULE(pypbd_b200, m) {
         .def("setSolidStiffness", &SimulationModel::setSolidStiffness).def("setSolidPoissonRatio", &SimulationModel::setSolidPoissonRatio)
         .def("setSolidVolumeStiffness", &SimulationModel::setSolidVolumeStiffness);
 
+    // CollisionDetection / DistanceFieldCollisionDetection (pyPBD/CollisionDetectionModule.cpp): the add* calls of the reference; `vertices` is an
+    // (n, 3) array or None
+    auto verts = [](const py::object &o, std::vector<Vector3r> &v) {
+        v.clear();
+        if (o.is_none()) return;
+        auto a = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(o);
+        if (!a || a.size() % 3) throw std::invalid_argument("vertices: expected an (n, 3) array");
+        for (ssize_t i = 0; i < a.size() / 3; i++) v.emplace_back((Real)a.data()[3 * i], (Real)a.data()[3 * i + 1], (Real)a.data()[3 * i + 2]);
+    };
+    auto vec2 = [](const py::object &o) {
+        auto a = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(o);
+        if (!a || a.size() != 2) throw std::invalid_argument("expected 2 numbers");
+        return Vector2r{{(Real)a.data()[0], (Real)a.data()[1]}};
+    };
+    py::class_<CollisionDetection> cdb(m, "CollisionDetection");
+    cdb.def("getTolerance", &CollisionDetection::getTolerance).def("setTolerance", &CollisionDetection::setTolerance)
+       .def("numCollisionObjects", [](CollisionDetection &c) { return c.getCollisionObjects().size(); })
+       .def("cleanup", &CollisionDetection::cleanup);
+    py::class_<CollisionDetection::CollisionObject> co(cdb, "CollisionObject");
+    co.attr("RigidBodyCollisionObjectType") = (unsigned)CollisionDetection::CollisionObject::RigidBodyCollisionObjectType;
+    co.attr("TriangleModelCollisionObjectType") = (unsigned)CollisionDetection::CollisionObject::TriangleModelCollisionObjectType;
+    co.attr("TetModelCollisionObjectType") = (unsigned)CollisionDetection::CollisionObject::TetModelCollisionObjectType;
+    py::class_<DistanceFieldCollisionDetection, CollisionDetection>(m, "DistanceFieldCollisionDetection")
+        .def(py::init<>())
+        .def("init", [](DistanceFieldCollisionDetection &) {})
+        .def("addCollisionBox", [verts](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &v, unsigned, const py::object &box, bool tm, bool inv) {
+                std::vector<Vector3r> vv; verts(v, vv); c.addCollisionBox(bi, bt, vv.data(), (unsigned)vv.size(), vec3(box), tm, inv); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("box"), py::arg("testMesh") = true, py::arg("invertSDF") = false)
+        .def("addCollisionSphere", [verts](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &v, unsigned, Real r, bool tm, bool inv) {
+                std::vector<Vector3r> vv; verts(v, vv); c.addCollisionSphere(bi, bt, vv.data(), (unsigned)vv.size(), r, tm, inv); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("radius"), py::arg("testMesh") = true, py::arg("invertSDF") = false)
+        .def("addCollisionTorus", [verts, vec2](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &v, unsigned, const py::object &radii, bool tm, bool inv) {
+                std::vector<Vector3r> vv; verts(v, vv); c.addCollisionTorus(bi, bt, vv.data(), (unsigned)vv.size(), vec2(radii), tm, inv); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("radii"), py::arg("testMesh") = true, py::arg("invertSDF") = false)
+        .def("addCollisionCylinder", [verts, vec2](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &v, unsigned, const py::object &dim, bool tm, bool inv) {
+                std::vector<Vector3r> vv; verts(v, vv); c.addCollisionCylinder(bi, bt, vv.data(), (unsigned)vv.size(), vec2(dim), tm, inv); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("dim"), py::arg("testMesh") = true, py::arg("invertSDF") = false)
+        .def("addCollisionHollowSphere", [verts](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &v, unsigned, Real r, Real th, bool tm, bool inv) {
+                std::vector<Vector3r> vv; verts(v, vv); c.addCollisionHollowSphere(bi, bt, vv.data(), (unsigned)vv.size(), r, th, tm, inv); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("radius"), py::arg("thickness"), py::arg("testMesh") = true, py::arg("invertSDF") = false)
+        .def("addCollisionHollowBox", [verts](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &v, unsigned, const py::object &box, Real th, bool tm, bool inv) {
+                std::vector<Vector3r> vv; verts(v, vv); c.addCollisionHollowBox(bi, bt, vv.data(), (unsigned)vv.size(), vec3(box), th, tm, inv); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("box"), py::arg("thickness"), py::arg("testMesh") = true, py::arg("invertSDF") = false)
+        .def("addCollisionObjectWithoutGeometry", [](DistanceFieldCollisionDetection &c, unsigned bi, unsigned bt, const py::object &, unsigned, bool tm) {
+                c.addCollisionObjectWithoutGeometry(bi, bt, nullptr, 0, tm); },
+             py::arg("bodyIndex"), py::arg("bodyType"), py::arg("vertices"), py::arg("numVertices"), py::arg("testMesh"));
+
     py::class_<TimeStepController> ts(m, "TimeStepController");
-    ts.def("init", &TimeStepController::init).def("reset", &TimeStepController::reset)
+    ts.def(py::init([](int device) {
+                auto t = std::unique_ptr<TimeStepController>(new TimeStepController(device));
+                if (!t->valid()) throw std::runtime_error("pypbd_b200: " + t->error() + " (no CPU fallback)");
+                return t; }), py::arg("device") = 0)
+      .def("init", &TimeStepController::init).def("reset", &TimeStepController::reset)
         .def("setValueUInt", [](TimeStepController &t, int id, unsigned v) { if (!t.setValueUInt(id, v)) throw std::invalid_argument("TimeStepController.setValueUInt: bad parameter id or value"); })
         .def("getValueUInt", &TimeStepController::getValueUInt)
         .def("setValueInt", [](TimeStepController &t, int id, int v) { if (!t.setValueInt(id, v)) throw std::invalid_argument("TimeStepController.setValueInt: bad parameter id or value"); })
         .def("getValueInt", &TimeStepController::getValueInt)
         .def("setSolverMode", &TimeStepController::setSolverMode)
+        .def("setCollisionDetection", [](TimeStepController &t, SimulationModel &model, CollisionDetection *cd) { t.setCollisionDetection(model, cd); },
+             py::keep_alive<1, 3>())  // TimeStep::setCollisionDetection: the time step refers to the collision detection
+        .def("getCollisionDetection", &TimeStepController::getCollisionDetection, py::return_value_policy::reference)
         .def("step", [](TimeStepController &t, SimulationModel &model) {  // TimeStepModule.cpp:15-31: the GIL is held for the whole step there too
                 if (!t.step(model)) throw std::runtime_error("pypbd_b200: " + t.error()); });
     ts.attr("NUM_SUB_STEPS") = (int)TimeStepController::NUM_SUB_STEPS;

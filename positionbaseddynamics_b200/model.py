@@ -20,7 +20,10 @@ MODEL_SYMBOLS = [
     "pbdm_tet_get_tets", "pbdm_first_fit_colouring", "pbdm_timestep_create", "pbdm_timestep_destroy", "pbdm_timestep_set_uint",
     "pbdm_timestep_get_uint", "pbdm_timestep_set_int", "pbdm_timestep_get_int", "pbdm_timestep_set_time_step_size",
     "pbdm_timestep_get_time_step_size", "pbdm_timestep_get_time", "pbdm_timestep_set_time", "pbdm_timestep_set_gravitation",
-    "pbdm_timestep_set_mode", "pbdm_timestep_step", "pbdm_timestep_error", "pbdm_timestep_engine"]
+    "pbdm_timestep_set_mode", "pbdm_timestep_step", "pbdm_timestep_error", "pbdm_timestep_engine",
+    "pbdm_cd_create", "pbdm_cd_destroy", "pbdm_cd_set_tolerance", "pbdm_cd_get_tolerance", "pbdm_cd_add_collision_shape",
+    "pbdm_cd_add_collision_object_without_geometry", "pbdm_cd_num_collision_objects", "pbdm_set_contact_coefficients",
+    "pbdm_set_contact_stiffness_particle_rigid_body", "pbdm_timestep_set_collision_detection"]
 
 _F = C.c_float
 _vp = C.c_void_p
@@ -85,6 +88,14 @@ def _l():
         L.pbdm_timestep_get_time.argtypes = one; L.pbdm_timestep_set_time.argtypes = [_vp, _F]
         L.pbdm_timestep_set_gravitation.argtypes = [_vp, _vp]; L.pbdm_timestep_set_mode.argtypes = [_vp, C.c_int]
         L.pbdm_timestep_step.argtypes = [_vp, _vp]; L.pbdm_timestep_error.argtypes = one; L.pbdm_timestep_engine.argtypes = one
+        L.pbdm_cd_create.restype = _vp; L.pbdm_cd_destroy.argtypes = one
+        L.pbdm_cd_set_tolerance.argtypes = [_vp, _F]; L.pbdm_cd_get_tolerance.argtypes = one; L.pbdm_cd_get_tolerance.restype = C.c_float
+        L.pbdm_cd_add_collision_shape.argtypes = [_vp, C.c_uint, C.c_uint, C.c_int, _vp, _F, _vp, C.c_uint, C.c_int, C.c_int]
+        L.pbdm_cd_add_collision_object_without_geometry.argtypes = [_vp, C.c_uint, C.c_uint, C.c_int]
+        L.pbdm_cd_num_collision_objects.argtypes = one; L.pbdm_cd_num_collision_objects.restype = C.c_uint
+        L.pbdm_set_contact_coefficients.argtypes = [_vp, C.c_int, C.c_uint, _F, _F]
+        L.pbdm_set_contact_stiffness_particle_rigid_body.argtypes = [_vp, _F]
+        L.pbdm_timestep_set_collision_detection.argtypes = [_vp, _vp, _vp]
         _configured = True
     return L
 
@@ -98,6 +109,33 @@ def _p(a):
 
 
 NUM_SUB_STEPS, MAX_ITERATIONS, MAX_ITERATIONS_V, VELOCITY_UPDATE_METHOD = 0, 1, 2, 3
+RIGID_BODY_COLLISION_OBJECT, TRIANGLE_MODEL_COLLISION_OBJECT, TET_MODEL_COLLISION_OBJECT = 0, 1, 2  # CollisionObject::*CollisionObjectType
+
+
+class CollisionDetection:
+    """Host mirror of PBD::DistanceFieldCollisionDetection: the registry of collision objects (the tests run on the GPU)."""
+
+    def __init__(self):
+        self._h = _vp(_l().pbdm_cd_create())
+
+    def close(self):
+        if self._h:
+            _l().pbdm_cd_destroy(self._h); self._h = _vp()
+
+    def set_tolerance(self, t): _l().pbdm_cd_set_tolerance(self._h, float(t))
+    def get_tolerance(self): return _l().pbdm_cd_get_tolerance(self._h)
+    def num_collision_objects(self): return _l().pbdm_cd_num_collision_objects(self._h)
+
+    def add_shape(self, body_index, body_type, shape, dims, thickness=0.0, vertices=None, test_mesh=True, invert_sdf=False):
+        d = np.zeros(3, np.float32); dd = np.atleast_1d(np.asarray(dims, dtype=np.float32)); d[:len(dd)] = dd
+        v = _f32(vertices).reshape(-1, 3) if vertices is not None else None
+        if _l().pbdm_cd_add_collision_shape(self._h, int(body_index), int(body_type), int(shape), _p(d), float(thickness), _p(v), 0 if v is None else len(v),
+                                            int(bool(test_mesh)), int(bool(invert_sdf))):
+            raise PbdError("unknown collision shape %r" % (shape,))
+
+    def add_object_without_geometry(self, body_index, body_type, test_mesh=True):
+        _l().pbdm_cd_add_collision_object_without_geometry(self._h, int(body_index), int(body_type), int(bool(test_mesh)))
+
 
 
 def first_fit_colouring(num_bodies, body_off, bodies):
@@ -159,6 +197,14 @@ class HostModel:
         b = np.zeros(4, dtype=np.uint32); b[:len(bodies)] = bodies
         a = np.zeros(8, dtype=np.float32); a[:len(args)] = args
         return _l().pbdm_add_constraint(self._h, ctype, _p(b), _p(a))
+
+    def set_contact_coefficients(self, kind, index, restitution, friction):
+        """kind 0 rigid body, 1 triangle model, 2 tet model (setRestitutionCoeff / setFrictionCoeff of the three classes)."""
+        if _l().pbdm_set_contact_coefficients(self._h, int(kind), int(index), float(restitution), float(friction)):
+            raise PbdError("no such object: kind %d index %d" % (kind, index))
+
+    def set_contact_stiffness_particle_rigid_body(self, k):
+        _l().pbdm_set_contact_stiffness_particle_rigid_body(self._h, float(k))
 
     def add_rigid_body(self, mass, x, inertia, q=(1, 0, 0, 0)):
         return _l().pbdm_add_rigid_body(self._h, float(mass), _p(_f32(x)), _p(_f32(inertia)), _p(_f32(q)))
@@ -321,6 +367,11 @@ class TimeStep:
 
     def set_mode(self, mode):
         _l().pbdm_timestep_set_mode(self._h, int(mode))
+
+    def set_collision_detection(self, model, cd):
+        """TimeStep::setCollisionDetection; cd = None detaches."""
+        self._cd = cd  # keep it alive
+        _l().pbdm_timestep_set_collision_detection(self._h, model._h, cd._h if cd is not None else None)
 
     def step(self, model):
         if _l().pbdm_timestep_step(self._h, model._h):

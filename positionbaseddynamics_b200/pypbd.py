@@ -309,10 +309,45 @@ class TimeStepController:
     def getValueUInt(self, pid): return self._ts.get_uint(pid)
     def setValueInt(self, pid, v): self._ts.set_int(pid, v)
     def getValueInt(self, pid): return self._ts.get_int(pid)
+    def setCollisionDetection(self, model, cd):
+        self._ts.set_collision_detection(model._host, cd._cd if cd is not None else None)
+
     def step(self, model):
         self._ts.step(model._host)
         if Timing.enabled:
             self._ts.sync(); Timing._record(self._ts.stats().last_step_ms)
+
+
+class CollisionObject:
+    RigidBodyCollisionObjectType, TriangleModelCollisionObjectType, TetModelCollisionObjectType = 0, 1, 2
+
+
+class DistanceFieldCollisionDetection:
+    """pyPBD's DistanceFieldCollisionDetection (pyPBD/CollisionDetectionModule.cpp): the add* calls of the reference; the tests and the
+    velocity-level contact solve run on the GPU for particles against static rigid bodies (include/pbd_b200.h "Contact path")."""
+
+    def __init__(self):
+        self._cd = _m.CollisionDetection()
+
+    def init(self): pass
+    def cleanup(self): pass
+    def getTolerance(self): return self._cd.get_tolerance()
+    def setTolerance(self, t): self._cd.set_tolerance(t)
+    def numCollisionObjects(self): return self._cd.num_collision_objects()
+    def addCollisionBox(self, bodyIndex, bodyType, vertices, numVertices, box, testMesh=True, invertSDF=False):
+        self._cd.add_shape(bodyIndex, bodyType, _capi.SHAPE_BOX, box, 0.0, vertices, testMesh, invertSDF)
+    def addCollisionSphere(self, bodyIndex, bodyType, vertices, numVertices, radius, testMesh=True, invertSDF=False):
+        self._cd.add_shape(bodyIndex, bodyType, _capi.SHAPE_SPHERE, [radius], 0.0, vertices, testMesh, invertSDF)
+    def addCollisionTorus(self, bodyIndex, bodyType, vertices, numVertices, radii, testMesh=True, invertSDF=False):
+        self._cd.add_shape(bodyIndex, bodyType, _capi.SHAPE_TORUS, radii, 0.0, vertices, testMesh, invertSDF)
+    def addCollisionCylinder(self, bodyIndex, bodyType, vertices, numVertices, dim, testMesh=True, invertSDF=False):
+        self._cd.add_shape(bodyIndex, bodyType, _capi.SHAPE_CYLINDER, dim, 0.0, vertices, testMesh, invertSDF)
+    def addCollisionHollowSphere(self, bodyIndex, bodyType, vertices, numVertices, radius, thickness, testMesh=True, invertSDF=False):
+        self._cd.add_shape(bodyIndex, bodyType, _capi.SHAPE_HOLLOW_SPHERE, [radius], thickness, vertices, testMesh, invertSDF)
+    def addCollisionHollowBox(self, bodyIndex, bodyType, vertices, numVertices, box, thickness, testMesh=True, invertSDF=False):
+        self._cd.add_shape(bodyIndex, bodyType, _capi.SHAPE_HOLLOW_BOX, box, thickness, vertices, testMesh, invertSDF)
+    def addCollisionObjectWithoutGeometry(self, bodyIndex, bodyType, vertices, numVertices, testMesh):
+        self._cd.add_object_without_geometry(bodyIndex, bodyType, testMesh)
 
 
 class Simulation:

@@ -165,3 +165,44 @@ def test_adapter_runs_the_contact_path(precision, cpu_libs):
     gpu.step(1)
     assert "dynamic collision object" in gpu.gpu_error()
     assert (gpu.get("x") == x1).all()
+
+
+def test_host_mirror_contact_path(cpu_libs):
+    """The same scene through the host mirror of the reference's interface (C++ SimulationModel / TimeStepController /
+    DistanceFieldCollisionDetection of csrc/host/pbd_model.h, driven through include/pbd_b200_model.h): addCollisionBox / Sphere / Torus on static
+    bodies, addCollisionObjectWithoutGeometry for the cloth, TimeStep::setCollisionDetection -- in lockstep with the reference."""
+    if not have_ref("f64"):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_f64.so not present on this box")
+    from positionbaseddynamics_b200 import _capi, model as hm_mod
+    cpu = cpu_libs.CpuPbd("ref", "f64")
+    bodies = scenes.cloth_on_colliders(cpu, 24, shapes=("box", "sphere", "torus"))
+    hm = hm_mod.HostModel()
+    hm.add_regular_triangle_model(24, 24, t=(-2.5, 2.2, -2.5), R=scenes.RX90, scale=(5.0, 5.0))
+    hm.add_cloth_constraints(0, 4, dist_k=1.0e5)
+    hm.add_bending_constraints(0, 3, 100.0)
+    hm.set_params(dt=0.005, sub_steps=1, max_iter=4)
+    rot = np.array([[0.9553365, -0.2955202, 0.0], [0.2955202, 0.9553365, 0.0], [0.0, 0.0, 1.0]])
+    qz = (float(np.cos(0.15)), 0.0, 0.0, float(np.sin(0.15)))  # 0.3 rad about z = `rot`
+    cd = hm_mod.CollisionDetection(); cd.set_tolerance(0.05)
+    spec = [((0.0, -0.5, 0.0), (1, 0, 0, 0), (20.0, 1.0, 20.0), _capi.SHAPE_BOX, (20.0, 1.0, 20.0), 0.2),
+            ((-0.8, 1.2, -0.6), (1, 0, 0, 0), (1.6, 1.6, 1.6), _capi.SHAPE_SPHERE, (0.8,), 0.1),
+            ((1.2, 1.0, 0.8), qz, (2.4, 0.8, 2.4), _capi.SHAPE_TORUS, (0.8, 0.4), 0.1)]
+    for x, q, scale, shape, dims, friction in spec:
+        i = hm.add_rigid_body(0.0, x, (1.0, 1.0, 1.0), q)
+        hm.set_contact_coefficients(0, i, 0.6, friction)
+        cd.add_shape(i, hm_mod.RIGID_BODY_COLLISION_OBJECT, shape, dims, 0.05, vertices=scenes.BOX_VERTS * np.array(scale))
+    hm.set_contact_coefficients(1, 0, 0.5, 0.1)
+    cd.add_object_without_geometry(0, hm_mod.TRIANGLE_MODEL_COLLISION_OBJECT, True)
+    hm.set_contact_stiffness_particle_rigid_body(100.0)
+    ts = hm.time_step(device=0)
+    ts.set_collision_detection(hm, cd)
+    def step_gpu(x, v):
+        hm.set("x", x); hm.set("v", v); hm.step(1)
+    events, seen, grazing, worst_x, worst_dv = _lockstep(step_gpu, lambda: (hm.get("x"), hm.get("v")), cpu, 120)
+    print("host mirror + contact path: %d contact events on bodies %s, %d grazing, worst rel pos %.2e, worst |dv| %.2e m/s" % (events, sorted(seen), grazing, worst_x, worst_dv))
+    assert events > 1000 and len(seen) == 3 and grazing <= 3
+    # a dynamic collision body is refused with the reference-style bool + error
+    hm.set_rigid_body_mass(1, 2.0)
+    with pytest.raises(hm_mod.PbdError, match="dynamic collision object"):
+        hm.step(1)
+    hm.close(); cd.close()

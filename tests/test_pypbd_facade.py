@@ -271,3 +271,78 @@ def test_compiled_pybind_module_steps_like_the_facade():
     assert np.isfinite(x1).all() and (x1 == x2).all()
     assert abs(native.TimeManager.getCurrent().getTime() - 0.02) < 1e-6
     assert (x1[0] == [0.0, 1.0, 0.0]).all() or np.allclose(x1[0], model.getParticles().getPosition0(0))  # pinned corner
+
+
+def test_collision_registry_in_both_python_surfaces():
+    """DistanceFieldCollisionDetection with the reference's add* signatures (pyPBD/CollisionDetectionModule.cpp) in the compiled module and in
+    the ctypes facade: construction and bookkeeping need no GPU."""
+    import importlib, os, sys
+    import positionbaseddynamics_b200.pypbd as pbd
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "positionbaseddynamics_b200")
+    sys.path.insert(0, pkg)
+    try:
+        native = importlib.import_module("pypbd_b200")
+    finally:
+        sys.path.remove(pkg)
+    for mod, rigid in ((native, native.CollisionDetection.CollisionObject.RigidBodyCollisionObjectType), (pbd, pbd.CollisionObject.RigidBodyCollisionObjectType)):
+        cd = mod.DistanceFieldCollisionDetection(); cd.init()
+        assert abs(cd.getTolerance() - 0.01) < 1e-7   # CollisionDetection.cpp:25
+        cd.setTolerance(0.05)
+        box = np.array([[-1, -1, -1], [1, 1, 1.0]])
+        cd.addCollisionBox(0, rigid, box, 2, [2.0, 2.0, 2.0])
+        cd.addCollisionSphere(1, rigid, None, 0, 0.5, True, False)
+        cd.addCollisionTorus(2, rigid, None, 0, [1.0, 0.25])
+        cd.addCollisionCylinder(3, rigid, None, 0, [0.5, 2.0])
+        cd.addCollisionHollowSphere(4, rigid, None, 0, 1.0, 0.1)
+        cd.addCollisionHollowBox(5, rigid, None, 0, [1.0, 1.0, 1.0], 0.1)
+        cd.addCollisionObjectWithoutGeometry(0, 1, None, 0, True)
+        assert cd.numCollisionObjects() == 7 and abs(cd.getTolerance() - 0.05) < 1e-7
+
+
+@pytest.mark.gpu
+def test_compiled_pybind_module_runs_the_contact_path():
+    """Cloth dropped on a static sphere through the compiled module (the flow of Demos/DistanceFieldDemos/ClothCollisionDemo.cpp in pyPBD
+    names): the sheet wraps the sphere instead of falling through it, and a dynamic collision body is refused with an exception."""
+    import importlib, os, sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "positionbaseddynamics_b200")
+    sys.path.insert(0, pkg)
+    try:
+        native = importlib.import_module("pypbd_b200")
+    finally:
+        sys.path.remove(pkg)
+    a = math.pi / 2
+    R = [[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]]
+    def run(with_collider):
+        model = native.SimulationModel()
+        tm = model.addRegularTriangleModel(30, 30, [-1.5, 1.5, -1.5], R, [3.0, 3.0])
+        model.addClothConstraints(tm, 4, 1.0e5, 1.0, 1.0, 1.0, 0.3, 0.3, False, False)
+        model.addBendingConstraints(tm, 3, 100.0)
+        rb = model.addRigidBody(0.0, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+        ts = native.TimeStepController(0)
+        ts.setValueUInt(native.TimeStepController.NUM_SUB_STEPS, 1); ts.setValueUInt(native.TimeStepController.MAX_ITERATIONS, 5)
+        cd = native.DistanceFieldCollisionDetection(); cd.setTolerance(0.05)
+        if with_collider:
+            T = native.CollisionDetection.CollisionObject
+            cd.addCollisionSphere(rb, T.RigidBodyCollisionObjectType, None, 0, 1.0)
+            cd.addCollisionObjectWithoutGeometry(0, T.TriangleModelCollisionObjectType, None, 0, True)
+            ts.setCollisionDetection(model, cd)
+        for _ in range(200):
+            ts.step(model)
+        return np.array(model.getParticles().getVertices()).copy(), model, ts
+    x_free, _, _ = run(False)
+    x_hit, model, ts = run(True)
+    r_free = np.linalg.norm(x_free, axis=1).min(); r_hit = np.linalg.norm(x_hit, axis=1).min()
+    print("closest particle to the sphere centre: %.3f without the collider, %.3f with it (radius 1)" % (r_free, r_hit))
+    assert x_free[:, 1].max() < -1.0                     # fell straight through
+    assert r_hit > 0.9 and x_hit[:, 1].max() > 0.5       # held up by the sphere
+    model.getRigidBodies()[0]  # the body object is reachable
+    # dynamic collision body: refused
+    model2 = native.SimulationModel()
+    tm = model2.addRegularTriangleModel(10, 10, [-1.5, 1.5, -1.5], R, [3.0, 3.0])
+    model2.addClothConstraints(tm, 4, 1.0e5, 1.0, 1.0, 1.0, 0.3, 0.3, False, False)
+    rb = model2.addRigidBody(2.0, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+    cd = native.DistanceFieldCollisionDetection()
+    cd.addCollisionSphere(rb, 0, None, 0, 1.0); cd.addCollisionObjectWithoutGeometry(0, 1, None, 0, True)
+    ts2 = native.TimeStepController(0); ts2.setCollisionDetection(model2, cd)
+    with pytest.raises(RuntimeError, match="dynamic collision object"):
+        ts2.step(model2)
