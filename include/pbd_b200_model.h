@@ -105,6 +105,10 @@ unsigned pbdm_cd_num_collision_objects(pbdm_collision_detection *cd);
 /* restitution / friction coefficients of a rigid body (kind 0), triangle model (1) or tet model (2): set*Coeff of the three classes */
 int pbdm_set_contact_coefficients(pbdm_model *m, int kind, unsigned index, float restitution, float friction);
 void pbdm_set_contact_stiffness_particle_rigid_body(pbdm_model *m, float stiffness);  /* SimulationModel.h:253-254 */
+/* Frame of a body's geometry relative to the body frame (the reference's m_q_mat / m_x0_mat, RigidBody.h:172-188): distance fields on
+ * the body are evaluated at x_local = R * R(q)^T (x_world - x) + t.  R row-major 3x3 (principal-axes matrix), t = centre of mass in the
+ * geometry's coordinates; identity / zero by default. */
+int pbdm_set_rigid_body_geometry_frame(pbdm_model *m, unsigned i, const float *R9, const float *t3);
 
 pbdm_timestep *pbdm_timestep_create(int device, void *stream);  /* NULL + pbd_last_error() when no CUDA device */
 void pbdm_timestep_destroy(pbdm_timestep *ts);

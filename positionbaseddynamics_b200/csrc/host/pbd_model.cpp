@@ -910,18 +910,23 @@ bool TimeStepController::uploadColliders(SimulationModel &model) {
             rc.shape = co.shape; rc.body = co.m_bodyIndex; rc.thickness = co.thickness; rc.invert_sdf = 0;
             for (int k = 0; k < 3; k++) rc.dim[k] = co.dim[k];
             rc.restitution = rb.getRestitutionCoeff(); rc.friction = rb.getFrictionCoeff();
-            // bodies of this mirror have no principal-axis / initial transformation: x_local = R(q)^T (x_w - x), x_w = R(q) x_local + x
+            // x_local = frameR * R(q)^T (x_w - x) + frameT  (RigidBody::updateInverseTransformation, RigidBody.h:172-188)
             const Quaternionr &q = rb.getRotation();
-            const Real R[9] = {1 - 2 * (q.y * q.y + q.z * q.z), 2 * (q.x * q.y - q.w * q.z), 2 * (q.x * q.z + q.w * q.y),
-                               2 * (q.x * q.y + q.w * q.z), 1 - 2 * (q.x * q.x + q.z * q.z), 2 * (q.y * q.z - q.w * q.x),
-                               2 * (q.x * q.z - q.w * q.y), 2 * (q.y * q.z + q.w * q.x), 1 - 2 * (q.x * q.x + q.y * q.y)};
-            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rc.R[3 * r + c] = R[3 * c + r];  // transformation R = R(q)^T
-            for (int k = 0; k < 3; k++) { rc.v1[k] = 0.0f; rc.v2[k] = rb.getPosition()[k]; }
+            const Real Rq[9] = {1 - 2 * (q.y * q.y + q.z * q.z), 2 * (q.x * q.y - q.w * q.z), 2 * (q.x * q.z + q.w * q.y),
+                                2 * (q.x * q.y + q.w * q.z), 1 - 2 * (q.x * q.x + q.z * q.z), 2 * (q.y * q.z - q.w * q.x),
+                                2 * (q.x * q.z - q.w * q.y), 2 * (q.y * q.z + q.w * q.x), 1 - 2 * (q.x * q.x + q.y * q.y)};
+            Real T[9];  // transformation R = frameR * R(q)^T
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { Real a = 0; for (int k = 0; k < 3; k++) a += rb.m_frameR.m[3 * r + k] * Rq[3 * c + k]; T[3 * r + c] = a; }
+            for (int k = 0; k < 9; k++) rc.R[k] = T[k];
+            for (int k = 0; k < 3; k++) {
+                rc.v1[k] = rb.m_frameT[k];
+                rc.v2[k] = rb.getPosition()[k] - (T[k] * rb.m_frameT[0] + T[3 + k] * rb.m_frameT[1] + T[6 + k] * rb.m_frameT[2]);  // x - T^T frameT
+            }
             // bounding box: the object's vertices in world space (CollisionDetection::updateAABB), else the shape's own box
             Real lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-            auto extend = [&](const Real v[3]) {
+            auto extend = [&](const Real v[3]) {  // x_w = T^T v + v2
                 for (int r = 0; r < 3; r++) {
-                    const Real w = R[3 * r] * v[0] + R[3 * r + 1] * v[1] + R[3 * r + 2] * v[2] + rb.getPosition()[r];
+                    const Real w = T[r] * v[0] + T[3 + r] * v[1] + T[6 + r] * v[2] + rc.v2[r];
                     lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
                 }
             };

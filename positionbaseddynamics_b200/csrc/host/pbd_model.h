@@ -185,6 +185,11 @@ public:
     Real getFrictionCoeff() const { return m_frictionCoeff; }
     void setFrictionCoeff(Real v) { m_frictionCoeff = v; }
     Real m_restitutionCoeff = static_cast<Real>(0.6), m_frictionCoeff = static_cast<Real>(0.2);
+    // Frame of the body's geometry (what the reference keeps as m_x0_mat / m_q_mat / m_q_initial, RigidBody.h:172-188): a distance field
+    // attached to the body is evaluated at  x_local = frameR * R(q)^T (x_world - x) + frameT.  Identity / zero for bodies created in their
+    // own frame; a body moved to its centre of mass and principal axes sets the principal-axes matrix and the centre of mass here.
+    Matrix3r m_frameR = Matrix3r::Identity();
+    Vector3r m_frameT;
     Real m_mass = 0, m_invMass = 0;
     Vector3r m_x, m_x0, m_v, m_omega, m_inertiaTensor;
     Quaternionr m_q, m_q0;

@@ -274,6 +274,13 @@ int pbdm_set_contact_coefficients(pbdm_model *m, int kind, unsigned index, float
     if (kind == 2) { auto &v = m->model.getTetModels(); if (index >= v.size()) return 1; v[index]->setRestitutionCoeff(restitution); v[index]->setFrictionCoeff(friction); return 0; }
     return 1;
 }
+int pbdm_set_rigid_body_geometry_frame(pbdm_model *m, unsigned i, const float *R9, const float *t3) {
+    auto &v = m->model.getRigidBodies();
+    if (i >= v.size() || !R9 || !t3) return 1;
+    std::memcpy(v[i]->m_frameR.m, R9, sizeof(v[i]->m_frameR.m));
+    v[i]->m_frameT = Vector3r(t3[0], t3[1], t3[2]);
+    return 0;
+}
 void pbdm_set_contact_stiffness_particle_rigid_body(pbdm_model *m, float k) { m->model.setContactStiffnessParticleRigidBody(k); }
 void pbdm_timestep_set_collision_detection(pbdm_timestep *ts, pbdm_model *m, pbdm_collision_detection *cd) {
     ts->ts.setCollisionDetection(m->model, cd ? &cd->cd : nullptr);

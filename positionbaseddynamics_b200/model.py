@@ -23,7 +23,7 @@ MODEL_SYMBOLS = [
     "pbdm_timestep_set_mode", "pbdm_timestep_step", "pbdm_timestep_error", "pbdm_timestep_engine",
     "pbdm_cd_create", "pbdm_cd_destroy", "pbdm_cd_set_tolerance", "pbdm_cd_get_tolerance", "pbdm_cd_add_collision_shape",
     "pbdm_cd_add_collision_object_without_geometry", "pbdm_cd_num_collision_objects", "pbdm_set_contact_coefficients",
-    "pbdm_set_contact_stiffness_particle_rigid_body", "pbdm_timestep_set_collision_detection"]
+    "pbdm_set_contact_stiffness_particle_rigid_body", "pbdm_timestep_set_collision_detection", "pbdm_set_rigid_body_geometry_frame"]
 
 _F = C.c_float
 _vp = C.c_void_p
@@ -96,6 +96,7 @@ def _l():
         L.pbdm_set_contact_coefficients.argtypes = [_vp, C.c_int, C.c_uint, _F, _F]
         L.pbdm_set_contact_stiffness_particle_rigid_body.argtypes = [_vp, _F]
         L.pbdm_timestep_set_collision_detection.argtypes = [_vp, _vp, _vp]
+        L.pbdm_set_rigid_body_geometry_frame.argtypes = [_vp, C.c_uint, _vp, _vp]
         _configured = True
     return L
 
@@ -202,6 +203,11 @@ class HostModel:
         """kind 0 rigid body, 1 triangle model, 2 tet model (setRestitutionCoeff / setFrictionCoeff of the three classes)."""
         if _l().pbdm_set_contact_coefficients(self._h, int(kind), int(index), float(restitution), float(friction)):
             raise PbdError("no such object: kind %d index %d" % (kind, index))
+
+    def set_rigid_body_geometry_frame(self, i, R, t):
+        """Frame of the body's geometry (principal-axes matrix R, centre of mass t in geometry coordinates): x_local = R R(q)^T (x_w - x) + t."""
+        if _l().pbdm_set_rigid_body_geometry_frame(self._h, int(i), _p(_f32(R).reshape(3, 3)), _p(_f32(t))):
+            raise PbdError("rigid body index %d out of range" % i)
 
     def set_contact_stiffness_particle_rigid_body(self, k):
         _l().pbdm_set_contact_stiffness_particle_rigid_body(self._h, float(k))

@@ -70,14 +70,33 @@ class _Mesh:
     def getEdges(self): return self._h.tri_edges(self._i) if self._tri else self._h.tet_edges(self._i)
 
 
-class TriangleModel:
+class _Coefficients:
+    """setRestitutionCoeff / setFrictionCoeff of RigidBody, TriangleModel and TetModel (defaults 0.6 / 0.2 as in the reference)."""
+    _kind = 0
+
+    def _coeffs(self):
+        return self._h.__dict__.setdefault("_contact_coeffs", {}).setdefault((self._kind, self._i), [0.6, 0.2])
+
+    def getRestitutionCoeff(self): return self._coeffs()[0]
+    def getFrictionCoeff(self): return self._coeffs()[1]
+
+    def setRestitutionCoeff(self, v):
+        c = self._coeffs(); c[0] = float(v); self._h.set_contact_coefficients(self._kind, self._i, c[0], c[1])
+
+    def setFrictionCoeff(self, v):
+        c = self._coeffs(); c[1] = float(v); self._h.set_contact_coefficients(self._kind, self._i, c[0], c[1])
+
+
+class TriangleModel(_Coefficients):
+    _kind = 1
     def __init__(self, host, idx): self._h, self._i = host, idx
     def getIndexOffset(self): return self._h.tri_index_offset(self._i)
     def getParticleMesh(self): return _Mesh(self._h, self._i, True)
     def updateMeshNormals(self, pd): pass  # rendering helper of the reference; no normals are kept on this path
 
 
-class TetModel:
+class TetModel(_Coefficients):
+    _kind = 2
     def __init__(self, host, idx): self._h, self._i = host, idx
     def getIndexOffset(self): return self._h.tet_index_offset(self._i)
     def getParticleMesh(self): return _Mesh(self._h, self._i, False)
@@ -101,7 +120,7 @@ def mass_properties(vertices, faces, density):
     return density * vol, com, inertia
 
 
-class RigidBody:
+class RigidBody(_Coefficients):
     """View of one rigid body of the model (pyPBD RigidBodyModule.cpp subset: what the coupling example touches)."""
     def __init__(self, host, idx): self._h, self._i = host, idx
     def _row(self): return self._h.rigid_bodies()[self._i]
@@ -193,6 +212,7 @@ class SimulationModel:
             r = math.sqrt(1.0 + Rw[i, i] - Rw[j, j] - Rw[k, k]); q[1 + i] = 0.5 * r; r = 0.5 / r
             q[0] = (Rw[k, j] - Rw[j, k]) * r; q[1 + j] = (Rw[j, i] + Rw[i, j]) * r; q[1 + k] = (Rw[k, i] + Rw[i, k]) * r
         idx = self._host.add_rigid_body(mass, x, w, q / np.linalg.norm(q))
+        self._host.set_rigid_body_geometry_frame(idx, R, com)  # distance fields on the body live in the mesh's coordinates
         return RigidBody(self._host, idx)
 
     def getRigidBodies(self): return [RigidBody(self._host, i) for i in range(len(self._host.rigid_bodies()))]

@@ -96,6 +96,13 @@ def test_example_scripts_run():
             assert (out[name][i] == np.asarray(pd.getPosition0(i), dtype=np.float32)).all()
         assert out[name][:, 1].min() < -1e-3               # the rest sags under gravity
     assert pbd.Timing.averageStepMs() > 0.0
+    # examples/cloth_collision.py (Demos/DistanceFieldDemos/ClothCollisionDemo.cpp in pyPBD names): the cloth ends up draped over the
+    # torus and resting on the floor, not below it
+    pbd.Simulation._current = None
+    spec = importlib.util.spec_from_file_location("cloth_collision", os.path.join(root, "cloth_collision.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    x = mod.main(frames=50)
+    assert np.isfinite(x).all() and x[:, 1].min() > -0.2 and x[:, 1].max() > 1.5
 
 
 CUBE_V = np.array([[-0.5, -0.5, -0.5], [0.5, -0.5, -0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, -0.5],
