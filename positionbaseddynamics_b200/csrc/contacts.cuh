@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(128) k_contacts(const ContactArgs A) {
     const unsigned particle = pc.offset + (gid - A.rangeStart[r]);
     const unsigned slot = A.slot[particle];
     const float4 X = A.pos[slot];
-    float4 V = A.vel[slot];
-    const float invMass0 = X.w, mass0 = V.w;
+    float4 V; bool haveV = false;  // the velocity is fetched for candidates only: most particles leave after the bounding-box tests
+    const float invMass0 = X.w;
 
     LiveContact live[kMaxRigidColliders];
     unsigned nLive = 0;
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128) k_contacts(const ContactArgs A) {
         const RigidCollider &c = A.rigid[k];
         // candidates outside the collider's (tolerance-extended) bounding box never reach collisionTest in the reference either
         if (X.x < c.aabbMin[0] || X.y < c.aabbMin[1] || X.z < c.aabbMin[2] || X.x > c.aabbMax[0] || X.y > c.aabbMax[1] || X.z > c.aabbMax[2]) continue;
+        if (!haveV) { V = A.vel[slot]; haveV = true; }
         const float4 com = A.rbX[c.body];
         const float d[3] = {X.x - com.x, X.y - com.y, X.z - com.z};
         float xl[3], cp[3], nl[3], dist;
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(128) k_contacts(const ContactArgs A) {
         nLive++;
     }
     if (nLive == 0 || invMass0 == 0.0f) return;  // velocitySolve returns false when both sides are static
+    const float mass0 = V.w;
 
     for (unsigned it = 0; it < A.maxIterV; it++) {
         for (unsigned k = 0; k < nLive; k++) {

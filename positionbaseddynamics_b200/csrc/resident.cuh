@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_step_resident(const __grid_const
     for (unsigned c = threadIdx.x; c < A.nColours; c += THREADS) {  // rotations: bucket k of a colour starts where bucket k-1 ended
         unsigned accR = 0;
         for (unsigned bi = sColour[c]; bi < sColour[c + 1]; bi++) {
-            runs[bi].rotR = accR % RT; accR += runs[bi].nR;
+            runs[bi].rotR = (accR % RT) & ~7u; accR += runs[bi].nR;  // multiple of 8: the quarter-warps of a run stay aligned with its item order
         }
     }
     __syncthreads();
