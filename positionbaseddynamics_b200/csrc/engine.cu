@@ -920,7 +920,6 @@ static int flatten_image(pbd_engine *e) {
     std::vector<unsigned> tileOff;
     std::vector<unsigned> &tileOf = pl.tileOf;
     if (tiled) CKE(prepare_resident(e, pl));
-    const bool sigSort = tiled && (sigSortEnv >= 0 ? sigSortEnv != 0 : (e->resMask == kMaskFem || e->resMask == kMaskSolid));
     else if (e->slotIsTiled) {
         std::vector<unsigned> m;
         formula_slot_map(e, m);
@@ -933,6 +932,7 @@ static int flatten_image(pbd_engine *e) {
     // order of the items inside a run by kind of element (see the sort key below): measured +2.8 % on the tet scenes (cfg3 7.69 -> 7.47 ms),
     // -3.6 % on the cloth scenes (cfg2 1.98 -> 2.05 ms), so it is on for the solid instantiations only; PBD_B200_SIGSORT=0/1 forces it
     static const int sigSortEnv = [] { const char *g = getenv("PBD_B200_SIGSORT"); return g ? (atoi(g) != 0 ? 1 : 0) : -1; }();
+    const bool sigSort = tiled && (sigSortEnv >= 0 ? sigSortEnv != 0 : (e->resMask == kMaskFem || e->resMask == kMaskSolid));
     std::vector<unsigned> order[PBD_NUM_TYPES];  // device position -> local host index
     e->buckets.clear();
     std::vector<unsigned> tmp[PBD_NUM_TYPES];
