@@ -51,10 +51,11 @@ extern "C" const char *pbd_last_error(void) { return g_err.c_str(); }
 // ------------------------------------------------------------------------------------------------------------
 // engine state
 // ------------------------------------------------------------------------------------------------------------
+using pbd_b200::PodVector;        // std::vector whose resize() does not zero (filled from all threads right after)
 struct HostType {                 // constraints of one type as handed in through pbd_add_constraints
-    std::vector<unsigned> ids;    // insertion index in the reference's m_constraints
-    std::vector<unsigned> bodies; // nBodies per constraint
-    std::vector<float> params;    // nParams per constraint (reference layout)
+    PodVector<unsigned> ids;      // insertion index in the reference's m_constraints
+    PodVector<unsigned> bodies;   // nBodies per constraint
+    PodVector<float> params;      // nParams per constraint (reference layout)
 };
 
 struct DevBuf {
@@ -123,6 +124,7 @@ struct pbd_engine {
     } pipe;
     // contact path (contacts.cuh): colliders, parameters, optional record of the last step's contacts
     std::vector<float> rbMass;
+    std::vector<int> scratchInt;
     std::vector<ParticleCollider> pColliders;
     std::vector<RigidCollider> rColliders;
     DevBuf dPColliders, dRColliders, dRangeStart, dContacts, dContactCount;
@@ -381,7 +383,8 @@ extern "C" int pbd_get_rigid_bodies(pbd_engine *e, float *x, float *q, float *v,
     return 0;
 }
 
-template <typename T> static int upload_vec(DevBuf &buf, const std::vector<T> &v, cudaStream_t s) {
+template <class V> static int upload_vec(DevBuf &buf, const V &v, cudaStream_t s) {  // V: std::vector / PodVector of PODs
+    typedef typename V::value_type T;
     if (v.empty()) return 0;
     if (buf.alloc(v.size() * sizeof(T) + 16)) return 1;
     cudaError_t e = cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
@@ -408,15 +411,33 @@ extern "C" int pbd_add_constraints(pbd_engine *e, int type, unsigned count, cons
     if (type < 0 || type >= PBD_NUM_TYPES) return fail("pbd_add_constraints: unknown constraint type %d", type);
     if (count && (!bodies || !params)) return fail("pbd_add_constraints: null arrays");
     const TypeShape s = type_shape(type);
-    for (size_t i = 0; i < (size_t)count * s.nBodies; i++) {
-        const bool isRb = (type == PBD_BALLJOINT) || (type == PBD_RB_PARTICLE_BALLJOINT && (i % 2) == 0);
-        if (isRb) { if (bodies[i] >= e->nRb) return fail("pbd_add_constraints: rigid-body index %u out of range (%u bodies; call pbd_set_rigid_bodies first)", bodies[i], e->nRb); }
-        else if (bodies[i] >= e->n) return fail("pbd_add_constraints: particle index %u out of range (n=%u)", bodies[i], e->n);
+    {   // index validation, all threads (millions of indices for a big cloth)
+        const size_t nIdx = (size_t)count * s.nBodies;
+        long long badAt = -1;
+        #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : badAt) if (nIdx > 100000)
+        for (long long i = 0; i < (long long)nIdx; i++) {
+            const bool isRb = (type == PBD_BALLJOINT) || (type == PBD_RB_PARTICLE_BALLJOINT && (i % 2) == 0);
+            if (bodies[i] >= (isRb ? e->nRb : e->n)) badAt = std::max(badAt, i);
+        }
+        if (badAt >= 0) {
+            const bool isRb = (type == PBD_BALLJOINT) || (type == PBD_RB_PARTICLE_BALLJOINT && (badAt % 2) == 0);
+            if (isRb) return fail("pbd_add_constraints: rigid-body index %u out of range (%u bodies; call pbd_set_rigid_bodies first)", bodies[badAt], e->nRb);
+            return fail("pbd_add_constraints: particle index %u out of range (n=%u)", bodies[badAt], e->n);
+        }
     }
     HostType &h = e->host[type];
-    for (unsigned i = 0; i < count; i++) h.ids.push_back(ids ? ids[i] : e->numConstraints + i);
-    h.bodies.insert(h.bodies.end(), bodies, bodies + (size_t)count * s.nBodies);
-    h.params.insert(h.params.end(), params, params + (size_t)count * s.nParams);
+    {
+        const size_t b0 = h.ids.size();
+        h.ids.resize(b0 + count); h.bodies.resize((b0 + count) * s.nBodies); h.params.resize((b0 + count) * s.nParams);  // uninitialised, filled below
+        unsigned *idDst = h.ids.data() + b0, *bDst = h.bodies.data() + b0 * s.nBodies; float *pDst = h.params.data() + b0 * s.nParams;
+        const unsigned firstId = e->numConstraints;
+        #pragma omp parallel for schedule(static) num_threads(host_threads()) if (count > 50000)
+        for (long long i = 0; i < (long long)count; i++) {
+            idDst[i] = ids ? ids[i] : firstId + (unsigned)i;
+            std::memcpy(bDst + (size_t)i * s.nBodies, bodies + (size_t)i * s.nBodies, sizeof(unsigned) * s.nBodies);
+            std::memcpy(pDst + (size_t)i * s.nParams, params + (size_t)i * s.nParams, sizeof(float) * s.nParams);
+        }
+    }
     e->numConstraints += count;
     e->groupsSet = false;  // any add invalidates the groups (SimulationModel: m_groupsInitialized = false)
     e->imageDirty = true; e->autoNoResident = false;
@@ -426,17 +447,24 @@ extern "C" int pbd_add_constraints(pbd_engine *e, int type, unsigned count, cons
 // insertion id -> (type, local index); verifies that the ids form a permutation of 0..N-1
 static int build_id_map(pbd_engine *e, std::vector<std::pair<int, unsigned>> &map) {
     const unsigned N = e->numConstraints;
-    map.assign(N, std::make_pair(-1, 0u));
+    map.resize(N);
+    std::vector<int> &seenType = e->scratchInt; seenType.resize(N);
+    #pragma omp parallel for schedule(static) num_threads(host_threads())
+    for (long long i = 0; i < (long long)N; i++) seenType[i] = -1;
     for (int t = 0; t < PBD_NUM_TYPES; t++) {
         const HostType &h = e->host[t];
-        for (unsigned i = 0; i < h.ids.size(); i++) {
+        long long bad = -1; int dup = 0;
+        #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : bad) reduction(| : dup) if (h.ids.size() > 50000)
+        for (long long i = 0; i < (long long)h.ids.size(); i++) {
             const unsigned id = h.ids[i];
-            if (id >= N) return fail("constraint id %u out of range (N=%u)", id, N);
-            if (map[id].first != -1) return fail("constraint id %u used twice", id);
-            map[id] = std::make_pair(t, i);
+            if (id >= N) { bad = std::max(bad, (long long)id); continue; }
+            if (__atomic_exchange_n(&seenType[id], t, __ATOMIC_RELAXED) != -1) { dup = 1; bad = std::max(bad, (long long)id); continue; }
+            map[id] = std::make_pair(t, (unsigned)i);
         }
+        if (bad >= 0 && !dup) return fail("constraint id %u out of range (N=%u)", (unsigned)bad, N);
+        if (dup) return fail("constraint id %u used twice", (unsigned)bad);
     }
-    return 0;
+    return 0;  // N ids, all below N, none twice: a permutation
 }
 
 extern "C" int pbd_set_groups(pbd_engine *e, unsigned nGroups, const unsigned *offsets, const unsigned *ids) {
@@ -465,26 +493,60 @@ static int build_id_csr(pbd_engine *e, std::vector<unsigned> &off, std::vector<u
     std::vector<std::pair<int, unsigned>> map;
     CKE(build_id_map(e, map));
     const unsigned N = e->numConstraints;
-    off.assign(N + 1, 0u);
-    bodies.clear(); bodies.reserve((size_t)N * 4);
-    for (unsigned id = 0; id < N; id++) {
+    off.resize((size_t)N + 1);
+    // off = exclusive prefix sum of the body counts (chunked two-pass scan), then every constraint copies its bodies
+    const int T = std::max(1, host_threads());
+    std::vector<unsigned long long> chunk((size_t)T + 1, 0ull);
+    #pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        const size_t lo = (size_t)N * t / nt, hi = (size_t)N * (t + 1) / nt;
+        unsigned long long sum = 0;
+        for (size_t id = lo; id < hi; id++) sum += (unsigned)type_shape(map[id].first).nBodies;
+        chunk[(size_t)t + 1] = sum;
+        #pragma omp barrier
+        #pragma omp single
+        for (int k = 0; k < nt; k++) chunk[(size_t)k + 1] += chunk[k];
+        unsigned long long run = chunk[t];
+        for (size_t id = lo; id < hi; id++) { off[id] = (unsigned)run; run += (unsigned)type_shape(map[id].first).nBodies; }
+        if (t == nt - 1) off[N] = (unsigned)run;
+    }
+    if (N == 0) off[0] = 0;
+    bodies.resize(off[N]);
+    #pragma omp parallel for schedule(static) num_threads(T)
+    for (long long id = 0; id < (long long)N; id++) {
         const int t = map[id].first;
         const int nb = type_shape(t).nBodies;
-        const unsigned *b = &e->host[t].bodies[(size_t)map[id].second * nb];
-        bodies.insert(bodies.end(), b, b + nb);
-        off[id + 1] = (unsigned)bodies.size();
+        std::memcpy(&bodies[off[id]], &e->host[t].bodies[(size_t)map[id].second * nb], sizeof(unsigned) * nb);
     }
     return 0;
 }
 // colour per constraint -> groups in insertion order (what SimulationModel::getConstraintGroups holds)
 static void groups_from_colours(pbd_engine *e, const std::vector<unsigned> &colour, unsigned nColours) {
     const unsigned N = e->numConstraints;
-    std::vector<unsigned> goff(nColours + 1, 0);
-    for (unsigned id = 0; id < N; id++) goff[colour[id] + 1]++;
-    for (unsigned c = 0; c < nColours; c++) goff[c + 1] += goff[c];
-    std::vector<unsigned> cur(goff.begin(), goff.end() - 1), ids(N);
-    for (unsigned id = 0; id < N; id++) ids[cur[colour[id]]++] = id;
-    e->groupOff = goff; e->groupIds = ids;
+    // stable counting sort by colour: per-thread histograms over contiguous id ranges, then every thread scatters its range
+    const int T = std::max(1, host_threads());
+    std::vector<unsigned> hist((size_t)T * nColours, 0u), goff(nColours + 1, 0u);
+    e->groupIds.resize(N);
+    #pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        const size_t lo = (size_t)N * t / nt, hi = (size_t)N * (t + 1) / nt;
+        unsigned *h = &hist[(size_t)t * nColours];
+        for (size_t id = lo; id < hi; id++) h[colour[id]]++;
+        #pragma omp barrier
+        #pragma omp single
+        {
+            unsigned run = 0;
+            for (unsigned c = 0; c < nColours; c++) {
+                goff[c] = run;
+                for (int k = 0; k < nt; k++) { const unsigned cntk = hist[(size_t)k * nColours + c]; hist[(size_t)k * nColours + c] = run; run += cntk; }
+            }
+            goff[nColours] = run;
+        }
+        for (size_t id = lo; id < hi; id++) e->groupIds[h[colour[id]]++] = (unsigned)id;
+    }
+    e->groupOff = goff;
     e->groupsSet = true; e->imageDirty = true;
 }
 
@@ -555,7 +617,8 @@ extern "C" int pbd_color_first_fit_device(pbd_engine *e, float *ms, unsigned *wa
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (cnt[2] != N) return fail("device colouring: coloured %u of %u constraints (dependency cycle?)", cnt[2], N);
     unsigned nColours = 0;
-    for (unsigned id = 0; id < N; id++) nColours = std::max(nColours, colour[id] + 1);
+    #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : nColours)
+    for (long long id = 0; id < (long long)N; id++) nColours = std::max(nColours, colour[id] + 1);
     groups_from_colours(e, colour, nColours);
     if (ms) *ms = t;
     if (wavefronts) *wavefronts = cnt[3];
@@ -903,11 +966,16 @@ static int flatten_image(pbd_engine *e) {
     for (int t = 0; t < PBD_NUM_TYPES; t++) {
         const HostType &h = e->host[t];
         const int nb = type_shape(t).nBodies;
-        for (size_t i = 0; i < h.bodies.size(); i++) {
+        long long badAt = -1;
+        #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : badAt) if (h.bodies.size() > 100000)
+        for (long long i = 0; i < (long long)h.bodies.size(); i++) {
             const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && (i % nb) == 0);
-            if (h.bodies[i] >= (isRb ? e->nRb : e->n))
-                return fail("constraint of type %d refers to %s %u, but the engine holds %u: re-add the constraints after shrinking the model", t,
-                            isRb ? "rigid body" : "particle", h.bodies[i], isRb ? e->nRb : e->n);
+            if (h.bodies[i] >= (isRb ? e->nRb : e->n)) badAt = std::max(badAt, i);
+        }
+        if (badAt >= 0) {
+            const bool isRb = (t == PBD_BALLJOINT) || (t == PBD_RB_PARTICLE_BALLJOINT && (badAt % nb) == 0);
+            return fail("constraint of type %d refers to %s %u, but the engine holds %u: re-add the constraints after shrinking the model", t,
+                        isRb ? "rigid body" : "particle", h.bodies[badAt], isRb ? e->nRb : e->n);
         }
     }
     std::vector<std::pair<int, unsigned>> map;
@@ -1045,29 +1113,32 @@ static int flatten_image(pbd_engine *e) {
             return e->slot[raw];
         };
 
+        if (verbose) fprintf(stderr, "[pbd_b200] flatten:   type %d (%u constraints)\n", t, cnt);
+        lap("  order ids");
         // indices
         if (s.nBodies == 2) {
-            std::vector<uint2> v(cnt);
+            PodVector<uint2> v(cnt);
             #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) v[i] = make_uint2(B(i, 0), B(i, 1));
             CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx2 = (const uint2 *)d.idx[0].p;
         } else if (s.nBodies == 4) {
-            std::vector<uint4> v(cnt);
+            PodVector<uint4> v(cnt);
             #pragma omp parallel for schedule(static) num_threads(host_threads())
             for (long long i = 0; i < (long long)cnt; i++) v[i] = make_uint4(B(i, 0), B(i, 1), B(i, 2), B(i, 3));
             CKE(upload_vec(d.idx[0], v, e->stream)); d.arrays.idx4 = (const uint4 *)d.idx[0].p;
         } else {
             for (int k = 0; k < 3; k++) {
-                std::vector<unsigned> v(cnt);
+                PodVector<unsigned> v(cnt);
                 #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)cnt; i++) v[i] = B(i, k);
                 CKE(upload_vec(d.idx[k], v, e->stream)); d.arrays.idx3[k] = (const unsigned *)d.idx[k].p;
             }
         }
 
+        lap("  indices (remap + upload)");
         // geometry + material slots: (param index of each material slot)
         int matSlot[kMaxMat] = {-1, -1, -1, -1, -1};
-        std::vector<float4> gv[kMaxGeoV]; std::vector<float> gs[kMaxGeoS];
+        PodVector<float4> gv[kMaxGeoV]; PodVector<float> gs[kMaxGeoS];
         int variant = 0;
         switch (t) {
         case PBD_DISTANCE: case PBD_DISTANCE_XPBD: case PBD_DIHEDRAL: case PBD_VOLUME: case PBD_VOLUME_XPBD:
@@ -1112,7 +1183,8 @@ static int flatten_image(pbd_engine *e) {
             break;
         case PBD_FEMTET: case PBD_FEMTET_XPBD:
             gv[0].resize(cnt); gv[1].resize(cnt); gs[0].resize(cnt); gs[1].resize(cnt);
-            for (unsigned i = 0; i < cnt; i++) {
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
+            for (long long i = 0; i < (long long)cnt; i++) {
                 gv[0][i] = make_float4(P(i, 1), P(i, 2), P(i, 3), P(i, 4));
                 gv[1][i] = make_float4(P(i, 5), P(i, 6), P(i, 7), P(i, 8));
                 gs[0][i] = P(i, 9); gs[1][i] = P(i, 0);
@@ -1121,7 +1193,8 @@ static int flatten_image(pbd_engine *e) {
             break;
         case PBD_STRAINTET:
             gv[0].resize(cnt); gv[1].resize(cnt); gs[0].resize(cnt);
-            for (unsigned i = 0; i < cnt; i++) {
+            #pragma omp parallel for schedule(static) num_threads(host_threads())
+            for (long long i = 0; i < (long long)cnt; i++) {
                 gv[0][i] = make_float4(P(i, 0), P(i, 1), P(i, 2), P(i, 3));
                 gv[1][i] = make_float4(P(i, 4), P(i, 5), P(i, 6), P(i, 7));
                 gs[0][i] = P(i, 8);
@@ -1153,17 +1226,21 @@ static int flatten_image(pbd_engine *e) {
         if (t == PBD_BALLJOINT || t == PBD_RB_PARTICLE_BALLJOINT) {
             d.arrays.rbX = (float4 *)e->rbX.p; d.arrays.rbQ = (float4 *)e->rbQ.p; d.arrays.rbIinv = (const float4 *)e->rbIinv.p;
         }
+        lap("  geometry (host fill)");
         for (int k = 0; k < kMaxGeoV; k++) if (!gv[k].empty()) { CKE(upload_vec(d.gv[k], gv[k], e->stream)); d.arrays.gv[k] = (const float4 *)d.gv[k].p; }
         for (int k = 0; k < kMaxGeoS; k++) if (!gs[k].empty()) { CKE(upload_vec(d.gs[k], gs[k], e->stream)); d.arrays.gs[k] = (const float *)d.gs[k].p; }
+        lap("  geometry (upload)");
         // material parameters: one uniform per type when every constraint agrees, else a per-constraint array
         for (int k = 0; k < kMaxMat; k++) {
             if (matSlot[k] < 0) continue;
             const float first = P(0, matSlot[k]);
-            bool uniform = true;
-            for (unsigned i = 1; i < cnt && uniform; i++) uniform = (P(i, matSlot[k]) == first);
+            int differs = 0;
+            #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(| : differs) if (cnt > 100000)
+            for (long long i = 1; i < (long long)cnt; i++) differs |= (P((unsigned)i, matSlot[k]) != first) ? 1 : 0;
+            const bool uniform = !differs;
             d.arrays.matU[k] = first;
             if (!uniform) {
-                std::vector<float> v(cnt);
+                PodVector<float> v(cnt);
                 #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)cnt; i++) v[i] = P(i, matSlot[k]);
                 CKE(upload_vec(d.mat[k], v, e->stream)); d.arrays.mat[k] = (const float *)d.mat[k].p;
@@ -1174,6 +1251,7 @@ static int flatten_image(pbd_engine *e) {
             CK(cudaMemsetAsync(d.lambda.p, 0, (size_t)cnt * sizeof(float), e->stream));
             d.arrays.lambda = (float *)d.lambda.p;
         }
+        lap("  material + multipliers");
         bytesPerSweep += (double)cnt * algorithmic_bytes(t, variant);
     }
 

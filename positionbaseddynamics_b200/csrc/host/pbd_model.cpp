@@ -21,6 +21,12 @@ void ParticleData::addVertex(const Vector3r &vertex) {
     m_v.push_back(Vector3r()); m_a.push_back(Vector3r());
     dirtyMask = 0x1f; massDirty = true;
 }
+void ParticleData::addVertices(const Vector3r *vertices, unsigned int n) {
+    for (auto *v : {&m_x0, &m_x, &m_oldX, &m_lastX}) v->insert(v->end(), vertices, vertices + n);
+    m_masses.insert(m_masses.end(), n, 1.0f); m_invMasses.insert(m_invMasses.end(), n, 1.0f);
+    m_v.insert(m_v.end(), n, Vector3r()); m_a.insert(m_a.end(), n, Vector3r());
+    dirtyMask = 0x1f; massDirty = true;
+}
 void ParticleData::reserve(unsigned int n) {
     m_masses.reserve(n); m_invMasses.reserve(n); m_x0.reserve(n); m_x.reserve(n); m_v.reserve(n); m_a.reserve(n);
     m_oldX.reserve(n); m_lastX.reserve(n);
@@ -46,6 +52,7 @@ void IndexedFaceMesh::initMesh(unsigned int nPoints, unsigned int nEdges, unsign
     m_numPoints = nPoints; m_indices.clear(); m_indices.reserve((size_t)nFaces * 3); m_edges.clear(); m_edges.reserve(nEdges);
 }
 void IndexedFaceMesh::addFace(const unsigned int *indices) { m_indices.insert(m_indices.end(), indices, indices + 3); }
+void IndexedFaceMesh::addFaces(const unsigned int *indices, unsigned int nFaces) { m_indices.insert(m_indices.end(), indices, indices + 3 * (size_t)nFaces); }
 
 // The reference looks an undirected edge {a,b} up among the edges already incident to a, in discovery order, and creates
 // it (oriented a->b, m_face[0] = current face) when absent; a later sighting overwrites m_face[1]
@@ -78,6 +85,27 @@ static int model_threads() {
 // Edge discovery in the reference's order (IndexedFaceMesh.cpp:118-226: faces in order, their three edges in order, an edge is
 // created by the first half-edge that mentions it), computed without a sequential hash walk: sort the half-edges by (vertex
 // pair, position), the first of every run creates the edge, the edge's index is the rank of that creating position.
+// exclusive prefix sum of flags[0..count) into pos[0..count] (pos[count] = total), two passes over per-thread chunks
+static void parallel_prefix(const unsigned char *flags, size_t count, unsigned int *pos) {
+    const int T = std::max(1, model_threads());
+    std::vector<size_t> chunkSum((size_t)T + 1, 0);
+    #pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        const size_t lo = count * (size_t)t / nt, hi = count * (size_t)(t + 1) / nt;
+        size_t sum = 0;
+        for (size_t i = lo; i < hi; i++) sum += flags[i];
+        chunkSum[(size_t)t + 1] = sum;
+        #pragma omp barrier
+        #pragma omp single
+        for (int k = 0; k < nt; k++) chunkSum[(size_t)k + 1] += chunkSum[k];
+        size_t run = chunkSum[t];
+        for (size_t i = lo; i < hi; i++) { pos[i] = (unsigned int)run; run += flags[i]; }
+        if (t == nt - 1) pos[count] = (unsigned int)run;
+    }
+    if (count == 0) pos[0] = 0;
+}
+
 void IndexedFaceMesh::buildNeighbors() {
     m_edges.clear();
     const size_t nH = (size_t)numFaces() * 3;
@@ -96,21 +124,25 @@ void IndexedFaceMesh::buildNeighbors() {
         }
     } else {
         struct Half { uint64_t key; unsigned int pos; };
-        std::vector<Half> h(nH);
+        std::unique_ptr<Half[]> hbuf(new Half[nH]);  // uninitialised: filled from all threads
+        Half *h = hbuf.get();
         const int threads = model_threads();
         #pragma omp parallel for schedule(static) num_threads(threads)
         for (long long p = 0; p < (long long)nH; p++) {
             const unsigned int f = (unsigned int)(p / 3), j = (unsigned int)(p % 3);
             h[p] = Half{edgeKey(m_indices[3 * (size_t)f + j], m_indices[3 * (size_t)f + (j + 1) % 3]), (unsigned int)p};
         }
-        __gnu_parallel::sort(h.begin(), h.end(), [](const Half &a, const Half &b) { return a.key < b.key || (a.key == b.key && a.pos < b.pos); },
+        __gnu_parallel::sort(h, h + nH, [](const Half &a, const Half &b) { return a.key < b.key || (a.key == b.key && a.pos < b.pos); },
                              __gnu_parallel::default_parallel_tag(threads));
         // creating position of every run -> rank among the creating positions = edge index
-        std::vector<unsigned int> creates(nH + 1, 0u);
+        std::unique_ptr<unsigned char[]> creates(new unsigned char[nH]);
+        std::unique_ptr<unsigned int[]> rank(new unsigned int[nH + 1]);
         #pragma omp parallel for schedule(static) num_threads(threads)
-        for (long long k = 0; k < (long long)nH; k++) if (k == 0 || h[k].key != h[k - 1].key) creates[h[k].pos + 1] = 1u;
-        for (size_t p = 0; p < nH; p++) creates[p + 1] += creates[p];
-        m_edges.resize(creates[nH]);
+        for (long long k = 0; k < (long long)nH; k++) creates[k] = 0;
+        #pragma omp parallel for schedule(static) num_threads(threads)
+        for (long long k = 0; k < (long long)nH; k++) if (k == 0 || h[k].key != h[k - 1].key) creates[h[k].pos] = 1;
+        parallel_prefix(creates.get(), nH, rank.get());
+        m_edges.resize(rank[nH]);
         #pragma omp parallel for schedule(static) num_threads(threads)
         for (long long k = 0; k < (long long)nH; k++) {
             if (k != 0 && h[k].key == h[k - 1].key) continue;
@@ -119,11 +151,13 @@ void IndexedFaceMesh::buildNeighbors() {
             const unsigned int p = h[k].pos, f = p / 3, j = p % 3;
             Edge e; e.m_vert = {m_indices[3 * (size_t)f + j], m_indices[3 * (size_t)f + (j + 1) % 3]};
             e.m_face = {f, last == (size_t)k ? 0xffffffffu : h[last].pos / 3};
-            m_edges[creates[p]] = e;
+            m_edges[rank[p]] = e;
         }
     }
-    m_closed = true;
-    for (const Edge &e : m_edges) if (e.m_face[1] == 0xffffffffu) { m_closed = false; break; }
+    int open = 0;
+    #pragma omp parallel for schedule(static) num_threads(model_threads()) reduction(| : open)
+    for (long long i = 0; i < (long long)m_edges.size(); i++) open |= (m_edges[i].m_face[1] == 0xffffffffu) ? 1 : 0;
+    m_closed = !open;
 }
 
 void IndexedTetMesh::initMesh(unsigned int nPoints, unsigned int nEdges, unsigned int, unsigned int nTets) {
@@ -151,7 +185,7 @@ void IndexedTetMesh::buildNeighbors() {
 void TriangleModel::initMesh(unsigned int nPoints, unsigned int nFaces, unsigned int indexOffset, const unsigned int *indices) {
     m_indexOffset = indexOffset;
     m_particleMesh.initMesh(nPoints, nFaces * 2, nFaces);
-    for (unsigned int i = 0; i < nFaces; i++) m_particleMesh.addFace(&indices[3 * (size_t)i]);
+    m_particleMesh.addFaces(indices, nFaces);
     m_particleMesh.buildNeighbors();
 }
 void TetModel::initMesh(unsigned int nPoints, unsigned int nTets, unsigned int indexOffset, const unsigned int *indices) {
@@ -240,7 +274,7 @@ void SimulationModel::addTriangleModel(unsigned int nPoints, unsigned int nFaces
     m_triangleModels.push_back(tm);
     const unsigned int startIndex = m_particles.size();
     m_particles.reserve(startIndex + nPoints);
-    for (unsigned int i = 0; i < nPoints; i++) m_particles.addVertex(points[i]);
+    m_particles.addVertices(points, nPoints);
     tm->initMesh(nPoints, nFaces, startIndex, indices);
 }
 
@@ -254,21 +288,22 @@ void SimulationModel::addRegularTriangleModel(int width, int height, const Vecto
     const Real dy = scale[1] / (Real)(height - 1);
     const Real dx = scale[0] / (Real)(width - 1);
     std::vector<Vector3r> points((size_t)width * height);
+    #pragma omp parallel for schedule(static) num_threads(model_threads())
     for (int i = 0; i < height; i++)
         for (int j = 0; j < width; j++) points[(size_t)i * width + j] = rotTrans(rotation, Vector3r(dx * j, dy * i, 0.0f), translation);
-    std::vector<unsigned int> indices;
-    indices.reserve((size_t)6 * (height - 1) * (width - 1));
+    PodVector<unsigned int> indices((size_t)6 * (height - 1) * (width - 1));
+    #pragma omp parallel for schedule(static) num_threads(model_threads())
     for (int i = 0; i < height - 1; i++)
         for (int j = 0; j < width - 1; j++) {
             const unsigned int helper = (i % 2 == j % 2) ? 1u : 0u;
             const unsigned int a = i * width + j, b = (i + 1) * width + j;
             const unsigned int tri[6] = {a, a + 1, b + helper, b + 1, b, a + 1 - helper};
-            indices.insert(indices.end(), tri, tri + 6);
+            std::memcpy(&indices[6 * ((size_t)i * (width - 1) + j)], tri, sizeof(tri));
         }
     const size_t modelIndex = m_triangleModels.size();
     addTriangleModel((unsigned int)points.size(), (unsigned int)indices.size() / 3, points.data(), indices.data());
     const unsigned int offset = m_triangleModels[modelIndex]->getIndexOffset();
-    for (unsigned int i = offset; i < offset + (unsigned int)points.size(); i++) m_particles.setMass(i, 1.0f);
+    for (unsigned int i = offset; i < offset + (unsigned int)points.size(); i++) m_particles.setMass(i, 1.0f);  // SimulationModel.cpp:897-900
 }
 
 void SimulationModel::addTetModel(unsigned int nPoints, unsigned int nTets, const Vector3r *points, const unsigned int *indices) {
@@ -276,7 +311,7 @@ void SimulationModel::addTetModel(unsigned int nPoints, unsigned int nTets, cons
     m_tetModels.push_back(tm);
     const unsigned int startIndex = m_particles.size();
     m_particles.reserve(startIndex + nPoints);
-    for (unsigned int i = 0; i < nPoints; i++) m_particles.addVertex(points[i]);
+    m_particles.addVertices(points, nPoints);
     tm->initMesh(nPoints, nTets, startIndex, indices);
 }
 
@@ -418,17 +453,18 @@ bool SimulationModel::pushConstraint(int type, const unsigned int *bodies, const
 // bool (the constraint class's initConstraint result), independently of the others and therefore in parallel; the accepted ones
 // are appended in candidate order, i.e. exactly as the reference's sequential add loop would have inserted them.
 template <class A, class F>
-static void push_bulk(TypeStore &s, std::vector<ConstraintRef> &order, int type, size_t count, A &&accept, F &&fill) {
+static void push_bulk(TypeStore &s, PodVector<ConstraintRef> &order, int type, size_t count, A &&accept, F &&fill) {
     const int nb = pbd_num_bodies(type), np = pbd_num_params(type);
-    std::vector<unsigned int> pos(count + 1, 0u);
+    std::unique_ptr<unsigned char[]> flag(new unsigned char[count + 1]);
+    std::unique_ptr<unsigned int[]> pos(new unsigned int[count + 1]);
     #pragma omp parallel for schedule(static) num_threads(model_threads())
-    for (long long i = 0; i < (long long)count; i++) pos[i + 1] = accept((size_t)i) ? 1u : 0u;  // cheap topological test
-    for (size_t i = 0; i < count; i++) pos[i + 1] += pos[i];
+    for (long long i = 0; i < (long long)count; i++) flag[i] = accept((size_t)i) ? 1 : 0;  // cheap topological test
+    parallel_prefix(flag.get(), count, pos.get());
     const size_t add = pos[count], base = s.ids.size(), obase = order.size();
-    s.ids.resize(base + add); s.bodies.resize((base + add) * nb); s.params.resize((base + add) * np); order.resize(obase + add);
+    s.ids.resize(base + add); s.bodies.resize((base + add) * nb); s.params.resize((base + add) * np); order.resize(obase + add);  // uninitialised: filled below
     #pragma omp parallel for schedule(static) num_threads(model_threads())
     for (long long i = 0; i < (long long)count; i++) {
-        if (pos[i + 1] == pos[i]) continue;
+        if (!flag[i]) continue;
         const size_t k = pos[i];
         s.ids[base + k] = (unsigned int)(obase + k);
         fill((size_t)i, &s.bodies[(base + k) * nb], &s.params[(base + k) * np]);  // straight into the store: no staging copy
@@ -756,6 +792,9 @@ bool TimeStepController::setValueInt(int id, int v) {
 }
 
 bool TimeStepController::uploadModel(SimulationModel &model) {
+    static const bool verbose = getenv("PBD_B200_VERBOSE") != nullptr;
+    double tPrev = omp_get_wtime();
+    auto lap = [&](const char *what) { if (verbose) { const double t = omp_get_wtime(); fprintf(stderr, "[pbd_b200] upload:  %-34s %.3f s\n", what, t - tPrev); tPrev = t; } };
     ParticleData &pd = model.getParticles();
     const unsigned int n = pd.size();
     const bool rebind = (m_boundModel != &model) || (m_boundParticles != n);
@@ -774,6 +813,7 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
             if ((pd.dirtyMask >> a) & 1u) { if (pbd_set_attr(m_engine, a, &(*src[a])[0][0])) return fail("pbd_set_attr"); }
         pd.dirtyMask = 0;
     }
+    if (rebind) lap("particles");
     SimulationModel::RigidBodyVector &rbs = model.getRigidBodies();
     if (rebind || model.rigidBodiesDirty || rbs.size() != m_boundRigidBodies) {
         const unsigned int nr = (unsigned int)rbs.size();
@@ -798,6 +838,7 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
         // Colour groups (TimeStepController.cpp:256 -> SimulationModel::initConstraintGroups).  When the model has not been coloured yet the
         // engine does it on the GPU (pbd_color_first_fit_device: the same greedy first fit, identical groups) and the result is mirrored
         // into the model, so getConstraintGroups() shows what is simulated; PBD_B200_HOST_COLOURING=1 keeps the host colouring.
+        lap("constraints (pbd_add_constraints)");
         static const bool hostColouring = [] { const char *g = getenv("PBD_B200_HOST_COLOURING"); return g && atoi(g) != 0; }();
         bool coloured = false;
         if (!model.m_groupsInitialized && !hostColouring && model.numConstraints() > 0 && pbd_color_first_fit_device(m_engine, nullptr, nullptr) == 0) {
@@ -821,6 +862,7 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
             for (size_t g = 0; g < groups.size(); g++) { ids.insert(ids.end(), groups[g].begin(), groups[g].end()); off[g + 1] = (unsigned int)ids.size(); }
             if (pbd_set_groups(m_engine, (unsigned int)groups.size(), off.data(), ids.data())) return fail("pbd_set_groups");
         }
+        lap("colouring + groups into the model");
         m_boundGeneration = model.constraintGeneration();
     }
     m_boundModel = &model;

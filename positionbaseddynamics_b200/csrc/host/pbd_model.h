@@ -11,6 +11,7 @@
 #include <array>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../../include/pbd_b200.h"
@@ -42,6 +43,7 @@ class SimulationModel;
 class ParticleData {
 public:
     void addVertex(const Vector3r &vertex);  // mass = invMass = 1, v = a = 0, x0 = x = oldX = lastX (ParticleData.h:127-137)
+    void addVertices(const Vector3r *vertices, unsigned int n);  // n x addVertex in one go
     unsigned int size() const { return (unsigned int)m_x.size(); }
     unsigned int getNumberOfParticles() const { return size(); }
     void reserve(unsigned int n);
@@ -87,13 +89,24 @@ public:
 // Mesh topology (Utils/IndexedFaceMesh.{h,cpp}, Utils/IndexedTetMesh.{h,cpp}); the edge DISCOVERY ORDER defines the
 // constraint order, hence the colouring and the Gauss-Seidel order.
 // ---------------------------------------------------------------------------------------------------------
+// std::vector whose resize() leaves new trivially-constructible elements uninitialised: the bulk builders size a store once and fill it
+// from all threads (first touch in parallel instead of one thread zeroing hundreds of megabytes first)
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { typedef DefaultInitAllocator<U> other; };
+    DefaultInitAllocator() = default;
+    template <class U> DefaultInitAllocator(const DefaultInitAllocator<U> &) {}
+    template <class U> void construct(U *p) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... Args> void construct(U *p, Args &&...args) { ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...); }
+};
+template <class T> using PodVector = std::vector<T, DefaultInitAllocator<T>>;
 class IndexedFaceMesh {
 public:
     struct Edge { std::array<unsigned int, 2> m_face; std::array<unsigned int, 2> m_vert; };  // IndexedFaceMesh.h:14-18
     typedef std::vector<unsigned int> Faces;
-    typedef std::vector<Edge> Edges;
+    typedef PodVector<Edge> Edges;
     void initMesh(unsigned int nPoints, unsigned int nEdges, unsigned int nFaces);
     void addFace(const unsigned int *indices);
+    void addFaces(const unsigned int *indices, unsigned int nFaces);
     void buildNeighbors();  // IndexedFaceMesh.cpp:118-226
     const Faces &getFaces() const { return m_indices; }
     const Edges &getEdges() const { return m_edges; }
@@ -203,7 +216,7 @@ struct ConstraintRef { int type; unsigned int local; };
 struct ConstraintView {  // what `model.getConstraints()[i]` exposes
     int type; unsigned int numberOfBodies; const unsigned int *m_bodies; const Real *params; unsigned int numParams;
 };
-struct TypeStore { std::vector<unsigned int> ids, bodies; std::vector<Real> params; };
+struct TypeStore { PodVector<unsigned int> ids, bodies; PodVector<Real> params; };
 
 class SimulationModel {
 public:
@@ -297,7 +310,7 @@ private:
     TriangleModelVector m_triangleModels;
     TetModelVector m_tetModels;
     TypeStore m_store[PBD_NUM_TYPES];
-    std::vector<ConstraintRef> m_order;
+    PodVector<ConstraintRef> m_order;
     ConstraintGroupVector m_constraintGroups;
     uint64_t m_generation = 1;
     Real m_contactStiffnessParticleRigidBody = static_cast<Real>(100.0);
