@@ -574,22 +574,32 @@ extern "C" int pbd_color_first_fit_device(pbd_engine *e, float *ms, unsigned *wa
     CKE(build_id_csr(e, off, bodies));
     const unsigned M = (unsigned)bodies.size();
     cudaStream_t s = e->stream;
-    DevBuf dOff, dBody, dBody4, dNext4, dKeys, dVals, dKeysS, dValsS, dIndeg, dUsed, dColour, dA, dB, dCnt, dTmp;
-    struct Release { std::vector<DevBuf *> b; ~Release() { for (auto *x : b) x->release(); } } rel{{&dOff, &dBody, &dBody4, &dNext4, &dKeys, &dVals, &dKeysS, &dValsS, &dIndeg, &dUsed, &dColour, &dA, &dB, &dCnt, &dTmp}};
-    CKE(upload_vec(dOff, off, s)); CKE(upload_vec(dBody, bodies, s));
-    for (DevBuf *b : {&dKeys, &dVals, &dKeysS, &dValsS}) CKE(b->alloc((size_t)M * sizeof(unsigned)));
-    for (DevBuf *b : {&dBody4, &dNext4}) CKE(b->alloc((size_t)N * sizeof(uint4)));
-    for (DevBuf *b : {&dIndeg, &dColour, &dA, &dB}) CKE(b->alloc((size_t)N * sizeof(unsigned)));
-    CKE(dCnt.alloc(4 * sizeof(unsigned)));
+    // one device allocation for all the work arrays (a dozen cudaMalloc / cudaFree pairs cost more than the colouring kernels of a small scene)
+    int endBit = 1; while (endBit < 32 && (1ull << endBit) < (unsigned long long)V) endBit++;
+    size_t tmpBytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const unsigned *)nullptr, (unsigned *)nullptr, (const unsigned *)nullptr, (unsigned *)nullptr, (int)M, 0, endBit, s));
+    struct View { void *p = nullptr; };
+    View dOff, dBody, dBody4, dNext4, dKeys, dVals, dKeysS, dValsS, dIndeg, dColour, dA, dB, dCnt, dTmp;
+    DevBuf dAll, dUsed;
+    struct Release { std::vector<DevBuf *> b; ~Release() { for (auto *x : b) x->release(); } } rel{{&dAll, &dUsed}};
+    {
+        struct Want { View *v; size_t bytes; } want[] = {{&dOff, ((size_t)N + 1) * sizeof(unsigned)}, {&dBody, (size_t)M * sizeof(unsigned)}, {&dKeys, (size_t)M * sizeof(unsigned)},
+            {&dVals, (size_t)M * sizeof(unsigned)}, {&dKeysS, (size_t)M * sizeof(unsigned)}, {&dValsS, (size_t)M * sizeof(unsigned)}, {&dBody4, (size_t)N * sizeof(uint4)},
+            {&dNext4, (size_t)N * sizeof(uint4)}, {&dIndeg, (size_t)N * sizeof(unsigned)}, {&dColour, (size_t)N * sizeof(unsigned)}, {&dA, (size_t)N * sizeof(unsigned)},
+            {&dB, (size_t)N * sizeof(unsigned)}, {&dCnt, 4 * sizeof(unsigned)}, {&dTmp, tmpBytes}};
+        size_t total = 0;
+        for (auto &w : want) total += (w.bytes + 255) & ~(size_t)255;
+        CKE(dAll.alloc(total));
+        size_t at = 0;
+        for (auto &w : want) { w.v->p = (char *)dAll.p + at; at += (w.bytes + 255) & ~(size_t)255; }
+    }
+    CK(cudaMemcpyAsync(dOff.p, off.data(), ((size_t)N + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dBody.p, bodies.data(), (size_t)M * sizeof(unsigned), cudaMemcpyHostToDevice, s));
     cudaEvent_t ev0, ev1;
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, s));
     // incidence lists: stable sort of (body, incidence) by body, then successor / in-degree of every constraint
     k_colour_expand<<<nblk(N, 256), 256, 0, s>>>((const unsigned *)dOff.p, (const unsigned *)dBody.p, (uint4 *)dBody4.p, (unsigned *)dKeys.p, (unsigned *)dVals.p, N);
-    int endBit = 1; while (endBit < 32 && (1ull << endBit) < (unsigned long long)V) endBit++;
-    size_t tmpBytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const unsigned *)dKeys.p, (unsigned *)dKeysS.p, (const unsigned *)dVals.p, (unsigned *)dValsS.p, (int)M, 0, endBit, s));
-    CKE(dTmp.alloc(tmpBytes));
     CK(cub::DeviceRadixSort::SortPairs(dTmp.p, tmpBytes, (const unsigned *)dKeys.p, (unsigned *)dKeysS.p, (const unsigned *)dVals.p, (unsigned *)dValsS.p, (int)M, 0, endBit, s));
     CK(cudaMemsetAsync(dNext4.p, 0xff, (size_t)N * sizeof(uint4), s));
     std::vector<unsigned> colour(N);

@@ -848,7 +848,8 @@ bool TimeStepController::uploadModel(SimulationModel &model) {
                 if (pbd_get_groups(m_engine, off.data(), ids.data()) == 0) {
                     SimulationModel::ConstraintGroupVector &groups = model.getConstraintGroups();
                     groups.assign(ng, std::vector<unsigned int>());
-                    for (unsigned int g = 0; g < ng; g++) groups[g].assign(ids.begin() + off[g], ids.begin() + off[g + 1]);
+                    #pragma omp parallel for schedule(dynamic, 1) num_threads(model_threads())
+                    for (long long g = 0; g < (long long)ng; g++) groups[g].assign(ids.begin() + off[g], ids.begin() + off[g + 1]);
                     model.m_groupsInitialized = true;
                     coloured = true;
                 }
