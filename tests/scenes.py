@@ -146,3 +146,23 @@ def cloth_on_colliders(m, n=24, tolerance=0.05, max_iter=4, sub_steps=1, shapes=
     m.add_model_collider(0, 0, restitution=0.5, friction=0.1)
     m.set_contact_params(stiffness=100.0, max_iter_v=5)
     return bodies
+
+
+def bar_on_colliders(m, tolerance=0.05, sub_steps=2, max_iter=3):
+    """Reference builds only.  A small FEM tet bar (no pinned particles) dropped onto a static sphere and a static cylinder above a floor box:
+    the tet-model branch of the contact path (DistanceFieldCollisionDetection.cpp:139-152), two substeps per step."""
+    m.add_regular_tet_model(9, 4, 4, t=(0.0, 2.0, 0.0), R=np.eye(3), scale=(3.0, 0.6, 0.6))
+    m.add_solid_constraints(0, 2, k=1.0e5, nu=0.3)
+    m.set_params(dt=0.005, sub_steps=sub_steps, max_iter=max_iter)
+    rot = np.array([[0.9553365, -0.2955202, 0.0], [0.2955202, 0.9553365, 0.0], [0.0, 0.0, 1.0]])
+    bodies = []
+    i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(0.0, -0.5, 0.0), R=np.eye(3), scale=(20.0, 1.0, 20.0)); bodies.append((i, 0, (20.0, 1.0, 20.0)))
+    i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(-0.7, 1.0, 0.0), R=np.eye(3), scale=(1.0, 1.0, 1.0)); bodies.append((i, 1, (0.5,)))
+    i, _ = m.add_rigid_body_mesh(1.0, BOX_VERTS, BOX_FACES, x=(0.9, 0.9, 0.0), R=rot, scale=(0.8, 1.2, 0.8)); bodies.append((i, 3, (0.4, 1.2)))
+    m.use_distance_field_cd(tolerance)
+    for i, shape, dims in bodies:
+        m.set_rigid_body_mass(i, 0.0)
+        m.add_rigid_collider(i, shape, dims, restitution=0.6, friction=0.2)
+    m.add_model_collider(1, 0, restitution=0.4, friction=0.3)
+    m.set_contact_params(stiffness=100.0, max_iter_v=5)
+    return bodies

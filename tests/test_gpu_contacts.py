@@ -118,6 +118,27 @@ def test_contact_path_vs_reference(mode, cpu_libs):
     eng.close(); eng2.close()
 
 
+def test_tet_model_contacts_with_substeps(cpu_libs):
+    """A tet model as the particle side (TetModelCollisionObjectType + rigid body: collisionDetectionRBSolid as well), two substeps per
+    step: the contacts are detected and solved once per step, after the substeps (TimeStepController.cpp:189-196)."""
+    if not have_ref("f64"):
+        pytest.skip("prebuilt oracle/_ref/libpbdref_f64.so not present on this box")
+    from positionbaseddynamics_b200 import _capi
+    cpu = cpu_libs.CpuPbd("ref", "f64")
+    scenes.bar_on_colliders(cpu)
+    cpu.init_groups()
+    eng = _engine_from(cpu)
+    eng.set_params(dt=0.005, sub_steps=2, max_iter=3)
+    n = cpu.num_particles()
+    xo = np.zeros((n, 3), np.float32); vo = np.zeros((n, 3), np.float32)
+    def step_gpu(x, v):
+        eng.step_host(1, x.astype(np.float32), v.astype(np.float32), xo, vo)
+    events, bodies, grazing, worst_x, worst_dv = _lockstep(step_gpu, lambda: (xo, vo), cpu, 200, contacts_gpu=lambda: eng.contacts())
+    print("tet bar, 2 substeps: %d contact events on bodies %s, %d grazing, worst rel pos %.2e, worst |dv| %.2e m/s" % (events, sorted(bodies), grazing, worst_x, worst_dv))
+    assert events > 300 and len(bodies) >= 2 and grazing <= 3
+    eng.close()
+
+
 def test_contacts_matter_and_colliders_are_validated(cpu_libs):
     """Negative control: the same engine without the colliders leaves the tolerance by orders of magnitude; a collider on a dynamic body
     is refused."""
