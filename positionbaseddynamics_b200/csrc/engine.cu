@@ -1011,6 +1011,9 @@ static int flatten_image(pbd_engine *e) {
     // -3.6 % on the cloth scenes (cfg2 1.98 -> 2.05 ms), so it is on for the solid instantiations only; PBD_B200_SIGSORT=0/1 forces it
     static const int sigSortEnv = [] { const char *g = getenv("PBD_B200_SIGSORT"); return g ? (atoi(g) != 0 ? 1 : 0) : -1; }();
     const bool sigSort = tiled && (sigSortEnv >= 0 ? sigSortEnv != 0 : (e->resMask == kMaskFem || e->resMask == kMaskSolid));
+    // bank-group fill of the shared-memory runs (below): cfg2 1.976 -> 1.914 ms, cfg5 1.379 -> 1.366 ms; PBD_B200_BANKSORT=0 switches it off
+    static const bool bankSortEnv = [] { const char *g = getenv("PBD_B200_BANKSORT"); return !g || atoi(g) != 0; }();
+    const bool bankSort = tiled && bankSortEnv;
     std::vector<unsigned> order[PBD_NUM_TYPES];  // device position -> local host index
     e->buckets.clear();
     std::vector<unsigned> tmp[PBD_NUM_TYPES];
@@ -1053,6 +1056,71 @@ static int flatten_image(pbd_engine *e) {
                 }
                 __gnu_parallel::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; },
                                             __gnu_parallel::default_parallel_tag(host_threads()));
+                if (tiled && e->resC == 1 && !joint && bankSort) {
+                    // Shared-memory bank groups.  The eight lanes of a quarter-warp (eight consecutive items of a tile's run) read operand k of
+                    // their items with one LDS.128; it takes as many wavefronts as the fullest 16-byte bank group (slot & 7 after the swizzle).
+                    // Greedy re-ordering inside every run: each group of eight is filled with the items, out of the next `kWindow` unused
+                    // ones, that add the fewest collisions over all operands.  The order inside a colour is free; results are bit-identical.
+                    constexpr int kWindow = 64;
+                    std::vector<size_t> runStart;
+                    for (size_t i = 0; i < keyed.size(); i++) if (i == 0 || (keyed[i].first >> 51) != (keyed[i - 1].first >> 51)) runStart.push_back(i);
+                    runStart.push_back(keyed.size());
+                    double wfBefore = 0, wfAfter = 0, requests = 0;
+                    const long long nRuns = (long long)runStart.size() - 1;
+                    #pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads()) reduction(+ : wfBefore, wfAfter, requests)
+                    for (long long r = 0; r < nRuns; r++) {
+                        const size_t lo = runStart[r], hi = runStart[r + 1], cnt = hi - lo;
+                        if (!((keyed[lo].first >> 51) & 1ull) || cnt < 16) continue;  // X runs gather from global memory: left alone
+                        const unsigned tl = (unsigned)((keyed[lo].first >> 51) >> 1);
+                        std::vector<unsigned char> bg(cnt * 4, 0);
+                        for (size_t i = 0; i < cnt; i++) {
+                            const unsigned *b = bod + (size_t)keyed[lo + i].second * nb;
+                            for (int k = 0; k < nb && k < 4; k++) bg[i * 4 + k] = (unsigned char)(tile_swizzle(e->slot[b[k]] - pl.tileStart[tl]) & 7u);
+                        }
+                        auto wavefronts = [&](const std::vector<unsigned> &ord) {
+                            double w = 0;
+                            for (size_t g8 = 0; g8 + 8 <= cnt; g8 += 8)
+                                for (int k = 0; k < nb && k < 4; k++) {
+                                    unsigned char c8[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned mx = 0;
+                                    for (int j = 0; j < 8; j++) mx = std::max<unsigned>(mx, ++c8[bg[ord[g8 + j] * 4 + k]]);
+                                    w += mx;
+                                }
+                            return w;
+                        };
+                        std::vector<unsigned> ord(cnt);
+                        for (size_t i = 0; i < cnt; i++) ord[i] = (unsigned)i;
+                        wfBefore += wavefronts(ord); requests += (double)(cnt / 8) * std::min(nb, 4);
+                        // greedy fill from a sliding pool of the next kWindow unused items (kept in run order)
+                        std::vector<unsigned> out; out.reserve(cnt);
+                        unsigned pool[kWindow]; int nPool = 0; size_t head = 0;
+                        while (out.size() < cnt) {
+                            unsigned char load[4][8] = {};
+                            for (int j = 0; j < 8 && out.size() < cnt; j++) {
+                                while (nPool < kWindow && head < cnt) pool[nPool++] = (unsigned)head++;
+                                int best = 0, bestCost = 1 << 30;
+                                for (int c = 0; c < nPool; c++) {
+                                    const unsigned char *g4 = &bg[(size_t)pool[c] * 4];
+                                    int cost = 0;
+                                    for (int k = 0; k < nb && k < 4; k++) cost += load[k][g4[k]];
+                                    if (cost < bestCost) { bestCost = cost; best = c; if (!cost) break; }
+                                }
+                                const unsigned pick = pool[best];
+                                for (int c = best; c + 1 < nPool; c++) pool[c] = pool[c + 1];
+                                nPool--;
+                                out.push_back(pick);
+                                for (int k = 0; k < nb && k < 4; k++) load[k][bg[(size_t)pick * 4 + k]]++;
+                            }
+                        }
+                        wfAfter += wavefronts(out);
+                        if (bankSort) {
+                            std::vector<std::pair<unsigned long long, unsigned>> tmpRun(cnt);
+                            for (size_t i = 0; i < cnt; i++) tmpRun[i] = keyed[lo + out[i]];
+                            for (size_t i = 0; i < cnt; i++) keyed[lo + i] = tmpRun[i];
+                        }
+                    }
+                    if (verbose && requests > 0) fprintf(stderr, "[pbd_b200] flatten:   colour %u type %d: %.2f wavefronts per quarter-warp gather as sorted, %.2f after the bank-group fill%s\n", g, t,
+                                                         wfBefore / requests, wfAfter / requests, bankSort ? " (applied)" : "");
+                }
                 #pragma omp parallel for schedule(static) num_threads(host_threads())
                 for (long long i = 0; i < (long long)keyed.size(); i++) tmp[t][i] = keyed[i].second;
                 if (tiled) {  // runs of every tile inside this bucket: [2 tile] X items, [2 tile + 1] the others
