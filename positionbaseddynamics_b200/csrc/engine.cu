@@ -1014,6 +1014,7 @@ static int flatten_image(pbd_engine *e) {
     // bank-group fill of the shared-memory runs (below): cfg2 1.976 -> 1.914 ms, cfg5 1.379 -> 1.366 ms; PBD_B200_BANKSORT=0 switches it off
     static const bool bankSortEnv = [] { const char *g = getenv("PBD_B200_BANKSORT"); return !g || atoi(g) != 0; }();
     const bool bankSort = tiled && bankSortEnv;
+    static const bool bankSortClusters = [] { const char *g = getenv("PBD_B200_BANKSORT_CLUSTERS"); return !g || atoi(g) != 0; }();  // cfg3 7.46 -> 7.28 ms (bank group taken inside the CTA that holds the particle)
     std::vector<unsigned> order[PBD_NUM_TYPES];  // device position -> local host index
     e->buckets.clear();
     std::vector<unsigned> tmp[PBD_NUM_TYPES];
@@ -1056,7 +1057,7 @@ static int flatten_image(pbd_engine *e) {
                 }
                 __gnu_parallel::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) { return a.first < b.first; },
                                             __gnu_parallel::default_parallel_tag(host_threads()));
-                if (tiled && e->resC == 1 && !joint && bankSort) {
+                if (tiled && (e->resC == 1 || bankSortClusters) && !joint && bankSort) {
                     // Shared-memory bank groups.  The eight lanes of a quarter-warp (eight consecutive items of a tile's run) read operand k of
                     // their items with one LDS.128; it takes as many wavefronts as the fullest 16-byte bank group (slot & 7 after the swizzle).
                     // Greedy re-ordering inside every run: each group of eight is filled with the items, out of the next `kWindow` unused
@@ -1071,11 +1072,10 @@ static int flatten_image(pbd_engine *e) {
                     for (long long r = 0; r < nRuns; r++) {
                         const size_t lo = runStart[r], hi = runStart[r + 1], cnt = hi - lo;
                         if (!((keyed[lo].first >> 51) & 1ull) || cnt < 16) continue;  // X runs gather from global memory: left alone
-                        const unsigned tl = (unsigned)((keyed[lo].first >> 51) >> 1);
                         std::vector<unsigned char> bg(cnt * 4, 0);
                         for (size_t i = 0; i < cnt; i++) {
                             const unsigned *b = bod + (size_t)keyed[lo + i].second * nb;
-                            for (int k = 0; k < nb && k < 4; k++) bg[i * 4 + k] = (unsigned char)(tile_swizzle(e->slot[b[k]] - pl.tileStart[tl]) & 7u);
+                            for (int k = 0; k < nb && k < 4; k++) bg[i * 4 + k] = (unsigned char)(tile_swizzle(e->slot[b[k]] - pl.tileStart[tileOf[b[k]]]) & 7u);  // bank group inside the CTA that holds the particle
                         }
                         auto wavefronts = [&](const std::vector<unsigned> &ord) {
                             double w = 0;
