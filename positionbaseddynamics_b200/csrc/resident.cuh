@@ -12,11 +12,16 @@
 //   * a projection reaches a particle of a sibling tile of the same cluster through DSMEM (mapa + ld/st.shared::cluster),
 //     so inside a cluster a colour phase ends with the hardware cluster barrier (barrier.cluster, ~0.2 us) instead of a
 //     grid-wide atomic barrier or a kernel boundary;
-//   * only particles touched by a constraint that spans two clusters stay in global memory ("global-homed", ~1 % of cfg2
-//     with 16-CTA clusters).  The constraints touching them ("X items") are run by a few dedicated warps of every CTA,
-//     which order themselves across clusters through one monotone arrival counter: red.release.gpu after their X items of
-//     phase p, ld.acquire.gpu spin before their X items of phase p+1.  The round trip overlaps the shared-memory work the
-//     other warps do in the meantime; those never touch the counter.  A scene that fits one cluster (G = 1) has no X items.
+//   * only particles touched by a constraint that spans two clusters stay in global memory ("global-homed").  The constraints
+//     touching them ("X items") are run by dedicated warps of every CTA, which order themselves across clusters through one
+//     monotone arrival counter: red.release.gpu after their X items of phase p, ld.acquire.gpu spin before their X items of
+//     phase p+1.  The round trip overlaps the shared-memory work the other warps do in the meantime; those never touch the
+//     counter.  A scene that fits one cluster (G = 1) has no X items.
+//   Two regimes are used (engine.cu:choose_resident_shape, measured in profiles/README.md R2.3): ONE cluster of up to 16 CTAs for
+//   scenes whose colour phases are small (cfg1 / cfg3 / cfg4), and G = #SMs clusters of ONE CTA for big scenes (cfg2 / cfg5: 148
+//   independent CTAs, 6.9 % of the particles global-homed, 11 % X items; the SINGLE instantiations: plain LDS / STS, __syncthreads).
+//   The order of the items inside a tile's run is chosen at flatten time so that the lanes of a quarter-warp hit distinct 16-byte
+//   bank groups (engine.cu, "bank-group fill").
 //
 // Exactness.  Colour phases are kept: inside a colour no two constraints share a particle (checked at flatten time),
 // across colours every constraint reads exactly what the reference's sequential sweep would have produced, whichever CTA
