@@ -887,8 +887,9 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
                     if (spans) for (int k = 0; k < nb; k++) hg[b[k]] = 1;  // every writer stores the same byte
                 }
             }
-        // threads of a CTA dedicated to the X items: in proportion to their share, times 2.7 because an X item waits for L2 where
-        // the others read shared memory (measured on cfg2: 11 % X items, best with 192 of 640 threads)
+        // threads of a CTA dedicated to the X items: in proportion to their share, times 3.1 because an X item waits for L2 where
+        // the others read shared memory (measured on cfg2, 11 % X items, 640 threads, after the bank-group fill: 160 / 192 / 224 / 256 X
+        // threads -> 2.07 / 1.93 / 1.90 / 1.93 ms)
         if (G > 1) {
             unsigned long long xItems = 0;
             for (int t = 0; t < PBD_NUM_TYPES; t++) {
@@ -902,7 +903,7 @@ static int prepare_resident(pbd_engine *e, ResidentPlan &pl) {
                 }
             }
             const double share = (double)xItems / std::max(1u, e->numConstraints);
-            unsigned xt = ((unsigned)(e->resThreads * share * 2.7) + 31u) & ~31u;
+            unsigned xt = ((unsigned)(e->resThreads * share * 3.1) + 31u) & ~31u;
             xt = std::max(64u, std::min(xt, (e->resThreads / 2u) & ~31u));
             if (const char *g = getenv("PBD_B200_XTHREADS")) { const int k = atoi(g); if (k >= 32 && k % 32 == 0 && (unsigned)k < e->resThreads) xt = (unsigned)k; }
             e->resXThreads = xt;
