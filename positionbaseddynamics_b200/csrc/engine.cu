@@ -1326,7 +1326,7 @@ static int flatten_image(pbd_engine *e) {
             }
         }
         if (s.xpbd) {
-            CKE(d.lambda.alloc((size_t)cnt * sizeof(float)));
+            CKE(d.lambda.alloc((size_t)cnt * sizeof(float) + 16));  // + 16 like the other streamed arrays: the L2 prefetch of a run rounds its end up to 16 bytes
             CK(cudaMemsetAsync(d.lambda.p, 0, (size_t)cnt * sizeof(float), e->stream));
             d.arrays.lambda = (float *)d.lambda.p;
         }
