@@ -845,6 +845,13 @@ typedef struct {
     quat q, lastQ, oldQ, q0;
 } RigidBody;
 
+/* contact path: DistanceFieldCollisionDetection objects as an adapter would hand them over (same layout as pbd_rigid_collider of
+ * include/pbd_b200.h): shape, body, dimensions, m_invertSDF, the body's coefficients, RigidBody::getTransformationR / V1 / V2 and m_aabb */
+struct RigidColl { int shape; unsigned body; double dim[3], thickness, invert; real restitution, friction; real Rm[9], v1[3], v2[3], lo[3], hi[3]; };
+struct PartColl { unsigned offset, count; real restitution, friction; };
+/* ParticleRigidBodyContactConstraint (Constraints.h): m_bodies, m_constraintInfo (3x5), m_sum_impulses, m_stiffness, m_frictionCoeff */
+struct Contact { unsigned particle, body; vec3 cp0, cp1, n, t; real nKnInv, pMax, goal, sum, stiffness, friction; };
+
 typedef struct {
     unsigned n, cap;
     RigidBody *rbs; unsigned nRb;
@@ -855,6 +862,11 @@ typedef struct {
     TetModel *tets; unsigned nTetModels;
     unsigned *groupOff, *groupIds; unsigned nGroups; int groupsInit;
     real dt, time; unsigned subSteps, maxIter; int velMethod; vec3 gravity;
+    /* contact path (static analytic colliders) */
+    struct RigidColl *rigidColl; unsigned nRigidColl;
+    struct PartColl *partColl; unsigned nPartColl;
+    struct Contact *contacts; unsigned nContacts, capContacts;
+    real contactTolerance, contactStiffness; unsigned maxIterV;
 } Model;
 
 static Model *G = NULL;
@@ -866,6 +878,7 @@ static void model_free(Model *m) {
     for (unsigned i = 0; i < m->nTris; i++) { free(m->tris[i].faces); free(m->tris[i].edges); }
     for (unsigned i = 0; i < m->nTetModels; i++) { free(m->tets[i].tets); free(m->tets[i].edges); free(m->tets[i].vertTets); }
     free(m->tris); free(m->tets); free(m->groupOff); free(m->groupIds); free(m->rbs);
+    free(m->rigidColl); free(m->partColl); free(m->contacts);
     free(m);
 }
 
@@ -891,6 +904,7 @@ void orc_reset(void) {
     model_free(G);
     G = (Model *)calloc(1, sizeof(Model));
     G->dt = R(0.005); G->subSteps = 5; G->maxIter = 1; G->velMethod = 0;
+    G->contactTolerance = R(0.01); G->contactStiffness = R(100.0); G->maxIterV = 5; /* CollisionDetection.cpp:25, SimulationModel.cpp:57, TimeStepController.cpp:29 */
     G->gravity = V(R(0.0), R(-9.81), R(0.0));
 }
 
@@ -1591,6 +1605,136 @@ static void position_constraint_projection(Model *m, real h) {
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* contact path: particles against analytic distance fields on static rigid bodies                   */
+/* ------------------------------------------------------------------------------------------------ */
+/* DistanceFieldCollision{Box,Sphere,Torus,Cylinder,HollowSphere,HollowBox}::distance, DistanceFieldCollisionDetection.cpp:598-682
+ * (evaluated in double precision there as here) */
+static double coll_distance(const struct RigidColl *c, const double x[3], double tol) {
+    const double inv = c->invert;
+    switch (c->shape) {
+    case 0: { /* box, :598-605 */
+        const double d[3] = {fabs(x[0]) - c->dim[0], fabs(x[1]) - c->dim[1], fabs(x[2]) - c->dim[2]};
+        const double m[3] = {fmax(d[0], 0.0), fmax(d[1], 0.0), fmax(d[2], 0.0)};
+        return inv * (fmin(fmax(d[0], fmax(d[1], d[2])), 0.0) + sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2])) - tol;
+    }
+    case 1: return inv * (sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) - c->dim[0]) - tol; /* sphere, :607-612 */
+    case 2: { /* torus, :632-637 (the ring distance is taken in Real precision there) */
+        const real rx = (real)x[0], rz = (real)x[2];
+        const double q0 = (double)RSQRT(rx * rx + rz * rz) - c->dim[0], q1 = x[1];
+        return inv * (sqrt(q0 * q0 + q1 * q1) - c->dim[1]) - tol;
+    }
+    case 3: { /* cylinder, :639-645 */
+        const double l = sqrt(x[0] * x[0] + x[2] * x[2]);
+        const double d[2] = {fabs(l) - c->dim[0], fabs(x[1]) - c->dim[1]};
+        const double m[2] = {fmax(d[0], 0.0), fmax(d[1], 0.0)};
+        return inv * (fmin(fmax(d[0], d[1]), 0.0) + sqrt(m[0] * m[0] + m[1] * m[1])) - tol;
+    }
+    case 4: return inv * (fabs(sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) - c->dim[0]) - c->thickness) - tol; /* hollow sphere, :648-653 */
+    default: { /* hollow box, :675-682 */
+        const double d[3] = {fabs(x[0]) - c->dim[0], fabs(x[1]) - c->dim[1], fabs(x[2]) - c->dim[2]};
+        const double m[3] = {fmax(d[0], 0.0), fmax(d[1], 0.0), fmax(d[2], 0.0)};
+        return inv * (fabs(fmin(fmax(d[0], fmax(d[1], d[2])), 0.0) + sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2])) - c->thickness) - tol;
+    }
+    }
+}
+/* collisionTest: the analytic overrides of the sphere (:614-630) and the hollow sphere (:655-673), else DistanceFieldCollisionObject::
+ * collisionTest with approximateNormal (:684-728) */
+static int coll_test(const struct RigidColl *c, vec3 x, real tol, vec3 *cp, vec3 *n, real *dist) {
+    if (c->shape == 1 || c->shape == 4) {
+        const real dl = vnorm(x), r = (real)c->dim[0], inv = (real)c->invert;
+        *dist = (c->shape == 4) ? inv * (RFABS(dl - r) - (real)c->thickness) - tol : inv * (dl - r) - tol;
+        if (!(*dist < R(0.0))) return 0;
+        if (dl < R(1.e-6)) *n = V(0, 0, 0);
+        else if (c->shape == 4 && dl < r) *n = vmul(vmul(x, -inv), R(1.0) / dl);
+        else *n = vmul(vmul(x, inv), R(1.0) / dl);
+        *cp = (c->shape == 4) ? vsub(x, vmul(*n, *dist)) : vmul(*n, r + tol);
+        return 1;
+    }
+    const double xd[3] = {(double)x.v[0], (double)x.v[1], (double)x.v[2]};
+    *dist = (real)coll_distance(c, xd, (double)tol);
+    if (!(*dist < R(0.0))) return 0;
+    const double eps = 1.e-6;
+    double xt[3] = {xd[0], xd[1], xd[2]};
+    for (int j = 0; j < 3; j++) {
+        xt[j] = xd[j] + eps; const double ep = coll_distance(c, xt, (double)tol);
+        xt[j] = xd[j] - eps; const double em = coll_distance(c, xt, (double)tol);
+        xt[j] = xd[j];
+        n->v[j] = (real)((ep - em) * (1.0 / (2.0 * eps)));
+    }
+    const real norm2 = vsq(*n);
+    if (norm2 < R(1.e-6)) *n = V(0, 0, 0); else *n = vmul(*n, R(1.0) / RSQRT(norm2));
+    *cp = vsub(x, vmul(*n, *dist));
+    return 1;
+}
+/* DistanceFieldCollisionDetection::collisionDetection + collisionDetectionRBSolid (:26-197, :290-357) for static bodies, every point tested
+ * (the bounding-sphere hierarchy only prunes), then ParticleRigidBodyContactConstraint::initConstraint (Constraints.cpp:2115-2145) +
+ * init_ParticleRigidBodyContactConstraint (PositionBasedRigidBodyDynamics.cpp:2386-2451) */
+static void contact_detection(Model *m) {
+    m->nContacts = 0;  /* SimulationModel::resetContacts */
+    for (unsigned pi = 0; pi < m->nPartColl; pi++)
+        for (unsigned k = 0; k < m->nRigidColl; k++) {
+            const struct PartColl *pc = &m->partColl[pi];
+            const struct RigidColl *c = &m->rigidColl[k];
+            const RigidBody *rb = &m->rbs[c->body];
+            for (unsigned i = pc->offset; i < pc->offset + pc->count; i++) {
+                const vec3 xw = m->x[i];
+                if (xw.v[0] < c->lo[0] || xw.v[1] < c->lo[1] || xw.v[2] < c->lo[2] || xw.v[0] > c->hi[0] || xw.v[1] > c->hi[1] || xw.v[2] > c->hi[2]) continue;
+                const vec3 d = vsub(xw, rb->x);
+                vec3 xl, cp, nl; real dist;
+                for (int r = 0; r < 3; r++) xl.v[r] = c->Rm[3 * r] * d.v[0] + c->Rm[3 * r + 1] * d.v[1] + c->Rm[3 * r + 2] * d.v[2] + c->v1[r];
+                if (!coll_test(c, xl, m->contactTolerance, &cp, &nl, &dist)) continue;
+                if (m->nContacts == m->capContacts) { m->capContacts = m->capContacts ? 2 * m->capContacts : 256; m->contacts = (struct Contact *)realloc(m->contacts, (size_t)m->capContacts * sizeof(struct Contact)); }
+                struct Contact *ct = &m->contacts[m->nContacts++];
+                ct->particle = i; ct->body = c->body; ct->cp0 = xw; ct->sum = R(0.0); ct->stiffness = m->contactStiffness; ct->friction = pc->friction + c->friction;
+                for (int r = 0; r < 3; r++) {  /* cp_w = R^T cp + v2, n_w = R^T n */
+                    ct->cp1.v[r] = c->Rm[r] * cp.v[0] + c->Rm[3 + r] * cp.v[1] + c->Rm[6 + r] * cp.v[2] + c->v2[r];
+                    ct->n.v[r] = c->Rm[r] * nl.v[0] + c->Rm[3 + r] * nl.v[1] + c->Rm[6 + r] * nl.v[2];
+                }
+                const real restitution = pc->restitution * c->restitution, invMass0 = m->invMass[i];
+                const vec3 r1 = vsub(ct->cp1, rb->x);
+                const vec3 u1 = vadd(rb->v, vcross(rb->omega, r1));
+                const vec3 urel = vsub(m->v[i], u1);
+                const real urn = vdot(ct->n, urel);
+                ct->t = vsub(urel, vmul(ct->n, urn));
+                const real tl2 = vsq(ct->t);
+                if (tl2 > R(1.0e-6)) ct->t = vmul(ct->t, R(1.0) / RSQRT(tl2));
+                /* computeMatrixK of a static body is zero: K = invMass0 * I */
+                const real kd = (invMass0 != R(0.0)) ? invMass0 : R(0.0);
+                ct->nKnInv = R(1.0) / (kd * vsq(ct->n));
+                ct->pMax = R(1.0) / (kd * vsq(ct->t)) * vdot(urel, ct->t);
+                ct->goal = (urn < R(0.0)) ? -restitution * urn : R(0.0);
+            }
+        }
+}
+/* TimeStepController::velocityConstraintProjection (TimeStepController.cpp:298-357; the particle constraints' velocity hooks are no-ops) over the
+ * contact list + velocitySolve_ParticleRigidBodyContactConstraint (PositionBasedRigidBodyDynamics.cpp:2454-2537) */
+static void contact_velocity_projection(Model *m) {
+    for (unsigned it = 0; it < m->maxIterV; it++)
+        for (unsigned k = 0; k < m->nContacts; k++) {
+            struct Contact *ct = &m->contacts[k];
+            const unsigned i = ct->particle;
+            const RigidBody *rb = &m->rbs[ct->body];
+            const real invMass0 = m->invMass[i];
+            if (invMass0 == R(0.0) && rb->invMass == R(0.0)) continue;
+            const real d = vdot(ct->n, vsub(ct->cp0, ct->cp1));
+            const vec3 r1 = vsub(ct->cp1, rb->x);
+            const vec3 u1 = vadd(rb->v, vcross(rb->omega, r1));
+            const vec3 urel = vsub(m->v[i], u1);
+            const real urn = vdot(urel, ct->n);
+            real mag = ct->nKnInv * (ct->goal - urn);
+            if (mag < -ct->sum) mag = -ct->sum;
+            if (d < R(0.0)) mag -= ct->stiffness * ct->nKnInv * d;
+            vec3 p = vmul(ct->n, mag);
+            ct->sum += mag;
+            const real pn = vdot(p, ct->n);
+            if (ct->friction * pn > ct->pMax) p = vsub(p, vmul(ct->t, ct->pMax));
+            else if (ct->friction * pn < -ct->pMax) p = vadd(p, vmul(ct->t, ct->pMax));
+            else p = vsub(p, vmul(ct->t, ct->friction * pn));
+            if (m->mass[i] != R(0.0)) m->v[i] = vadd(m->v[i], vmul(p, invMass0));
+        }
+}
+
 /* TimeStepController::step, TimeStepController.cpp:75-241, particle part only
  * (no rigid bodies / orientations / collision detection; velocity constraints are no-ops for particle constraints) */
 static void step_once(Model *m) {
@@ -1652,7 +1796,41 @@ static void step_once(Model *m) {
             }
         }
     }
+    if (m->nRigidColl && m->nPartColl) { contact_detection(m); contact_velocity_projection(m); } /* TimeStepController.cpp:189-196 */
     m->time += hOld; /* TimeStepController.cpp:239 */
+}
+
+/* colliders in the layout of oracle/ref_driver's ref_collision_object_info (what an adapter hands to pbd_set_colliders): models = 4 doubles
+ * each (offset, count, restitution, friction), rigid = 30 doubles each */
+void orc_set_colliders(unsigned nModels, const double *models, unsigned nRigid, const double *rigid) {
+    Model *m = G;
+    m->partColl = (struct PartColl *)realloc(m->partColl, (size_t)(nModels ? nModels : 1) * sizeof(struct PartColl)); m->nPartColl = nModels;
+    m->rigidColl = (struct RigidColl *)realloc(m->rigidColl, (size_t)(nRigid ? nRigid : 1) * sizeof(struct RigidColl)); m->nRigidColl = nRigid;
+    for (unsigned i = 0; i < nModels; i++) {
+        struct PartColl *p = &m->partColl[i];
+        p->offset = (unsigned)models[4 * i]; p->count = (unsigned)models[4 * i + 1]; p->restitution = (real)models[4 * i + 2]; p->friction = (real)models[4 * i + 3];
+    }
+    for (unsigned i = 0; i < nRigid; i++) {
+        const double *d = rigid + 30 * (size_t)i;
+        struct RigidColl *c = &m->rigidColl[i];
+        c->shape = (int)d[0]; c->body = (unsigned)d[1];
+        for (int k = 0; k < 3; k++) c->dim[k] = (double)(real)d[2 + k];  /* the reference stores the dimensions in Real */
+        c->thickness = (double)(real)d[5]; c->invert = d[6] != 0.0 ? -1.0 : 1.0; c->restitution = (real)d[7]; c->friction = (real)d[8];
+        for (int k = 0; k < 9; k++) c->Rm[k] = (real)d[9 + k];
+        for (int k = 0; k < 3; k++) { c->v1[k] = (real)d[18 + k]; c->v2[k] = (real)d[21 + k]; c->lo[k] = (real)d[24 + k]; c->hi[k] = (real)d[27 + k]; }
+    }
+}
+void orc_set_contact_params(double tolerance, double stiffness, unsigned maxIterV) {
+    G->contactTolerance = (real)tolerance; G->contactStiffness = (real)stiffness; G->maxIterV = maxIterV;
+}
+unsigned orc_num_contacts(void) { return G->nContacts; }
+void orc_get_contacts(unsigned *particle, unsigned *body, double *out) { /* 10 doubles per contact: cp0 | cp1 | n | 1/(n^T K n) */
+    for (unsigned i = 0; i < G->nContacts; i++) {
+        const struct Contact *c = &G->contacts[i];
+        particle[i] = c->particle; body[i] = c->body;
+        for (int k = 0; k < 3; k++) { out[10 * i + k] = c->cp0.v[k]; out[10 * i + 3 + k] = c->cp1.v[k]; out[10 * i + 6 + k] = c->n.v[k]; }
+        out[10 * i + 9] = c->nKnInv;
+    }
 }
 
 double orc_step(int n) {

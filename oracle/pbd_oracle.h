@@ -93,6 +93,12 @@ void orc_tet_get_tets(unsigned tm, unsigned *out);
 int orc_get_constraint(unsigned i, unsigned *bodies, double *p, double *lambda);
 void orc_get_constraints(int *types, unsigned *bodies, double *params, int *nbodies);
 
+/* contact path (static analytic colliders): objects as an adapter hands them to pbd_set_colliders (see pbd_oracle.c) */
+void orc_set_colliders(unsigned nModels, const double *models, unsigned nRigid, const double *rigid);
+void orc_set_contact_params(double tolerance, double stiffness, unsigned maxIterV);
+unsigned orc_num_contacts(void);
+void orc_get_contacts(unsigned *particle, unsigned *body, double *out);
+
 double orc_step(int n);
 double orc_time(void);
 

@@ -187,6 +187,24 @@ class CpuPbd:
             else: raise RuntimeError("collision object %d is of a kind the contact path does not cover" % i)
         return models, rigid
 
+    # -- contact path of the C restatement: colliders handed over the way an adapter hands them to pbd_set_colliders
+    def set_colliders(self, models, rigid):
+        """oracle only: `models` = [(offset, count, restitution, friction)], `rigid` = 30 doubles per collider (collision_objects() of a reference build)."""
+        assert self.kind == "oracle"
+        mo = _f64(np.asarray(models, dtype=np.float64).reshape(-1, 4)); ri = _f64(np.asarray(rigid, dtype=np.float64).reshape(-1, 30))
+        self.lib.orc_set_colliders(len(mo), _dp(mo), len(ri), _dp(ri))
+
+    def set_oracle_contact_params(self, tolerance=0.01, stiffness=100.0, max_iter_v=5):
+        assert self.kind == "oracle"
+        self.lib.orc_set_contact_params(_D(tolerance), _D(stiffness), int(max_iter_v))
+
+    def oracle_contacts(self):
+        self.lib.orc_num_contacts.restype = C.c_uint
+        n = self.lib.orc_num_contacts()
+        particle = np.zeros(max(n, 1), dtype=np.uint32); body = np.zeros(max(n, 1), dtype=np.uint32); info = np.zeros((max(n, 1), 10))
+        self.lib.orc_get_contacts(particle.ctypes.data_as(C.c_void_p), body.ctypes.data_as(C.c_void_p), _dp(info))
+        return particle[:n], body[:n], info[:n]
+
     def add_ball_joint(self, rb0, rb1, pos):
         return self.add_constraint(BALLJOINT, [rb0, rb1], list(pos))
 
