@@ -338,6 +338,9 @@ class TimeStepController:
             self._ts.sync(); Timing._record(self._ts.stats().last_step_ms)
 
 
+from .loaders import TetGenLoader, OBJLoader, MeshFaceIndices, VertexData  # Utilities::TetGenLoader / OBJLoader under their pyPBD names
+
+
 class CollisionObject:
     RigidBodyCollisionObjectType, TriangleModelCollisionObjectType, TetModelCollisionObjectType = 0, 1, 2
 
